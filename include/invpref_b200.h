@@ -1,0 +1,178 @@
+/*
+ * invpref_b200.h -- C ABI of the B200-native InvPref hot path (libinvpref_b200.so).
+ *
+ * The reference (AIflowerQ/InvPref_KDD_2022) has no FFI layer: its boundary is the Python
+ * API of models.py / train.py, whose arithmetic is stock ATen.  This library replaces that
+ * arithmetic for the train step and the EM environment re-assignment; every entry point
+ * names the reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the name ends in _host.  The caller owns every
+ *    buffer; the library allocates nothing persistent and frees nothing.
+ *  - Tables are fp32, row-major, contiguous [rows, dim]; ids / envs are int64 (the reference
+ *    uses LongTensor, train.py:708-713); scores / weights are fp32.
+ *  - Every call is asynchronous on the given cudaStream_t (passed as void*) and never
+ *    synchronises the device.  Return value: 0 = ok, negative = invpref_status.
+ *  - There is no CPU fallback: a build without a usable GPU fails at launch with a CUDA error.
+ */
+#ifndef INVPREF_B200_H
+#define INVPREF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define INVPREF_ABI_VERSION 1
+#define INVPREF_MAX_ENVS 8      /* drivers use K = 2, 4, 5, 6 */
+#define INVPREF_MAX_DIM 256     /* drivers use D = 30, 40; synthetic config D = 64 */
+#define INVPREF_NUM_LOSSES 6    /* train.py:836-843: invariant, env_aware, envs, L2, L1, loss */
+
+typedef enum {
+    INVPREF_OK = 0,
+    INVPREF_ERR_BAD_DIM = -1,        /* dim not in [1, INVPREF_MAX_DIM] or unsupported parity */
+    INVPREF_ERR_BAD_ENVS = -2,       /* n_envs not in [1, INVPREF_MAX_ENVS] */
+    INVPREF_ERR_BAD_ARG = -3,        /* null pointer / negative size / table too large */
+    INVPREF_ERR_MISALIGNED = -4,     /* table base pointer not aligned for the vector width */
+    INVPREF_ERR_WORKSPACE = -5,      /* workspace / plan buffer too small */
+    INVPREF_ERR_CUDA = -6,           /* cudaGetLastError() != cudaSuccess after a launch */
+    INVPREF_ERR_ID_RANGE = -7        /* (debug check) id outside its table */
+} invpref_status;
+
+/* models.py:415-446 / 273-305: model shape and variant flags. */
+typedef struct {
+    int64_t n_users;
+    int64_t n_items;
+    int32_t n_envs;          /* K */
+    int32_t dim;             /* D = factor_num */
+    int32_t implicit;        /* 0: InvPrefExplicit (MSE), 1: InvPrefImplicit (sigmoid + BCE) */
+    int32_t reg_only_embed;  /* models.py:507-511 */
+    int32_t reg_env_embed;   /* models.py:516-517 */
+    int32_t _pad;
+} invpref_desc;
+
+/* The seven parameter tensors, in model.parameters() order (models.py:424-432). */
+typedef struct {
+    float* Uinv;  /* embed_user_invariant.weight  [n_users, D] */
+    float* Iinv;  /* embed_item_invariant.weight  [n_items, D] */
+    float* Uenv;  /* embed_user_env_aware.weight  [n_users, D] */
+    float* Ienv;  /* embed_item_env_aware.weight  [n_items, D] */
+    float* E;     /* embed_env.weight             [K, D] */
+    float* W;     /* env_classifier.linear_map.weight [K, D] */
+    float* b;     /* env_classifier.linear_map.bias   [K] */
+} invpref_params;
+
+/* torch.optim.Adam state (exp_avg, exp_avg_sq) for the same seven tensors (train.py:718). */
+typedef struct {
+    invpref_params m;
+    invpref_params v;
+} invpref_adam;
+
+/* One mini-batch = rows [s*B, (s+1)*B) of the training tensors (utils.py:12-19). */
+typedef struct {
+    const int64_t* users;
+    const int64_t* items;
+    const int64_t* envs;
+    const float* scores;
+    const float* weights;   /* sample_weights slice (train.py:956); may be NULL if both re-weights are off */
+    int64_t B;
+} invpref_batch;
+
+/* Loss coefficients (train.py:829-830), gradient-reversal alpha (functions.py:13-16) and
+ * Adam settings.  bias corrections are derived from `step` in double, as torch does. */
+typedef struct {
+    double c_inv, c_ea, c_env, c_L2, c_L1;
+    double alpha;
+    double lr, beta1, beta2, eps;
+    int64_t step;            /* 1-based Adam step of THIS update */
+    int32_t use_class_rw;    /* train.py:814-815 */
+    int32_t use_rec_rw;      /* train.py:817-819 */
+} invpref_hyper;
+
+const char* invpref_strerror(int status);
+int invpref_abi_version(void);
+
+/* ---- sizes -------------------------------------------------------------------------- */
+
+/* Bytes of scratch a call on a batch of at most max_batch rows needs (plan building, train
+ * step, backward).  The scratch holds nothing across calls. */
+int invpref_workspace_bytes(const invpref_desc* desc, int64_t max_batch, size_t* out_bytes);
+
+/* Bytes of one batch plan (both sort orders, see invpref_build_plan). */
+int invpref_plan_bytes(const invpref_desc* desc, int64_t max_batch, size_t* out_bytes);
+
+/* ---- sort-segment plan ------------------------------------------------------------------
+ * Replaces the duplicate handling of embedding_dense_backward (autograd of models.py:449-455):
+ * a STABLE sort of the batch by user id and by item id, unique rows and segment offsets, the
+ * split of long segments into fixed chunks, and a bitmap of touched rows.  A plan depends only
+ * on (users, items) of the batch, which utils.mini_batch keeps fixed across epochs, so a
+ * trainer builds it once per batch and reuses it. */
+int invpref_build_plan(const invpref_desc* desc, const int64_t* users, const int64_t* items, int64_t B,
+                       void* plan, size_t plan_bytes, void* ws, size_t ws_bytes, void* stream);
+
+/* Stand-alone segment builder with int64 outputs, for callers/tests that want the raw result:
+ * perm is bit-equal to torch.sort(ids, stable=True).indices; seg_row[0..n_seg) are the unique
+ * ids ascending; seg_off[0..n_seg] the offsets into perm.  n_seg is a device int64. */
+int invpref_build_segments(const int64_t* ids, int64_t B, int64_t n_rows, int64_t* perm, int64_t* seg_row,
+                           int64_t* seg_off, int64_t* n_seg, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- forward ------------------------------------------------------------------------------
+ * models.py:448-467 (explicit) / 307-326 (implicit), incl. the classifier models.py:206-209.
+ * Any of s_inv / s_env / logp may be NULL.  logp is [B, K]. */
+int invpref_forward(const invpref_desc* desc, const invpref_params* params, const int64_t* users,
+                    const int64_t* items, const int64_t* envs, int64_t B, float* s_inv, float* s_env,
+                    float* logp, void* stream);
+
+/* models.py:534-539: explicit predict = invariant score only (envs not needed). */
+int invpref_predict(const invpref_desc* desc, const invpref_params* params, const int64_t* users,
+                    const int64_t* items, int64_t B, float* score, void* stream);
+
+/* Autograd backward of invpref_forward (what loss.backward() does through models.py:448-467 and
+ * functions.py:13-16): given upstream gradients of s_inv, s_env, logp (any may be NULL) it
+ * ACCUMULATES (+=) dense gradients into `grads` (same layout as params).  Deterministic. */
+int invpref_backward(const invpref_desc* desc, const invpref_params* params, const invpref_batch* batch,
+                     double alpha, const float* g_s_inv, const float* g_s_env, const float* g_logp,
+                     const void* plan, invpref_params* grads, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused train step -------------------------------------------------------------------------
+ * train.py:771-844 in one call: forward, the five loss terms, closed-form backward (SURVEY.md
+ * §3.4), dense torch.optim.Adam update of all seven tensors.  The four embedding tables are
+ * double-buffered: rows are read from params_in and the updated rows written to params_out
+ * (params_out->{Uinv,Iinv,Uenv,Ienv} must not alias params_in; E/W/b may alias and are updated
+ * last).  The caller swaps the two sets after the call.  Adam state is updated in place.
+ * loss_out: 6 device floats in the order of train.py:836-843.
+ * If `grads_out` is non-NULL the dense gradients are ALSO written there (testing aid; moves
+ * extra bytes).  plan may be NULL: the step then builds a plan in the workspace first. */
+int invpref_train_step(const invpref_desc* desc, const invpref_params* params_in, invpref_params* params_out,
+                       invpref_adam* adam, const invpref_batch* batch, const invpref_hyper* hyper,
+                       const void* plan, float* loss_out, invpref_params* grads_out, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* ---- EM environment re-assignment ---------------------------------------------------------------
+ * train.py:846-879 for a whole slice at once: each sample's loss under all K environments,
+ * optional tie-break perturbation eps_table[perm_idx[n]] (train.py:868-873; perm_idx is the
+ * host-drawn np.random.randint, NULL = cluster_use_random_sort off), first-min argmin.
+ * new_envs: int64 [B].  hist (int64[K], nullable) and diff (int64, nullable; counts
+ * new != old_envs, train.py:933-934) are ACCUMULATED into; zero them first. */
+int invpref_cluster(const invpref_desc* desc, const invpref_params* params, const int64_t* users,
+                    const int64_t* items, const float* scores, const int64_t* perm_idx, const float* eps_table,
+                    const int64_t* old_envs, int64_t B, int64_t* new_envs, int64_t* hist, int64_t* diff,
+                    void* stream);
+
+/* train.py:945-957: class_weights[k] = min(cnt_k + 1, N - 1) / N (double -> fp32) from a finished
+ * histogram, and sample_weights[n] = class_weights[envs[n]]. */
+int invpref_stat_envs(const int64_t* envs, int64_t N, int32_t n_envs, const int64_t* hist, float* class_weights,
+                      float* sample_weights, void* stream);
+
+/* Histogram of envs (train.py:949), accumulated into hist (int64[K]). */
+int invpref_env_hist(const int64_t* envs, int64_t N, int32_t n_envs, int64_t* hist, void* stream);
+
+/* Number of kernels the library has launched in this process (bench.py's gpu_launches). */
+int64_t invpref_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* INVPREF_B200_H */

@@ -1,0 +1,330 @@
+// extern "C" entry points of libinvpref_b200.so (see include/invpref_b200.h).
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace invpref {
+long long g_launch_count = 0;
+
+namespace {
+
+inline bool aligned_for(const void* p, int vec) { return ((uintptr_t)p % (size_t)(vec * 4)) == 0; }
+
+int check_tables(const Geometry& g, const invpref_params* p) {
+    if (!p || !p->Uinv || !p->Iinv || !p->Uenv || !p->Ienv || !p->E || !p->W || !p->b) return INVPREF_ERR_BAD_ARG;
+    if (!aligned_for(p->Uinv, g.VEC) || !aligned_for(p->Iinv, g.VEC) || !aligned_for(p->Uenv, g.VEC) ||
+        !aligned_for(p->Ienv, g.VEC))
+        return INVPREF_ERR_MISALIGNED;
+    return INVPREF_OK;
+}
+
+AdamScalars make_adam(const invpref_hyper* h) {
+    // torch/optim/adam.py (_single_tensor_adam): python-float bias corrections from the int step
+    AdamScalars s;
+    const double bc1 = 1.0 - pow(h->beta1, (double)h->step);
+    const double bc2 = 1.0 - pow(h->beta2, (double)h->step);
+    s.one_minus_b1 = (float)(1.0 - h->beta1);
+    s.b2 = (float)h->beta2;
+    s.one_minus_b2 = (float)(1.0 - h->beta2);
+    s.step_size = (float)(h->lr / bc1);
+    s.bc2_sqrt = (float)sqrt(bc2);
+    s.eps = (float)h->eps;
+    return s;
+}
+
+void carve_plan(const invpref_desc* d, int64_t B, char* plan, PlanSide* pu, PlanSide* pi) {
+    int64_t Bp = B > 0 ? B : 1;
+    *pu = carve_plan_side(plan, Bp, d->n_users);
+    *pi = carve_plan_side(plan + plan_side_bytes(Bp, d->n_users), Bp, d->n_items);
+    pu->B = B;
+    pi->B = B;
+}
+
+int build_plan_impl(const invpref_desc* d, const int64_t* users, const int64_t* items, int64_t B, char* plan,
+                    char* tmp, size_t tmp_bytes, cudaStream_t st) {
+    PlanSide pu, pi;
+    carve_plan(d, B, plan, &pu, &pi);
+    int rc = build_plan_side(users, items, d->n_items, pu, tmp, tmp_bytes, st);
+    if (rc != INVPREF_OK) return rc;
+    return build_plan_side(items, users, d->n_users, pi, tmp, tmp_bytes, st);
+}
+
+}  // namespace
+}  // namespace invpref
+
+using namespace invpref;
+
+extern "C" {
+
+const char* invpref_strerror(int status) {
+    switch (status) {
+        case INVPREF_OK: return "ok";
+        case INVPREF_ERR_BAD_DIM: return "unsupported embedding dimension";
+        case INVPREF_ERR_BAD_ENVS: return "unsupported number of environments";
+        case INVPREF_ERR_BAD_ARG: return "bad argument (null pointer, negative size or table too large)";
+        case INVPREF_ERR_MISALIGNED: return "table pointer not aligned for the vector width of this dimension";
+        case INVPREF_ERR_WORKSPACE: return "workspace or plan buffer too small";
+        case INVPREF_ERR_CUDA: return "CUDA error at kernel launch";
+        case INVPREF_ERR_ID_RANGE: return "id outside its table";
+        default: return "unknown status";
+    }
+}
+
+int invpref_abi_version(void) { return INVPREF_ABI_VERSION; }
+
+int64_t invpref_launch_count(void) { return (int64_t)g_launch_count; }
+
+int invpref_workspace_bytes(const invpref_desc* desc, int64_t max_batch, size_t* out_bytes) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if (max_batch < 0 || max_batch > 0x7fffffffLL || !out_bytes) return INVPREF_ERR_BAD_ARG;
+    *out_bytes = workspace_bytes_impl(desc, g, max_batch, nullptr, nullptr);
+    return INVPREF_OK;
+}
+
+int invpref_plan_bytes(const invpref_desc* desc, int64_t max_batch, size_t* out_bytes) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if (max_batch < 0 || max_batch > 0x7fffffffLL || !out_bytes) return INVPREF_ERR_BAD_ARG;
+    int64_t Bp = max_batch > 0 ? max_batch : 1;
+    *out_bytes = plan_side_bytes(Bp, desc->n_users) + plan_side_bytes(Bp, desc->n_items);
+    return INVPREF_OK;
+}
+
+int invpref_build_plan(const invpref_desc* desc, const int64_t* users, const int64_t* items, int64_t B, void* plan,
+                       size_t plan_bytes, void* ws, size_t ws_bytes, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if (B < 0 || B > 0x7fffffffLL || !plan || !ws || (B > 0 && (!users || !items))) return INVPREF_ERR_BAD_ARG;
+    size_t need = 0;
+    invpref_plan_bytes(desc, B, &need);
+    if (plan_bytes < need) return INVPREF_ERR_WORKSPACE;
+    Workspace w;
+    if (ws_bytes < workspace_bytes_impl(desc, g, B, &w, (char*)ws)) return INVPREF_ERR_WORKSPACE;
+    return build_plan_impl(desc, users, items, B, (char*)plan, w.sort_tmp, w.sort_tmp_bytes, (cudaStream_t)stream);
+}
+
+int invpref_build_segments(const int64_t* ids, int64_t B, int64_t n_rows, int64_t* perm, int64_t* seg_row,
+                           int64_t* seg_off, int64_t* n_seg, void* ws, size_t ws_bytes, void* stream) {
+    if (B < 0 || B > 0x7fffffffLL || n_rows < 1 || n_rows > 0x7fffffffLL || !ws || !seg_off || !n_seg ||
+        (B > 0 && (!ids || !perm || !seg_row)))
+        return INVPREF_ERR_BAD_ARG;
+    return build_segments_i64(ids, B, n_rows, perm, seg_row, seg_off, n_seg, (char*)ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int invpref_forward(const invpref_desc* desc, const invpref_params* params, const int64_t* users, const int64_t* items,
+                    const int64_t* envs, int64_t B, float* s_inv, float* s_env, float* logp, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, params)) != INVPREF_OK) return rc;
+    if (B < 0 || (B > 0 && (!users || !items || !envs))) return INVPREF_ERR_BAD_ARG;
+    if (B == 0) return INVPREF_OK;
+    FwdOnlyArgs a;
+    a.Uinv = params->Uinv; a.Iinv = params->Iinv; a.Uenv = params->Uenv; a.Ienv = params->Ienv;
+    a.E = params->E; a.W = params->W; a.b = params->b;
+    a.users = users; a.items = items; a.envs = envs; a.B = B;
+    a.D = g.D; a.K = g.K; a.implicit = desc->implicit;
+    a.s_inv = s_inv; a.s_env = s_env; a.logp = logp;
+    return launch_fwd_only(g, a, (cudaStream_t)stream);
+}
+
+int invpref_predict(const invpref_desc* desc, const invpref_params* params, const int64_t* users, const int64_t* items,
+                    int64_t B, float* score, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, params)) != INVPREF_OK) return rc;
+    if (B < 0 || (B > 0 && (!users || !items || !score))) return INVPREF_ERR_BAD_ARG;
+    if (B == 0) return INVPREF_OK;
+    return launch_predict(g, params->Uinv, params->Iinv, users, items, B, score, (cudaStream_t)stream);
+}
+
+static void fill_side(BwdSideArgs* s, const Geometry& g, const float* gpack, const float* E, const float* W) {
+    s->gpack = gpack; s->E = E; s->W = W; s->D = g.D; s->K = g.K; s->GS = g.GS;
+}
+
+int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invpref_params* pout, invpref_adam* adam,
+                       const invpref_batch* batch, const invpref_hyper* hyper, const void* plan, float* loss_out,
+                       invpref_params* grads_out, void* ws, size_t ws_bytes, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, pin)) != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, pout)) != INVPREF_OK) return rc;
+    if (!adam || !batch || !hyper || !ws) return INVPREF_ERR_BAD_ARG;
+    if ((rc = check_tables(g, &adam->m)) != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, &adam->v)) != INVPREF_OK) return rc;
+    if (grads_out && (rc = check_tables(g, grads_out)) != INVPREF_OK) return rc;
+    const int64_t B = batch->B;
+    if (B < 1 || B > 0x7fffffffLL || !batch->users || !batch->items || !batch->envs || !batch->scores)
+        return INVPREF_ERR_BAD_ARG;
+    if ((hyper->use_class_rw || hyper->use_rec_rw) && !batch->weights) return INVPREF_ERR_BAD_ARG;
+    if (pin->Uinv == pout->Uinv || pin->Iinv == pout->Iinv || pin->Uenv == pout->Uenv || pin->Ienv == pout->Ienv)
+        return INVPREF_ERR_BAD_ARG;   // tables are double-buffered
+    if (hyper->step < 1) return INVPREF_ERR_BAD_ARG;
+    Workspace w;
+    if (ws_bytes < workspace_bytes_impl(desc, g, B, &w, (char*)ws)) return INVPREF_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const char* plan_base = (const char*)plan;
+    if (plan_base == nullptr) {
+        rc = build_plan_impl(desc, batch->users, batch->items, B, w.plan, w.sort_tmp, w.sort_tmp_bytes, st);
+        if (rc != INVPREF_OK) return rc;
+        plan_base = w.plan;
+    }
+    PlanSide pu, pi;
+    carve_plan(desc, B, (char*)plan_base, &pu, &pi);
+
+    // (1)+(2) fused forward, losses, per-interaction gradients, dW/db/dE partials
+    FwdTrainArgs f;
+    f.Uinv = pin->Uinv; f.Iinv = pin->Iinv; f.Uenv = pin->Uenv; f.Ienv = pin->Ienv;
+    f.E = pin->E; f.W = pin->W; f.b = pin->b;
+    f.users = batch->users; f.items = batch->items; f.envs = batch->envs;
+    f.scores = batch->scores; f.weights = batch->weights; f.B = B;
+    f.D = g.D; f.K = g.K; f.GS = g.GS;
+    f.implicit = desc->implicit; f.reg_env_embed = desc->reg_env_embed;
+    f.use_class_rw = hyper->use_class_rw; f.use_rec_rw = hyper->use_rec_rw;
+    f.c_inv = (float)hyper->c_inv; f.c_ea = (float)hyper->c_ea; f.c_env = (float)hyper->c_env;
+    f.neg_alpha = (float)(-hyper->alpha); f.invB = 1.f / (float)B;
+    f.gpack = w.gpack; f.partials = w.partials; f.P = fwd_partial_floats(g);
+    f.up_s_inv = f.up_s_env = f.up_logp = nullptr; f.generic = 0;
+    const int fgrid = fwd_train_grid(B);
+    if ((rc = launch_fwd_train(g, f, fgrid, st)) != INVPREF_OK) return rc;
+
+    // (3)+(4) segmented backward feeding Adam, per side
+    const AdamScalars as = make_adam(hyper);
+    const double bd2 = (double)B * g.D * 2.0;
+    BwdSideArgs su, si;
+    fill_side(&su, g, w.gpack, pin->E, pin->W);
+    su.own_inv_in = pin->Uinv; su.own_env_in = pin->Uenv; su.own_inv_out = pout->Uinv; su.own_env_out = pout->Uenv;
+    su.m_inv = adam->m.Uinv; su.m_env = adam->m.Uenv; su.v_inv = adam->v.Uinv; su.v_env = adam->v.Uenv;
+    su.partner_inv = pin->Iinv; su.partner_env = pin->Ienv;
+    su.grad_inv = grads_out ? grads_out->Uinv : nullptr; su.grad_env = grads_out ? grads_out->Uenv : nullptr;
+    su.plan = pu; su.chunk_part = w.chunk_part_u;
+    su.reg2 = (float)(2.0 * hyper->c_L2 / bd2); su.reg1 = (float)(hyper->c_L1 / bd2); su.adam = as;
+    fill_side(&si, g, w.gpack, pin->E, pin->W);
+    si.own_inv_in = pin->Iinv; si.own_env_in = pin->Ienv; si.own_inv_out = pout->Iinv; si.own_env_out = pout->Ienv;
+    si.m_inv = adam->m.Iinv; si.m_env = adam->m.Ienv; si.v_inv = adam->v.Iinv; si.v_env = adam->v.Ienv;
+    si.partner_inv = pin->Uinv; si.partner_env = pin->Uenv;
+    si.grad_inv = grads_out ? grads_out->Iinv : nullptr; si.grad_env = grads_out ? grads_out->Ienv : nullptr;
+    si.plan = pi; si.chunk_part = w.chunk_part_i;
+    si.reg2 = su.reg2; si.reg1 = su.reg1; si.adam = as;
+
+    if ((rc = launch_bwd_chunks(g, si, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_bwd_chunks(g, su, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_bwd_rows(g, si, EPI_ADAM, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_bwd_rows(g, su, EPI_ADAM, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_sweep(g, si, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_sweep(g, su, st)) != INVPREF_OK) return rc;
+
+    // losses, E / W / b gradients and their Adam update
+    TailArgs t;
+    t.partials = w.partials; t.n_partials = fgrid; t.P = f.P; t.B = B; t.D = g.D; t.K = g.K;
+    t.reg_only_embed = desc->reg_only_embed; t.reg_env_embed = desc->reg_env_embed;
+    t.c_inv = (float)hyper->c_inv; t.c_ea = (float)hyper->c_ea; t.c_env = (float)hyper->c_env;
+    t.c_L2 = (float)hyper->c_L2; t.c_L1 = (float)hyper->c_L1;
+    t.E_in = pin->E; t.W_in = pin->W; t.b_in = pin->b;
+    t.E_out = pout->E; t.W_out = pout->W; t.b_out = pout->b;
+    t.mE = adam->m.E; t.mW = adam->m.W; t.mb = adam->m.b; t.vE = adam->v.E; t.vW = adam->v.W; t.vb = adam->v.b;
+    t.gE = grads_out ? grads_out->E : nullptr; t.gW = grads_out ? grads_out->W : nullptr;
+    t.gb = grads_out ? grads_out->b : nullptr;
+    t.loss_out = loss_out; t.adam = as; t.epi = EPI_ADAM;
+    return launch_tail(t, st);
+}
+
+int invpref_backward(const invpref_desc* desc, const invpref_params* params, const invpref_batch* batch, double alpha,
+                     const float* g_s_inv, const float* g_s_env, const float* g_logp, const void* plan,
+                     invpref_params* grads, void* ws, size_t ws_bytes, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, params)) != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, grads)) != INVPREF_OK) return rc;
+    if (!batch || !ws) return INVPREF_ERR_BAD_ARG;
+    const int64_t B = batch->B;
+    if (B < 0 || B > 0x7fffffffLL) return INVPREF_ERR_BAD_ARG;
+    if (B == 0) return INVPREF_OK;
+    if (!batch->users || !batch->items || !batch->envs) return INVPREF_ERR_BAD_ARG;
+    Workspace w;
+    if (ws_bytes < workspace_bytes_impl(desc, g, B, &w, (char*)ws)) return INVPREF_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* plan_base = (const char*)plan;
+    if (plan_base == nullptr) {
+        rc = build_plan_impl(desc, batch->users, batch->items, B, w.plan, w.sort_tmp, w.sort_tmp_bytes, st);
+        if (rc != INVPREF_OK) return rc;
+        plan_base = w.plan;
+    }
+    PlanSide pu, pi;
+    carve_plan(desc, B, (char*)plan_base, &pu, &pi);
+
+    FwdTrainArgs f;
+    f.Uinv = params->Uinv; f.Iinv = params->Iinv; f.Uenv = params->Uenv; f.Ienv = params->Ienv;
+    f.E = params->E; f.W = params->W; f.b = params->b;
+    f.users = batch->users; f.items = batch->items; f.envs = batch->envs;
+    f.scores = nullptr; f.weights = nullptr; f.B = B;
+    f.D = g.D; f.K = g.K; f.GS = g.GS;
+    f.implicit = desc->implicit; f.reg_env_embed = 0; f.use_class_rw = 0; f.use_rec_rw = 0;
+    f.c_inv = f.c_ea = f.c_env = 0.f; f.neg_alpha = (float)(-alpha); f.invB = 0.f;
+    f.gpack = w.gpack; f.partials = w.partials; f.P = fwd_partial_floats(g);
+    f.up_s_inv = g_s_inv; f.up_s_env = g_s_env; f.up_logp = g_logp; f.generic = 1;
+    const int fgrid = fwd_train_grid(B);
+    if ((rc = launch_fwd_train(g, f, fgrid, st)) != INVPREF_OK) return rc;
+
+    AdamScalars as = {};
+    BwdSideArgs su = {}, si = {};
+    fill_side(&su, g, w.gpack, params->E, params->W);
+    su.partner_inv = params->Iinv; su.partner_env = params->Ienv;
+    su.grad_inv = grads->Uinv; su.grad_env = grads->Uenv; su.plan = pu; su.chunk_part = w.chunk_part_u; su.adam = as;
+    fill_side(&si, g, w.gpack, params->E, params->W);
+    si.partner_inv = params->Uinv; si.partner_env = params->Uenv;
+    si.grad_inv = grads->Iinv; si.grad_env = grads->Ienv; si.plan = pi; si.chunk_part = w.chunk_part_i; si.adam = as;
+    if ((rc = launch_bwd_chunks(g, si, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_bwd_chunks(g, su, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_bwd_rows(g, si, EPI_ACCUM, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_bwd_rows(g, su, EPI_ACCUM, st)) != INVPREF_OK) return rc;
+
+    TailArgs t = {};
+    t.partials = w.partials; t.n_partials = fgrid; t.P = f.P; t.B = B; t.D = g.D; t.K = g.K;
+    t.gE = grads->E; t.gW = grads->W; t.gb = grads->b; t.epi = EPI_ACCUM;
+    return launch_tail(t, st);
+}
+
+int invpref_cluster(const invpref_desc* desc, const invpref_params* params, const int64_t* users, const int64_t* items,
+                    const float* scores, const int64_t* perm_idx, const float* eps_table, const int64_t* old_envs,
+                    int64_t B, int64_t* new_envs, int64_t* hist, int64_t* diff, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, params)) != INVPREF_OK) return rc;
+    if (B < 0 || (B > 0 && (!users || !items || !scores || !new_envs))) return INVPREF_ERR_BAD_ARG;
+    if (perm_idx && !eps_table) return INVPREF_ERR_BAD_ARG;
+    if (diff && !old_envs) return INVPREF_ERR_BAD_ARG;
+    if (B == 0) return INVPREF_OK;
+    ClusterArgs a;
+    a.Uinv = params->Uinv; a.Iinv = params->Iinv; a.Uenv = params->Uenv; a.Ienv = params->Ienv; a.E = params->E;
+    a.users = users; a.items = items; a.scores = scores; a.perm_idx = perm_idx; a.eps_table = eps_table;
+    a.old_envs = old_envs; a.B = B; a.D = g.D; a.K = g.K; a.implicit = desc->implicit;
+    a.new_envs = new_envs; a.hist = (unsigned long long*)hist; a.diff = (unsigned long long*)diff;
+    return launch_cluster(g, a, (cudaStream_t)stream);
+}
+
+int invpref_stat_envs(const int64_t* envs, int64_t N, int32_t n_envs, const int64_t* hist, float* class_weights,
+                      float* sample_weights, void* stream) {
+    if (n_envs < 1 || n_envs > INVPREF_MAX_ENVS) return INVPREF_ERR_BAD_ENVS;
+    if (N < 1 || !hist || (sample_weights && !envs)) return INVPREF_ERR_BAD_ARG;
+    return launch_stat_envs(envs, N, n_envs, hist, class_weights, sample_weights, (cudaStream_t)stream);
+}
+
+int invpref_env_hist(const int64_t* envs, int64_t N, int32_t n_envs, int64_t* hist, void* stream) {
+    if (n_envs < 1 || n_envs > INVPREF_MAX_ENVS) return INVPREF_ERR_BAD_ENVS;
+    if (N < 0 || !hist || (N > 0 && !envs)) return INVPREF_ERR_BAD_ARG;
+    if (N == 0) return INVPREF_OK;
+    return launch_env_hist(envs, N, n_envs, (unsigned long long*)hist, (cudaStream_t)stream);
+}
+
+}  // extern "C"

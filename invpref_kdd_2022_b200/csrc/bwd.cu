@@ -1,0 +1,356 @@
+// Deterministic segmented backward + fused dense Adam.
+//
+// Replaces, for the four embedding tables, ATen's embedding_dense_backward (zero-fill + index_add,
+// 13x per step in the reference: autograd of models.py:449-455 and of the re-gathers in
+// models.py:469-532), the norm backward (2x / sign(x)) and torch.optim.Adam.step (train.py:832-834).
+//
+//  bwd_chunks_kernel : pre-reduces CHUNK-sized pieces of long segments (hot items) into partials.
+//  bwd_rows_kernel   : one 16-lane group per touched row: sums its segment (or its chunk partials) in
+//                      the fixed sorted order -- no atomics -- adds the L1/L2 term of the row, and
+//                      applies Adam in registers; the gradient table is never materialised.
+//  sweep_kernel      : dense Adam for every row WITHOUT a segment (g = 0: momentum still moves it),
+//                      a pure stream over theta, m, v.
+//  tail_kernel       : fixed-order sum of the forward kernel's per-CTA partials -> the six loss
+//                      scalars (train.py:836-843), gradients of E / W / b and their Adam update.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace invpref {
+
+namespace {
+
+// Sum over sorted positions [beg, end) of this side's per-interaction gradient contributions:
+//   acc_inv += (g_z1 + sum_k (-alpha g_logits[k]) W[k, d]) * partner_inv[d]      (g_p (.) partner)
+//   acc_env += g_z2 * partner_env[d] * E[e, d]
+template <int VEC, int NV>
+__device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const float* __restrict__ sE,
+                                                 const float* __restrict__ sW, int beg, int end, int lane,
+                                                 float* acc_inv, float* acc_env) {
+    const int D = a.D, K = a.K, GS = a.GS;
+    const int32_t* __restrict__ perm = a.plan.perm;
+    const int32_t* __restrict__ partner = a.plan.partner;
+#pragma unroll 2
+    for (int k = beg; k < end; ++k) {
+        const int n = perm[k];
+        const int pid = partner[k];
+        const float4* gp = reinterpret_cast<const float4*>(a.gpack + (int64_t)n * GS);
+        float g[12];
+        float4 q0 = gp[0], q1 = gp[1];
+        g[0] = q0.x; g[1] = q0.y; g[2] = q0.z; g[3] = q0.w;
+        g[4] = q1.x; g[5] = q1.y; g[6] = q1.z; g[7] = q1.w;
+        if (GS > 8) {
+            float4 q2 = gp[2];
+            g[8] = q2.x; g[9] = q2.y; g[10] = q2.z; g[11] = q2.w;
+        } else {
+            g[8] = g[9] = g[10] = g[11] = 0.f;
+        }
+        Row<VEC, NV> pc, pe;
+        load_row<VEC, NV>(pc, a.partner_inv, pid, D, lane);
+        load_row<VEC, NV>(pe, a.partner_env, pid, D, lane);
+        const float g_z1 = g[0], g_z2 = g[1];
+        const int e = __float_as_int(g[2]);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int d0 = dim_of<VEC>(lane, j);
+            if (d0 < D) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const int x = j * VEC + v;
+                    float gpd = g_z1;
+#pragma unroll
+                    for (int kk = 0; kk < INVPREF_MAX_ENVS; ++kk)
+                        if (kk < K) gpd += g[3 + kk] * sW[kk * D + d0 + v];
+                    acc_inv[x] += gpd * pc.x[x];
+                    acc_env[x] += g_z2 * pe.x[x] * sE[e * D + d0 + v];
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_EW(const BwdSideArgs& a, float* sE, float* sW) {
+    for (int t = threadIdx.x; t < a.K * a.D; t += blockDim.x) {
+        sE[t] = a.E[t];
+        sW[t] = a.W[t];
+    }
+    __syncthreads();
+}
+
+template <int VEC, int NV>
+__global__ void __launch_bounds__(BLOCK) bwd_chunks_kernel(BwdSideArgs a) {
+    extern __shared__ float smem[];
+    float* sE = smem;
+    float* sW = smem + a.K * a.D;
+    stage_EW(a, sE, sW);
+    const int lane = threadIdx.x & (GROUP - 1);
+    const int n_chunks = a.plan.counters[1];
+    const int ngroups = gridDim.x * GROUPS_PER_BLOCK;
+    for (int c = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4); c < n_chunks; c += ngroups) {
+        const int4 desc = reinterpret_cast<const int4*>(a.plan.chunk_desc)[c];
+        Row<VEC, NV> ai, ae;
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) { ai.x[x] = 0.f; ae.x[x] = 0.f; }
+        accumulate_range<VEC, NV>(a, sE, sW, desc.y, desc.z, lane, ai.x, ae.x);
+        store_row<VEC, NV>(ai, a.chunk_part, (int64_t)c * 2, a.D, lane);
+        store_row<VEC, NV>(ae, a.chunk_part, (int64_t)c * 2 + 1, a.D, lane);
+    }
+}
+
+template <int VEC, int NV, int EPI>
+__global__ void __launch_bounds__(BLOCK) bwd_rows_kernel(BwdSideArgs a) {
+    extern __shared__ float smem[];
+    float* sE = smem;
+    float* sW = smem + a.K * a.D;
+    stage_EW(a, sE, sW);
+    const int D = a.D;
+    const int lane = threadIdx.x & (GROUP - 1);
+    const int n_seg = a.plan.counters[0];
+    const int ngroups = gridDim.x * GROUPS_PER_BLOCK;
+    for (int s = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4); s < n_seg; s += ngroups) {
+        const int64_t row = a.plan.seg_row[s];
+        const int beg = a.plan.seg_off[s], end = a.plan.seg_off[s + 1];
+        const int c0 = a.plan.seg_chunk[s], c1 = a.plan.seg_chunk[s + 1];
+        Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
+        if (EPI == EPI_ADAM) {
+            load_row<VEC, NV>(th_i, a.own_inv_in, row, D, lane);
+            load_row<VEC, NV>(th_e, a.own_env_in, row, D, lane);
+            load_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+            load_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+            load_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+            load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
+        }
+        Row<VEC, NV> gi, ge;
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
+        if (c1 > c0) {
+            for (int c = c0; c < c1; ++c) {
+                Row<VEC, NV> pi, pe;
+                load_row<VEC, NV>(pi, a.chunk_part, (int64_t)c * 2, D, lane);
+                load_row<VEC, NV>(pe, a.chunk_part, (int64_t)c * 2 + 1, D, lane);
+#pragma unroll
+                for (int x = 0; x < NV * VEC; ++x) { gi.x[x] += pi.x[x]; ge.x[x] += pe.x[x]; }
+            }
+        } else {
+            accumulate_range<VEC, NV>(a, sE, sW, beg, end, lane, gi.x, ge.x);
+        }
+        if (EPI == EPI_ADAM) {
+            // L1/L2 term of the gathered rows (models.py:469-497): every occurrence counts
+            const float cnt = (float)(end - beg);
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) {
+                gi.x[x] += cnt * (a.reg2 * th_i.x[x] + a.reg1 * signf_(th_i.x[x]));
+                ge.x[x] += cnt * (a.reg2 * th_e.x[x] + a.reg1 * signf_(th_e.x[x]));
+            }
+            if (a.grad_inv != nullptr) {
+                store_row<VEC, NV>(gi, a.grad_inv, row, D, lane);
+                store_row<VEC, NV>(ge, a.grad_env, row, D, lane);
+            }
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) {
+                adam_update(th_i.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.adam);
+                adam_update(th_e.x[x], m_e.x[x], v_e.x[x], ge.x[x], a.adam);
+            }
+            store_row<VEC, NV>(th_i, a.own_inv_out, row, D, lane);
+            store_row<VEC, NV>(th_e, a.own_env_out, row, D, lane);
+            store_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+            store_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+            store_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+            store_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
+        } else {
+            Row<VEC, NV> oi, oe;
+            load_row<VEC, NV>(oi, a.grad_inv, row, D, lane);
+            load_row<VEC, NV>(oe, a.grad_env, row, D, lane);
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) { oi.x[x] += gi.x[x]; oe.x[x] += ge.x[x]; }
+            store_row<VEC, NV>(oi, a.grad_inv, row, D, lane);
+            store_row<VEC, NV>(oe, a.grad_env, row, D, lane);
+        }
+    }
+}
+
+// Dense Adam over the rows that received no gradient this step.
+template <int VEC, int NV>
+__global__ void __launch_bounds__(BLOCK) sweep_kernel(BwdSideArgs a) {
+    const int D = a.D;
+    const int lane = threadIdx.x & (GROUP - 1);
+    const int64_t rows = a.plan.rows;
+    const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
+    const uint32_t* __restrict__ touched = a.plan.touched;
+    for (int64_t row = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4); row < rows; row += ngroups) {
+        if ((touched[row >> 5] >> (row & 31)) & 1u) continue;
+        Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
+        load_row<VEC, NV, true>(th_i, a.own_inv_in, row, D, lane);
+        load_row<VEC, NV, true>(th_e, a.own_env_in, row, D, lane);
+        load_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+        load_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+        load_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+        load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) {
+            adam_update(th_i.x[x], m_i.x[x], v_i.x[x], 0.f, a.adam);
+            adam_update(th_e.x[x], m_e.x[x], v_e.x[x], 0.f, a.adam);
+        }
+        store_row<VEC, NV, true>(th_i, a.own_inv_out, row, D, lane);
+        store_row<VEC, NV, true>(th_e, a.own_env_out, row, D, lane);
+        store_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+        store_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+        store_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+        store_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
+        if (a.grad_inv != nullptr) {
+            Row<VEC, NV> z;
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) z.x[x] = 0.f;
+            store_row<VEC, NV>(z, a.grad_inv, row, D, lane);
+            store_row<VEC, NV>(z, a.grad_env, row, D, lane);
+        }
+    }
+}
+
+constexpr int TAIL_THREADS = 256;
+constexpr int P_DB = 8, P_CNT = 16, P_DW = 24;
+
+__device__ __forceinline__ double block_sum_double(double v, double* sbuf) {
+    __syncthreads();
+    sbuf[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = TAIL_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sbuf[threadIdx.x] += sbuf[threadIdx.x + s];
+        __syncthreads();
+    }
+    return sbuf[0];
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
+    extern __shared__ double stot[];          // [P] totals, then [TAIL_THREADS] scratch
+    double* sbuf = stot + a.P;
+    const int tid = threadIdx.x;
+    const int K = a.K, D = a.D, KD = a.K * a.D;
+    for (int idx = tid; idx < a.P; idx += TAIL_THREADS) {
+        double s = 0.0;
+        for (int b = 0; b < a.n_partials; ++b) s += (double)a.partials[(int64_t)b * a.P + idx];
+        stot[idx] = s;
+    }
+    __syncthreads();
+    const double Bf = (double)a.B, Df = (double)D;
+    if (a.epi == EPI_ADAM) {
+        // classifier norms (models.py:210-217), only when it is regularised
+        double w2 = 0.0, w1 = 0.0, b2 = 0.0, b1 = 0.0;
+        if (!a.reg_only_embed) {
+            for (int idx = tid; idx < KD; idx += TAIL_THREADS) {
+                double x = a.W_in[idx];
+                w2 += x * x; w1 += fabs(x);
+            }
+            if (tid < K) { double x = a.b_in[tid]; b2 = x * x; b1 = fabs(x); }
+            w2 = block_sum_double(w2, sbuf);
+            w1 = block_sum_double(w1, sbuf);
+            b2 = block_sum_double(b2, sbuf);
+            b1 = block_sum_double(b1, sbuf);
+        }
+        if (tid == 0 && a.loss_out != nullptr) {
+            const float inv_loss = (float)(stot[0] / Bf);
+            const float ea_loss = (float)(stot[1] / Bf);
+            const float envs_loss = (float)(stot[2] / Bf);
+            double L2 = stot[3] / (Bf * Df * 2.0), L1 = stot[4] / (Bf * Df * 2.0);
+            if (!a.reg_only_embed) {
+                L2 += w2 / (Df * K) + b2 / K;
+                L1 += w1 / (Df * K) + b1 / K;
+            }
+            if (a.reg_env_embed) {
+                L2 += stot[5] / (Bf * Df);
+                L1 += stot[6] / (Bf * Df);
+            }
+            const float L2f = (float)L2, L1f = (float)L1;
+            a.loss_out[0] = inv_loss;
+            a.loss_out[1] = ea_loss;
+            a.loss_out[2] = envs_loss;
+            a.loss_out[3] = L2f;
+            a.loss_out[4] = L1f;
+            a.loss_out[5] = inv_loss * a.c_inv + ea_loss * a.c_ea + envs_loss * a.c_env + L2f * a.c_L2 + L1f * a.c_L1;
+        }
+        const float rW2 = 2.f * a.c_L2 / (float)(Df * K), rW1 = a.c_L1 / (float)(Df * K);
+        const float rb2 = 2.f * a.c_L2 / (float)K, rb1 = a.c_L1 / (float)K;
+        const float rE2 = (float)(2.0 * a.c_L2 / (Bf * Df)), rE1 = (float)(a.c_L1 / (Bf * Df));
+        for (int idx = tid; idx < KD; idx += TAIL_THREADS) {
+            const int k = idx / D;
+            float w = a.W_in[idx], e = a.E_in[idx];
+            float gW = (float)stot[P_DW + idx];
+            float gE = (float)stot[P_DW + KD + idx];
+            if (!a.reg_only_embed) gW += rW2 * w + rW1 * signf_(w);
+            if (a.reg_env_embed) gE += (float)stot[P_CNT + k] * (rE2 * e + rE1 * signf_(e));
+            if (a.gW) { a.gW[idx] = gW; a.gE[idx] = gE; }
+            float m = a.mW[idx], v = a.vW[idx];
+            adam_update(w, m, v, gW, a.adam);
+            a.W_out[idx] = w; a.mW[idx] = m; a.vW[idx] = v;
+            m = a.mE[idx]; v = a.vE[idx];
+            adam_update(e, m, v, gE, a.adam);
+            a.E_out[idx] = e; a.mE[idx] = m; a.vE[idx] = v;
+        }
+        if (tid < K) {
+            float bb = a.b_in[tid];
+            float gb = (float)stot[P_DB + tid];
+            if (!a.reg_only_embed) gb += rb2 * bb + rb1 * signf_(bb);
+            if (a.gb) a.gb[tid] = gb;
+            float m = a.mb[tid], v = a.vb[tid];
+            adam_update(bb, m, v, gb, a.adam);
+            a.b_out[tid] = bb; a.mb[tid] = m; a.vb[tid] = v;
+        }
+    } else {
+        for (int idx = tid; idx < KD; idx += TAIL_THREADS) {
+            a.gW[idx] += (float)stot[P_DW + idx];
+            a.gE[idx] += (float)stot[P_DW + KD + idx];
+        }
+        if (tid < K) a.gb[tid] += (float)stot[P_DB + tid];
+    }
+}
+
+inline int grid_groups(int64_t n, int max_blocks) {
+    int64_t need = (n + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
+    if (need < 1) need = 1;
+    return (int)(need < max_blocks ? need : max_blocks);
+}
+
+}  // namespace
+
+int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream) {
+    size_t smem = (size_t)2 * g.K * g.D * sizeof(float);
+    int grid = grid_groups(a.plan.max_chunks, 148 * 8);
+#define CALL(V, N) bwd_chunks_kernel<V, N><<<grid, BLOCK, smem, stream>>>(a)
+    INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream_t stream) {
+    size_t smem = (size_t)2 * g.K * g.D * sizeof(float);
+    int grid = grid_groups(a.plan.max_seg, 148 * 8);
+    if (epi == EPI_ADAM) {
+#define CALL(V, N) bwd_rows_kernel<V, N, EPI_ADAM><<<grid, BLOCK, smem, stream>>>(a)
+        INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    } else {
+#define CALL(V, N) bwd_rows_kernel<V, N, EPI_ACCUM><<<grid, BLOCK, smem, stream>>>(a)
+        INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    }
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_sweep(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream) {
+    int grid = grid_groups(a.plan.rows, 148 * 16);
+#define CALL(V, N) sweep_kernel<V, N><<<grid, BLOCK, 0, stream>>>(a)
+    INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_tail(const TailArgs& a, cudaStream_t stream) {
+    size_t smem = (size_t)(a.P + TAIL_THREADS) * sizeof(double);
+    tail_kernel<<<1, TAIL_THREADS, smem, stream>>>(a);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+}  // namespace invpref

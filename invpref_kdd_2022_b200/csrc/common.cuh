@@ -1,0 +1,298 @@
+// Shared device helpers and internal structs for libinvpref_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "invpref_b200.h"
+
+namespace invpref {
+
+// One embedding row is handled by a GROUP of 16 lanes; lane l owns NV vectors of VEC floats at
+// dims (j*GROUP + l)*VEC .. +VEC, j < NV.  D = 64 -> 16 x float4 (one 128-bit load per lane per
+// row, a half-warp reads a full 256 B row = 8 sectors, coalesced); D = 40 -> 10 active lanes;
+// D = 30 -> float2 x 15 lanes.
+constexpr int GROUP = 16;
+constexpr int BLOCK = 256;                 // threads per CTA for the row kernels (16 groups)
+constexpr int GROUPS_PER_BLOCK = BLOCK / GROUP;
+
+// Segments longer than LONG_T interactions are pre-reduced in CHUNK-sized pieces by separate
+// groups (fixed shape => deterministic), the owner row then sums the partials in order.
+constexpr int LONG_T = 512;
+constexpr int CHUNK = 256;
+
+struct Geometry {
+    int D, K;
+    int VEC, NV, KT;   // vector width, vectors per lane, compile-time env capacity
+    int GS;            // floats per interaction in the g-pack
+};
+
+inline int make_geometry(const invpref_desc* d, Geometry* g) {
+    if (d == nullptr) return INVPREF_ERR_BAD_ARG;
+    if (d->dim < 1 || d->dim > INVPREF_MAX_DIM) return INVPREF_ERR_BAD_DIM;
+    if (d->n_envs < 1 || d->n_envs > INVPREF_MAX_ENVS) return INVPREF_ERR_BAD_ENVS;
+    if (d->n_users < 1 || d->n_items < 1 || d->n_users > 0x7fffffffLL || d->n_items > 0x7fffffffLL)
+        return INVPREF_ERR_BAD_ARG;
+    int D = d->dim;
+    g->D = D;
+    g->K = d->n_envs;
+    if (D % 4 == 0) {
+        g->VEC = 4;
+        g->NV = D <= 64 ? 1 : (D <= 128 ? 2 : 4);
+    } else if (D % 2 == 0) {
+        g->VEC = 2;
+        if (D > 64) return INVPREF_ERR_BAD_DIM;
+        g->NV = D <= 32 ? 1 : 2;
+    } else {
+        g->VEC = 1;
+        if (D > 64) return INVPREF_ERR_BAD_DIM;
+        g->NV = 4;
+    }
+    g->KT = g->K <= 2 ? 2 : (g->K <= 4 ? 4 : (g->K <= 6 ? 6 : 8));
+    g->GS = g->K <= 5 ? 8 : 12;
+    return INVPREF_OK;
+}
+
+// Invokes F<VEC,NV,KT>() for the instantiated combinations.
+#define INVPREF_DISPATCH_GEOM(geom, CALL)                                                   \
+    do {                                                                                    \
+        const int _v = (geom).VEC, _n = (geom).NV, _k = (geom).KT;                          \
+        if (_v == 4 && _n == 1) { INVPREF_DISPATCH_K(4, 1, _k, CALL); }                     \
+        else if (_v == 4 && _n == 2) { INVPREF_DISPATCH_K(4, 2, _k, CALL); }                \
+        else if (_v == 4 && _n == 4) { INVPREF_DISPATCH_K(4, 4, _k, CALL); }                \
+        else if (_v == 2 && _n == 1) { INVPREF_DISPATCH_K(2, 1, _k, CALL); }                \
+        else if (_v == 2 && _n == 2) { INVPREF_DISPATCH_K(2, 2, _k, CALL); }                \
+        else { INVPREF_DISPATCH_K(1, 4, _k, CALL); }                                        \
+    } while (0)
+
+#define INVPREF_DISPATCH_K(V, N, k, CALL)                                                   \
+    do {                                                                                    \
+        if ((k) == 2) { CALL(V, N, 2); }                                                    \
+        else if ((k) == 4) { CALL(V, N, 4); }                                               \
+        else if ((k) == 6) { CALL(V, N, 6); }                                               \
+        else { CALL(V, N, 8); }                                                             \
+    } while (0)
+
+// Same, for kernels that do not depend on the env capacity.
+#define INVPREF_DISPATCH_VN(geom, CALL)                                                     \
+    do {                                                                                    \
+        const int _v = (geom).VEC, _n = (geom).NV;                                          \
+        if (_v == 4 && _n == 1) { CALL(4, 1); }                                             \
+        else if (_v == 4 && _n == 2) { CALL(4, 2); }                                        \
+        else if (_v == 4 && _n == 4) { CALL(4, 4); }                                        \
+        else if (_v == 2 && _n == 1) { CALL(2, 1); }                                        \
+        else if (_v == 2 && _n == 2) { CALL(2, 2); }                                        \
+        else { CALL(1, 4); }                                                                \
+    } while (0)
+
+extern long long g_launch_count;   // host-side counter (api.cu)
+inline void count_launch(int n = 1) { g_launch_count += n; }
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- plan layout (one side = one sort order) ----------------------------------------------
+struct PlanSide {
+    int32_t* counters;    // [0] n_seg, [1] n_chunks, [2] error flag ; 16 ints
+    int32_t* perm;        // [B]   sorted position -> original index in the batch
+    int32_t* partner;     // [B]   id of the OTHER table's row, in sorted order
+    int32_t* seg_row;     // [S]   unique ids ascending                     (S <= min(B, rows))
+    int32_t* seg_off;     // [S+1] offsets into perm
+    int32_t* seg_chunk;   // [S+1] exclusive scan of per-segment chunk counts (0 for short segments)
+    int32_t* chunk_desc;  // [max_chunks*4] (seg, begin, end, unused)
+    uint32_t* touched;    // [ceil(rows/32)] bitmap of rows that have a segment
+    int64_t max_seg, max_chunks, rows, B;
+};
+
+inline int64_t plan_max_seg(int64_t B, int64_t rows) { return B < rows ? B : rows; }
+inline int64_t plan_max_chunks(int64_t B) { return B / CHUNK + B / LONG_T + 2; }
+
+inline size_t plan_side_bytes(int64_t B, int64_t rows) {
+    int64_t S = plan_max_seg(B, rows);
+    size_t n = 0;
+    n += align_up(16 * 4);
+    n += align_up((size_t)B * 4) * 2;
+    n += align_up((size_t)S * 4);
+    n += align_up((size_t)(S + 1) * 4) * 2;
+    n += align_up((size_t)plan_max_chunks(B) * 16);
+    n += align_up((size_t)((rows + 31) / 32) * 4);
+    return n;
+}
+
+inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
+    PlanSide p;
+    int64_t S = plan_max_seg(B, rows);
+    p.max_seg = S;
+    p.max_chunks = plan_max_chunks(B);
+    p.rows = rows;
+    p.B = B;
+    char* c = base;
+    p.counters = (int32_t*)c;   c += align_up(16 * 4);
+    p.perm = (int32_t*)c;       c += align_up((size_t)B * 4);
+    p.partner = (int32_t*)c;    c += align_up((size_t)B * 4);
+    p.seg_row = (int32_t*)c;    c += align_up((size_t)S * 4);
+    p.seg_off = (int32_t*)c;    c += align_up((size_t)(S + 1) * 4);
+    p.seg_chunk = (int32_t*)c;  c += align_up((size_t)(S + 1) * 4);
+    p.chunk_desc = (int32_t*)c; c += align_up((size_t)p.max_chunks * 16);
+    p.touched = (uint32_t*)c;
+    return p;
+}
+
+// ---- workspace layout ------------------------------------------------------------------------
+constexpr int FWD_MAX_BLOCKS = 148 * 8;
+
+struct Workspace {
+    float* gpack;        // [B * GS]
+    float* partials;     // [FWD_MAX_BLOCKS * P]   per-CTA partial sums of the forward kernel
+    float* chunk_part_u; // [max_chunks * 2 * D]
+    float* chunk_part_i; // [max_chunks * 2 * D]
+    char* plan;          // scratch plan (when the caller passes none)
+    char* sort_tmp;      // keys / values / flags / scan temp + CUB temp storage
+    size_t sort_tmp_bytes;
+    size_t plan_bytes;
+};
+
+// number of floats one forward CTA writes: 8 scalars, db[KT], cnt[KT], dW[K*D], dE[K*D]
+inline int fwd_partial_floats(const Geometry& g) { return 8 + 2 * 8 + 2 * g.K * g.D; }
+
+size_t sort_tmp_bytes_for(int64_t B, int64_t max_rows);   // plan.cu
+
+inline size_t workspace_bytes_impl(const invpref_desc* d, const Geometry& g, int64_t B, Workspace* w, char* base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base ? base + o : (char*)nullptr; };
+    int64_t Bp = B > 0 ? B : 1;
+    char* gp = take((size_t)Bp * g.GS * 4);
+    char* pa = take((size_t)FWD_MAX_BLOCKS * fwd_partial_floats(g) * 4);
+    char* cu = take((size_t)plan_max_chunks(Bp) * 2 * g.D * 4);
+    char* ci = take((size_t)plan_max_chunks(Bp) * 2 * g.D * 4);
+    size_t pb = plan_side_bytes(Bp, d->n_users) + plan_side_bytes(Bp, d->n_items);
+    char* pl = take(pb);
+    int64_t mr = d->n_users > d->n_items ? d->n_users : d->n_items;
+    size_t sb = sort_tmp_bytes_for(Bp, mr);
+    char* st = take(sb);
+    if (w) {
+        w->gpack = (float*)gp; w->partials = (float*)pa; w->chunk_part_u = (float*)cu; w->chunk_part_i = (float*)ci;
+        w->plan = pl; w->sort_tmp = st; w->sort_tmp_bytes = sb; w->plan_bytes = pb;
+    }
+    return off;
+}
+
+// =============================== device helpers ================================================
+#ifdef __CUDACC__
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+// plain (cached) vector load of VEC floats
+template <int VEC> __device__ __forceinline__ void ldv(const float* p, float* r);
+template <> __device__ __forceinline__ void ldv<4>(const float* p, float* r) {
+    float4 v = *reinterpret_cast<const float4*>(p); r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+}
+template <> __device__ __forceinline__ void ldv<2>(const float* p, float* r) {
+    float2 v = *reinterpret_cast<const float2*>(p); r[0] = v.x; r[1] = v.y;
+}
+template <> __device__ __forceinline__ void ldv<1>(const float* p, float* r) { r[0] = *p; }
+
+// streaming load (read once: evict-first, do not allocate in L1)
+template <int VEC> __device__ __forceinline__ void ldv_stream(const float* p, float* r);
+template <> __device__ __forceinline__ void ldv_stream<4>(const float* p, float* r) {
+    float4 v = __ldcs(reinterpret_cast<const float4*>(p)); r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+}
+template <> __device__ __forceinline__ void ldv_stream<2>(const float* p, float* r) {
+    float2 v = __ldcs(reinterpret_cast<const float2*>(p)); r[0] = v.x; r[1] = v.y;
+}
+template <> __device__ __forceinline__ void ldv_stream<1>(const float* p, float* r) { r[0] = __ldcs(p); }
+
+template <int VEC> __device__ __forceinline__ void stv(float* p, const float* r);
+template <> __device__ __forceinline__ void stv<4>(float* p, const float* r) {
+    *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+}
+template <> __device__ __forceinline__ void stv<2>(float* p, const float* r) {
+    *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]);
+}
+template <> __device__ __forceinline__ void stv<1>(float* p, const float* r) { *p = r[0]; }
+
+template <int VEC> __device__ __forceinline__ void stv_stream(float* p, const float* r);
+template <> __device__ __forceinline__ void stv_stream<4>(float* p, const float* r) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(r[0], r[1], r[2], r[3]));
+}
+template <> __device__ __forceinline__ void stv_stream<2>(float* p, const float* r) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(r[0], r[1]));
+}
+template <> __device__ __forceinline__ void stv_stream<1>(float* p, const float* r) { __stcs(p, r[0]); }
+
+// A row slice held by one lane: NV vectors of VEC floats.
+template <int VEC, int NV> struct Row {
+    float x[NV * VEC];
+};
+
+// dim index of element (j, v) for this lane
+template <int VEC> __device__ __forceinline__ int dim_of(int lane, int j) { return (j * GROUP + lane) * VEC; }
+
+template <int VEC, int NV, bool STREAM = false>
+__device__ __forceinline__ void load_row(Row<VEC, NV>& r, const float* __restrict__ table, int64_t row, int D, int lane) {
+    const float* p = table + row * (int64_t)D;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        int d0 = dim_of<VEC>(lane, j);
+        if (d0 < D) {
+            if (STREAM) ldv_stream<VEC>(p + d0, &r.x[j * VEC]);
+            else ldv<VEC>(p + d0, &r.x[j * VEC]);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) r.x[j * VEC + v] = 0.f;
+        }
+    }
+}
+
+template <int VEC, int NV, bool STREAM = false>
+__device__ __forceinline__ void store_row(const Row<VEC, NV>& r, float* __restrict__ table, int64_t row, int D, int lane) {
+    float* p = table + row * (int64_t)D;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        int d0 = dim_of<VEC>(lane, j);
+        if (d0 < D) {
+            if (STREAM) stv_stream<VEC>(p + d0, &r.x[j * VEC]);
+            else stv<VEC>(p + d0, &r.x[j * VEC]);
+        }
+    }
+}
+
+// sum over the 16 lanes of a group; every lane gets the result (xor butterfly stays inside the
+// aligned half-warp)
+__device__ __forceinline__ float group_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return group_sum(v);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float signf_(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+// Scalars of one dense torch.optim.Adam update (torch/optim/adam.py, single-tensor path):
+// computed on the host in double from the integer step, used as fp32 in the tensor ops.
+struct AdamScalars {
+    float one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps;
+};
+
+// exp_avg.lerp_(g, 1-b1); exp_avg_sq.mul_(b2).addcmul_(g, g, 1-b2);
+// denom = sqrt(v)/sqrt(bc2) + eps; p.addcdiv_(m, denom, value=-lr/bc1)
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, const AdamScalars& s) {
+    m = m + (g - m) * s.one_minus_b1;
+    v = v * s.b2 + (s.one_minus_b2 * g) * g;
+    float denom = sqrtf(v) / s.bc2_sqrt + s.eps;
+    p = p - s.step_size * (m / denom);
+}
+
+#endif  // __CUDACC__
+
+}  // namespace invpref

@@ -1,0 +1,105 @@
+// Internal launcher interface between api.cu and the kernel translation units.
+#pragma once
+
+#include "common.cuh"
+
+namespace invpref {
+
+// ---- fwd.cu ----------------------------------------------------------------------------------
+struct FwdTrainArgs {
+    const float *Uinv, *Iinv, *Uenv, *Ienv, *E, *W, *b;
+    const int64_t *users, *items, *envs;
+    const float *scores, *weights;
+    int64_t B;
+    int D, K, GS;
+    int implicit, reg_env_embed, use_class_rw, use_rec_rw;
+    float c_inv, c_ea, c_env, neg_alpha, invB;
+    float* gpack;      // [B, GS]: g_z1, g_z2, env (int bits), -alpha * g_logits[K]
+    float* partials;   // [gridDim.x, P]
+    int P;
+    // generic autograd backward (invpref_backward): upstream grads instead of the built-in losses
+    const float *up_s_inv, *up_s_env, *up_logp;
+    int generic;
+};
+
+struct FwdOnlyArgs {
+    const float *Uinv, *Iinv, *Uenv, *Ienv, *E, *W, *b;
+    const int64_t *users, *items, *envs;
+    int64_t B;
+    int D, K, implicit;
+    float *s_inv, *s_env, *logp;
+};
+
+int fwd_train_grid(int64_t B);
+int launch_fwd_train(const Geometry& g, const FwdTrainArgs& a, int grid, cudaStream_t stream);
+int launch_fwd_only(const Geometry& g, const FwdOnlyArgs& a, cudaStream_t stream);
+int launch_predict(const Geometry& g, const float* Uinv, const float* Iinv, const int64_t* users, const int64_t* items,
+                   int64_t B, float* score, cudaStream_t stream);
+
+// ---- bwd.cu ----------------------------------------------------------------------------------
+enum { EPI_ADAM = 0, EPI_ACCUM = 1 };
+
+// One side (user tables or item tables) of the segmented backward.
+struct BwdSideArgs {
+    const float *own_inv_in, *own_env_in;     // this side's tables, values BEFORE the step
+    float *own_inv_out, *own_env_out;         // where the updated rows go (double buffer)
+    float *m_inv, *m_env, *v_inv, *v_env;     // Adam state, updated in place
+    const float *partner_inv, *partner_env;   // the other side's tables (BEFORE the step)
+    float *grad_inv, *grad_env;               // optional dense gradient output / accumulation target
+    PlanSide plan;
+    float* chunk_part;                        // [max_chunks, 2, D]
+    const float* gpack;
+    const float *E, *W;
+    int D, K, GS;
+    float reg2, reg1;                         // 2*c_L2/(B*D*2), c_L1/(B*D*2)
+    AdamScalars adam;
+};
+
+int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);
+int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream_t stream);
+int launch_sweep(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);
+
+struct TailArgs {
+    const float* partials;
+    int n_partials, P;
+    int64_t B;
+    int D, K;
+    int reg_only_embed, reg_env_embed;
+    float c_inv, c_ea, c_env, c_L2, c_L1;
+    const float *E_in, *W_in, *b_in;
+    float *E_out, *W_out, *b_out;
+    float *mE, *mW, *mb, *vE, *vW, *vb;
+    float *gE, *gW, *gb;      // optional grads out (EPI_ADAM) / accumulation target (EPI_ACCUM)
+    float* loss_out;          // [6]
+    AdamScalars adam;
+    int epi;
+};
+
+int launch_tail(const TailArgs& a, cudaStream_t stream);
+
+// ---- cluster.cu ------------------------------------------------------------------------------
+struct ClusterArgs {
+    const float *Uinv, *Iinv, *Uenv, *Ienv, *E;
+    const int64_t *users, *items;
+    const float* scores;
+    const int64_t* perm_idx;
+    const float* eps_table;
+    const int64_t* old_envs;
+    int64_t B;
+    int D, K, implicit;
+    int64_t* new_envs;
+    unsigned long long *hist, *diff;
+};
+
+int launch_cluster(const Geometry& g, const ClusterArgs& a, cudaStream_t stream);
+int launch_env_hist(const int64_t* envs, int64_t N, int K, unsigned long long* hist, cudaStream_t stream);
+int launch_stat_envs(const int64_t* envs, int64_t N, int K, const int64_t* hist, float* class_weights,
+                     float* sample_weights, cudaStream_t stream);
+
+// ---- plan.cu ---------------------------------------------------------------------------------
+int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, PlanSide p, char* tmp,
+                    size_t tmp_bytes, cudaStream_t stream);
+int build_segments_i64(const int64_t* ids, int64_t B, int64_t rows, int64_t* perm, int64_t* seg_row, int64_t* seg_off,
+                       int64_t* n_seg, char* ws, size_t ws_bytes, cudaStream_t stream);
+
+}  // namespace invpref

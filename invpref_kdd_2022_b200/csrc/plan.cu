@@ -1,0 +1,201 @@
+// Sort-segment plan: stable sort of a batch by row id, unique rows, segment offsets, chunking of
+// long segments, touched-row bitmap.  Replaces the duplicate handling of ATen's
+// embedding_dense_backward (autograd of the reference's models.py:449-455).
+//
+// The sort itself is a library call (cub::DeviceRadixSort, LSD => stable, so `perm` is bit-equal to
+// torch.sort(ids, stable=True)); the plan depends only on the (fixed) batch slicing of
+// utils.py:12-19 and is built once per batch by the trainer, outside the per-step hot loop.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace invpref {
+
+namespace {
+
+__global__ void prep_keys_kernel(const int64_t* __restrict__ ids, int64_t B, int64_t rows, int32_t* __restrict__ keys,
+                                 int32_t* __restrict__ vals, int32_t* __restrict__ counters) {
+    int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n == 0) { counters[0] = 0; counters[1] = 0; }
+    if (n >= B) return;
+    int64_t id = ids[n];
+    if (id < 0 || id >= rows) {
+        counters[2] = 1;   // id out of range: flagged, clamped so that nothing reads out of bounds
+        id = id < 0 ? 0 : rows - 1;
+    }
+    keys[n] = (int32_t)id;
+    vals[n] = (int32_t)n;
+}
+
+__global__ void flag_heads_kernel(const int32_t* __restrict__ sorted, int64_t B, int32_t* __restrict__ flag) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= B) return;
+    flag[k] = (k == 0 || sorted[k] != sorted[k - 1]) ? 1 : 0;
+}
+
+__global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const int32_t* __restrict__ segid,
+                                      const int32_t* __restrict__ perm, const int64_t* __restrict__ other_ids,
+                                      int64_t other_rows, int64_t B, PlanSide p) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= B) return;
+    int32_t key = sorted[k];
+    int32_t s = segid[k] - 1;
+    bool head = (k == 0) || (sorted[k - 1] != key);
+    if (head) {
+        p.seg_row[s] = key;
+        p.seg_off[s] = (int32_t)k;
+        atomicOr(&p.touched[key >> 5], 1u << (key & 31));
+    }
+    if (k == B - 1) {
+        p.counters[0] = s + 1;
+        p.seg_off[s + 1] = (int32_t)B;
+    }
+    if (other_ids != nullptr) {
+        int64_t o = other_ids[perm[k]];
+        if (o < 0) o = 0;
+        if (o >= other_rows) o = other_rows - 1;
+        p.partner[k] = (int32_t)o;
+    }
+}
+
+__global__ void chunk_counts_kernel(PlanSide p) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s > p.max_seg) return;
+    int32_t n_seg = p.counters[0];
+    int32_t c = 0;
+    if (s < n_seg) {
+        int32_t len = p.seg_off[s + 1] - p.seg_off[s];
+        if (len > LONG_T) c = (len + CHUNK - 1) / CHUNK;
+    }
+    p.seg_chunk[s] = c;
+}
+
+__global__ void write_chunks_kernel(PlanSide p) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int32_t n_seg = p.counters[0];
+    if (s == 0) p.counters[1] = p.seg_chunk[n_seg];
+    if (s >= n_seg) return;
+    int32_t c0 = p.seg_chunk[s], c1 = p.seg_chunk[s + 1];
+    if (c1 == c0) return;
+    int32_t beg = p.seg_off[s], end = p.seg_off[s + 1];
+    for (int32_t c = c0; c < c1; ++c) {
+        int32_t b = beg + (c - c0) * CHUNK;
+        int32_t e = b + CHUNK < end ? b + CHUNK : end;
+        reinterpret_cast<int4*>(p.chunk_desc)[c] = make_int4((int32_t)s, b, e, 0);
+    }
+}
+
+__global__ void empty_plan_kernel(PlanSide p) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        p.counters[0] = 0; p.counters[1] = 0;
+        p.seg_off[0] = 0; p.seg_chunk[0] = 0;
+    }
+}
+
+__global__ void widen_kernel(const int32_t* __restrict__ src, int64_t* __restrict__ dst, int64_t n, const int32_t* limit,
+                             int64_t extra) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t lim = limit ? (int64_t)(*limit) + extra : n;
+    if (k < n && k < lim) dst[k] = src[k];
+}
+
+__global__ void widen_scalar_kernel(const int32_t* src, int64_t* dst) { *dst = *src; }
+
+struct SortTmp {
+    int32_t *keys_in, *keys_out, *vals_in, *scan;
+    void* cub_tmp;
+    size_t cub_bytes;
+};
+
+size_t cub_bytes_for(int64_t B, int64_t max_seg_plus1) {
+    size_t a = 0, b = 0, c = 0;
+    int n = (int)B;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, n, 0, 32);
+    cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr, n);
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (const int32_t*)nullptr, (int32_t*)nullptr, (int)max_seg_plus1);
+    size_t m = a > b ? a : b;
+    return (m > c ? m : c) + 256;
+}
+
+SortTmp carve_sort_tmp(char* base, int64_t B, size_t total) {
+    SortTmp t;
+    size_t arr = align_up((size_t)B * 4);
+    t.keys_in = (int32_t*)base;
+    t.keys_out = (int32_t*)(base + arr);
+    t.vals_in = (int32_t*)(base + 2 * arr);
+    t.scan = (int32_t*)(base + 3 * arr);
+    t.cub_tmp = base + 4 * arr;
+    t.cub_bytes = total - 4 * arr;
+    return t;
+}
+
+inline int bits_for(int64_t rows) {
+    int b = 1;
+    while (b < 32 && ((int64_t)1 << b) < rows) ++b;
+    return b;
+}
+
+inline unsigned grid_for(int64_t n, int block = 256) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+size_t sort_tmp_bytes_for(int64_t B, int64_t max_rows) {
+    int64_t S = plan_max_seg(B, max_rows);
+    return 4 * align_up((size_t)B * 4) + align_up(cub_bytes_for(B, S + 1));
+}
+
+// Builds one side of a plan.  All work is enqueued on `stream`; nothing is read back.
+int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, PlanSide p, char* tmp,
+                    size_t tmp_bytes, cudaStream_t stream) {
+    int64_t B = p.B;
+    cudaMemsetAsync(p.touched, 0, (size_t)((p.rows + 31) / 32) * 4, stream);
+    cudaMemsetAsync(p.counters, 0, 16 * 4, stream);
+    if (B == 0) {
+        empty_plan_kernel<<<1, 32, 0, stream>>>(p);
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+    }
+    if (tmp_bytes < sort_tmp_bytes_for(B, p.rows)) return INVPREF_ERR_WORKSPACE;
+    SortTmp t = carve_sort_tmp(tmp, B, tmp_bytes);
+    prep_keys_kernel<<<grid_for(B), 256, 0, stream>>>(ids, B, p.rows, t.keys_in, t.vals_in, p.counters);
+    size_t cb = t.cub_bytes;
+    cub::DeviceRadixSort::SortPairs(t.cub_tmp, cb, t.keys_in, t.keys_out, t.vals_in, p.perm, (int)B, 0, bits_for(p.rows),
+                                    stream);
+    flag_heads_kernel<<<grid_for(B), 256, 0, stream>>>(t.keys_out, B, t.scan);
+    cb = t.cub_bytes;
+    cub::DeviceScan::InclusiveSum(t.cub_tmp, cb, t.scan, t.scan, (int)B, stream);
+    write_segments_kernel<<<grid_for(B), 256, 0, stream>>>(t.keys_out, t.scan, p.perm, other_ids, other_rows, B, p);
+    chunk_counts_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p);
+    cb = t.cub_bytes;
+    cub::DeviceScan::ExclusiveSum(t.cub_tmp, cb, p.seg_chunk, p.seg_chunk, (int)(p.max_seg + 1), stream);
+    write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p);
+    count_launch(5 + 6);   // 5 of ours + CUB's (radix passes, 2 scans; approximate)
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int build_segments_i64(const int64_t* ids, int64_t B, int64_t rows, int64_t* perm, int64_t* seg_row, int64_t* seg_off,
+                       int64_t* n_seg, char* ws, size_t ws_bytes, cudaStream_t stream) {
+    int64_t Bp = B > 0 ? B : 1;
+    size_t side = plan_side_bytes(Bp, rows);
+    size_t need = side + sort_tmp_bytes_for(Bp, rows);
+    if (ws_bytes < need) return INVPREF_ERR_WORKSPACE;
+    PlanSide p = carve_plan_side(ws, Bp, rows);
+    p.B = B;
+    int rc = build_plan_side(ids, nullptr, 0, p, ws + side, ws_bytes - side, stream);
+    if (rc != INVPREF_OK) return rc;
+    if (B > 0) {
+        widen_kernel<<<grid_for(B), 256, 0, stream>>>(p.perm, perm, B, nullptr, 0);
+        widen_kernel<<<grid_for(p.max_seg), 256, 0, stream>>>(p.seg_row, seg_row, p.max_seg, p.counters, 0);
+        widen_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p.seg_off, seg_off, p.max_seg + 1, p.counters, 1);
+        count_launch(3);
+    } else {
+        widen_kernel<<<1, 32, 0, stream>>>(p.seg_off, seg_off, 1, nullptr, 0);
+        count_launch();
+    }
+    widen_scalar_kernel<<<1, 1, 0, stream>>>(p.counters, n_seg);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+}  // namespace invpref

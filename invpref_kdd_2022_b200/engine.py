@@ -1,0 +1,199 @@
+"""Host-side driver of the C ABI: owns the double-buffered tables, Adam state, workspace and plans.
+
+The arithmetic lives in ``libinvpref_b200.so``; this module only holds torch tensors (device memory)
+and marshals pointers.  One ``HotPath`` per model per process (= per GPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+PARAM_FIELDS = _lib.PARAM_FIELDS
+TABLES = ("Uinv", "Iinv", "Uenv", "Ienv")
+
+
+class HotPath:
+    """Fused train step / EM re-assignment / forward for one set of InvPref parameters.
+
+    ``params``: dict ``{Uinv, Iinv, Uenv, Ienv, E, W, b}`` of fp32 CUDA tensors (the nn.Parameter
+    ``.data`` of the model, so the model sees every update).  The four tables are double-buffered
+    (``invpref_train_step`` reads one set and writes the other); after each step ``params`` holds
+    the NEW tensors and ``on_swap`` (if given) is called so the owner can re-point its Parameters.
+    """
+
+    def __init__(self, params: Dict[str, torch.Tensor], implicit: bool, reg_only_embed: bool, reg_env_embed: bool,
+                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, on_swap=None):
+        self.lib = _lib.load()
+        for k in PARAM_FIELDS:
+            t = params[k]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError(f"parameter {k} must be a contiguous fp32 CUDA tensor (no CPU fallback)")
+        self.params = dict(params)
+        self.device = params["Uinv"].device
+        n_users, dim = params["Uinv"].shape
+        n_items = params["Iinv"].shape[0]
+        n_envs = params["E"].shape[0]
+        self.n_users, self.n_items, self.n_envs, self.dim = n_users, n_items, n_envs, dim
+        self.implicit = bool(implicit)
+        self.desc = _lib.make_desc(n_users, n_items, n_envs, dim, implicit, reg_only_embed, reg_env_embed)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.step = 0
+        self.on_swap = on_swap
+        self.shadow = None           # allocated on the first train step
+        self.m = None
+        self.v = None
+        self._ws = None
+        self._ws_batch = -1
+        self.loss_buf = torch.zeros(6, dtype=torch.float32, device=self.device)
+
+    # ---- buffers -------------------------------------------------------------------------
+    def _ensure_state(self):
+        if self.m is None:
+            self.m = {k: torch.zeros_like(self.params[k]) for k in PARAM_FIELDS}
+            self.v = {k: torch.zeros_like(self.params[k]) for k in PARAM_FIELDS}
+        if self.shadow is None:
+            self.shadow = {k: self.params[k].clone() for k in TABLES}
+
+    def workspace(self, batch: int) -> torch.Tensor:
+        if self._ws is None or batch > self._ws_batch:
+            n = _lib.workspace_bytes(self.desc, batch)
+            self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+            self._ws_batch = batch
+        return self._ws
+
+    def new_plan(self, users: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+        """Sort-segment plan of one batch (``invpref_build_plan``); reusable while (users, items) are fixed."""
+        B = users.numel()
+        n = _lib.plan_bytes(self.desc, B)
+        plan = torch.empty(n, dtype=torch.uint8, device=self.device)
+        ws = self.workspace(B)
+        _lib.check(self.lib.invpref_build_plan(C.byref(self.desc), _lib.ptr(users, torch.int64),
+                                               _lib.ptr(items, torch.int64), B, _lib.ptr(plan), n, _lib.ptr(ws),
+                                               ws.numel(), _lib.stream_ptr()), "build_plan")
+        return plan
+
+    # ---- fused train step ---------------------------------------------------------------------
+    def train_step(self, users, items, scores, envs, weights, *, c_inv, c_ea, c_env, c_L2, c_L1, alpha,
+                   use_class_rw, use_rec_rw, plan: Optional[torch.Tensor] = None,
+                   loss_out: Optional[torch.Tensor] = None, grads_out: Optional[Dict[str, torch.Tensor]] = None):
+        """train.py:771-844 in one library call.  Returns the device tensor holding the six losses."""
+        self._ensure_state()
+        B = users.numel()
+        ws = self.workspace(B)
+        self.step += 1
+        hyper = _lib.Hyper(float(c_inv), float(c_ea), float(c_env), float(c_L2), float(c_L1), float(alpha), self.lr,
+                           self.betas[0], self.betas[1], self.eps, self.step, int(bool(use_class_rw)),
+                           int(bool(use_rec_rw)))
+        p_in = _lib.make_params(self.params)
+        out = dict(self.params)
+        out.update(self.shadow)
+        p_out = _lib.make_params(out)
+        adam = _lib.Adam(_lib.make_params(self.m), _lib.make_params(self.v))
+        batch = _lib.Batch(_lib.ptr(users, torch.int64), _lib.ptr(items, torch.int64), _lib.ptr(envs, torch.int64),
+                           _lib.ptr(scores, torch.float32), _lib.ptr(weights, torch.float32), B)
+        if loss_out is None:
+            loss_out = self.loss_buf
+        g = _lib.make_params(grads_out) if grads_out is not None else None
+        rc = self.lib.invpref_train_step(C.byref(self.desc), C.byref(p_in), C.byref(p_out), C.byref(adam),
+                                         C.byref(batch), C.byref(hyper), _lib.ptr(plan), _lib.ptr(loss_out),
+                                         C.byref(g) if g is not None else None, _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr())
+        if rc != 0:
+            self.step -= 1
+        _lib.check(rc, "train_step")
+        # the updated rows are in the other buffer set: swap
+        for k in TABLES:
+            self.params[k], self.shadow[k] = self.shadow[k], self.params[k]
+        if self.on_swap is not None:
+            self.on_swap(self.params)
+        return loss_out
+
+    # ---- forward / backward (autograd-compatible path) ----------------------------------------
+    def forward(self, users, items, envs, want_logp=True):
+        B = users.numel()
+        s_inv = torch.empty(B, dtype=torch.float32, device=self.device)
+        s_env = torch.empty(B, dtype=torch.float32, device=self.device)
+        logp = torch.empty((B, self.n_envs), dtype=torch.float32, device=self.device) if want_logp else None
+        p = _lib.make_params(self.params)
+        _lib.check(self.lib.invpref_forward(C.byref(self.desc), C.byref(p), _lib.ptr(users, torch.int64),
+                                            _lib.ptr(items, torch.int64), _lib.ptr(envs, torch.int64), B,
+                                            _lib.ptr(s_inv), _lib.ptr(s_env), _lib.ptr(logp), _lib.stream_ptr()),
+                   "forward")
+        return s_inv, s_env, logp
+
+    def predict(self, users, items):
+        B = users.numel()
+        out = torch.empty(B, dtype=torch.float32, device=self.device)
+        p = _lib.make_params(self.params)
+        _lib.check(self.lib.invpref_predict(C.byref(self.desc), C.byref(p), _lib.ptr(users, torch.int64),
+                                            _lib.ptr(items, torch.int64), B, _lib.ptr(out), _lib.stream_ptr()),
+                   "predict")
+        return out
+
+    def backward(self, users, items, envs, alpha, g_s_inv, g_s_env, g_logp, grads: Dict[str, torch.Tensor], plan=None):
+        """Accumulates the autograd gradients of ``forward`` into ``grads`` (dense, deterministic)."""
+        B = users.numel()
+        ws = self.workspace(B)
+        p = _lib.make_params(self.params)
+        g = _lib.make_params(grads)
+        batch = _lib.Batch(_lib.ptr(users, torch.int64), _lib.ptr(items, torch.int64), _lib.ptr(envs, torch.int64),
+                           None, None, B)
+        _lib.check(self.lib.invpref_backward(C.byref(self.desc), C.byref(p), C.byref(batch), float(alpha),
+                                             _lib.ptr(g_s_inv), _lib.ptr(g_s_env), _lib.ptr(g_logp), _lib.ptr(plan),
+                                             C.byref(g), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "backward")
+
+    # ---- EM re-assignment -------------------------------------------------------------------------
+    def cluster(self, users, items, scores, perm_idx, eps_table, old_envs):
+        """train.py:846-879 over a whole slice.  Returns (new_envs int64[B], hist int64[K], diff int64[1])."""
+        B = users.numel()
+        new_envs = torch.empty(B, dtype=torch.int64, device=self.device)
+        hist = torch.zeros(self.n_envs, dtype=torch.int64, device=self.device)
+        diff = torch.zeros(1, dtype=torch.int64, device=self.device)
+        p = _lib.make_params(self.params)
+        _lib.check(self.lib.invpref_cluster(C.byref(self.desc), C.byref(p), _lib.ptr(users, torch.int64),
+                                            _lib.ptr(items, torch.int64), _lib.ptr(scores, torch.float32),
+                                            _lib.ptr(perm_idx, torch.int64) if perm_idx is not None else None,
+                                            _lib.ptr(eps_table, torch.float32) if eps_table is not None else None,
+                                            _lib.ptr(old_envs, torch.int64) if old_envs is not None else None, B,
+                                            _lib.ptr(new_envs), _lib.ptr(hist),
+                                            _lib.ptr(diff) if old_envs is not None else None, _lib.stream_ptr()),
+                   "cluster")
+        return new_envs, hist, diff
+
+    def env_hist(self, envs):
+        hist = torch.zeros(self.n_envs, dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.invpref_env_hist(_lib.ptr(envs, torch.int64), envs.numel(), self.n_envs, _lib.ptr(hist),
+                                             _lib.stream_ptr()), "env_hist")
+        return hist
+
+    def stat_envs(self, envs, hist):
+        """train.py:945-957 -> (class_weights fp32[K], sample_weights fp32[N])."""
+        N = envs.numel()
+        cw = torch.empty(self.n_envs, dtype=torch.float32, device=self.device)
+        sw = torch.empty(N, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.invpref_stat_envs(_lib.ptr(envs, torch.int64), N, self.n_envs, _lib.ptr(hist, torch.int64),
+                                              _lib.ptr(cw), _lib.ptr(sw), _lib.stream_ptr()), "stat_envs")
+        return cw, sw
+
+
+def build_segments(ids: torch.Tensor, n_rows: int):
+    """``invpref_build_segments``: (perm, seg_row, seg_off) as int64 tensors, trimmed to n_seg."""
+    lib = _lib.load()
+    B = ids.numel()
+    dev = ids.device
+    desc = _lib.make_desc(n_rows, n_rows, 2, 4, 0, 0, 0)
+    ws = torch.empty(_lib.workspace_bytes(desc, B), dtype=torch.uint8, device=dev)
+    S = min(max(B, 1), n_rows)
+    perm = torch.empty(max(B, 1), dtype=torch.int64, device=dev)
+    seg_row = torch.empty(S, dtype=torch.int64, device=dev)
+    seg_off = torch.zeros(S + 1, dtype=torch.int64, device=dev)
+    n_seg = torch.zeros(1, dtype=torch.int64, device=dev)
+    _lib.check(lib.invpref_build_segments(_lib.ptr(ids, torch.int64) if B else None, B, n_rows, _lib.ptr(perm),
+                                          _lib.ptr(seg_row), _lib.ptr(seg_off), _lib.ptr(n_seg), _lib.ptr(ws),
+                                          ws.numel(), _lib.stream_ptr()), "build_segments")
+    n = int(n_seg.item())
+    return perm[:B], seg_row[:n], seg_off[:n + 1]

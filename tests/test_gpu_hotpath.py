@@ -1,0 +1,323 @@
+"""GPU parity of the C-ABI hot path against the golden fixtures (= the reference's own outputs) and
+against the numpy oracle.  Tolerances follow BASELINE.json.north_star: index work bit-exact (argmin ties
+excepted and counted); losses / gradients / updated embeddings within 1e-5 relative in fp32, evaluated
+norm-wise per tensor, one teacher-forced step from identical state (SURVEY.md §7 hard part 1: the
+reference's own fp32-vs-fp64 error is of that order, so the gate on gradients is
+err(ours, fp64) <= max(1e-5, 2 * err(ref_fp32, fp64)))."""
+import numpy as np
+import pytest
+import torch
+
+from _golden import CASES, Golden
+from oracle import invpref_numpy as on
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def nerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.abs(b).max()
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0))
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def make_hotpath(g: Golden, group="init", overrides=None):
+    from invpref_kdd_2022_b200.engine import HotPath
+    sd = g.group(group)
+    if overrides:
+        sd.update(overrides)
+    params = {k: torch.tensor(np.ascontiguousarray(sd[v]), device=dev()) for k, v in on.STATE_KEYS.items()}
+    return HotPath(params, g.implicit, g.roe, g.ree, lr=g.lr)
+
+
+def batch_tensors(g: Golden, lo, hi, envs, weights):
+    d = g.data
+    return (torch.tensor(d[lo:hi, 0], device=dev()), torch.tensor(d[lo:hi, 1], device=dev()),
+            torch.tensor(d[lo:hi, 2].astype(np.float32), device=dev()),
+            torch.tensor(envs[lo:hi].astype(np.int64), device=dev()),
+            torch.tensor(weights[lo:hi].astype(np.float32), device=dev()))
+
+
+def step_kwargs(g: Golden, alpha):
+    return dict(alpha=alpha, use_class_rw=g.crw, use_rec_rw=g.rrw, **g.coef)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_forward_matches_reference(case):
+    g = Golden(case)
+    hp = make_hotpath(g)
+    B = min(g.B, g.N)
+    u, i, _, e, _ = batch_tensors(g, 0, B, g["envs0"], g["sample_weights0"])
+    s_inv, s_env, logp = hp.forward(u, i, e)
+    assert nerr(s_inv.cpu().numpy(), g["fwd0/s_inv"]) <= TOL
+    assert nerr(s_env.cpu().numpy(), g["fwd0/s_env"]) <= TOL
+    assert nerr(logp.cpu().numpy(), g["fwd0/logp"]) <= TOL
+    if not g.implicit:
+        pr = hp.predict(u, i)
+        assert nerr(pr.cpu().numpy(), g["fwd0/s_inv"]) <= TOL
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("cached_plan", [False, True])
+def test_train_step_matches_reference(case, cached_plan):
+    g = Golden(case)
+    hp = make_hotpath(g)
+    B = min(g.B, g.N)
+    u, i, y, e, w = batch_tensors(g, 0, B, g["envs0"], g["sample_weights0"])
+    grads = {k: torch.full_like(hp.params[k], float("nan")) for k in on.PARAM_ORDER}
+    plan = hp.new_plan(u, i) if cached_plan else None
+    loss = hp.train_step(u, i, y, e, w, plan=plan, grads_out=grads, **step_kwargs(g, float(g["alpha0"])))
+    loss = loss.cpu().numpy()
+    ref_loss = g["epoch_losses"][0]
+    for j, k in enumerate(on.LOSS_KEYS):
+        assert abs(loss[j] - ref_loss[j]) <= TOL * max(abs(ref_loss[j]), 1e-30), (k, loss[j], ref_loss[j])
+    g32, g64 = g.group("grad0"), g.group("grad0_f64")
+    s1, m1, v1 = g.group("step1"), g.group("step1_m"), g.group("step1_v")
+    # fp64 truth of the post-step state: the numpy oracle (pinned to the reference's fp64 run at 1e-14)
+    p64 = on.params_from_state_dict(g.group("init"), np.float64)
+    st64 = on.new_adam_state(p64, np.float64)
+    d = g.data
+    hyp = on.Hyper(alpha=float(g["alpha0"]), lr=g.lr, use_class_rw=g.crw, use_rec_rw=g.rrw, **g.coef)
+    on.train_step(p64, st64, d[:B, 0], d[:B, 1], d[:B, 2], g["envs0"][:B].astype(np.int64),
+                  g["sample_weights0"][:B], hyp, on.Flags(g.implicit, g.roe, g.ree), np.float64)
+    for k, sk in on.STATE_KEYS.items():
+        ours = grads[k].cpu().numpy()
+        assert np.isfinite(ours).all(), k
+        assert nerr(st64["m"][k] * 10, g64[sk]) <= 1e-12      # oracle == reference fp64 gradient
+        ref_self = nerr(g32[sk], g64[sk])
+        assert nerr(ours, g64[sk]) <= max(TOL, 2 * ref_self), (k, nerr(ours, g64[sk]), ref_self)
+        # Adam's g/(|g|+eps) amplifies noise on tiny gradients: the reference's own fp32 run is off its
+        # fp64 run by up to 1e-4 here, so the gate is relative to that
+        ref_self_p = nerr(s1[sk], p64[k])
+        assert nerr(hp.params[k].cpu().numpy(), p64[k]) <= max(TOL, 3 * ref_self_p), \
+            (k, nerr(hp.params[k].cpu().numpy(), p64[k]), ref_self_p)
+        assert nerr(hp.m[k].cpu().numpy(), st64["m"][k]) <= max(TOL, 2 * nerr(m1[sk], st64["m"][k])), k
+        assert nerr(hp.v[k].cpu().numpy(), st64["v"][k]) <= max(2 * TOL, 2 * nerr(v1[sk], st64["v"][k])), k
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_epoch_matches_reference(case):
+    """One full train_a_epoch (train.py:881-910): same batches, alpha schedule, Adam steps.  Multi-step
+    drift is reported by the reference itself at ~1e-4, so the gate is 5e-4 here."""
+    g = Golden(case)
+    hp = make_hotpath(g)
+    bounds = on.mini_batch_bounds(g.N, g.B)
+    losses = []
+    for bi, (lo, hi) in enumerate(bounds):
+        alpha = g.alpha if g.alpha is not None else on.alpha_schedule(bi, 0, len(bounds))
+        u, i, y, e, w = batch_tensors(g, lo, hi, g["envs0"], g["sample_weights0"])
+        losses.append(hp.train_step(u, i, y, e, w, **step_kwargs(g, alpha)).cpu().numpy().copy())
+    losses = np.asarray(losses, dtype=np.float64)
+    ref = g["epoch_losses"]
+    assert losses.shape == ref.shape
+    assert np.abs(losses - ref).max() <= 1e-4 * np.abs(ref).max()
+    e1 = g.group("epoch1")
+    for k, sk in on.STATE_KEYS.items():
+        assert nerr(hp.params[k].cpu().numpy(), e1[sk]) <= 5e-4, k
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("which", ["cluster", "sep"])
+def test_cluster_matches_reference(case, which):
+    """train.py:912-936.  Assignments must equal the reference's except where the two smallest
+    distances are an fp32 tie (counted); histogram and diff count must be consistent."""
+    g = Golden(case)
+    over = g.group("sep") if which == "sep" else None
+    hp = make_hotpath(g, "epoch1", over)
+    d = g.data
+    u = torch.tensor(d[:, 0], device=dev())
+    i = torch.tensor(d[:, 1], device=dev())
+    y = torch.tensor(d[:, 2].astype(np.float32), device=dev())
+    if which == "sep":
+        perm_idx, ref_envs, old = g["sep_perm_idx"], g["sep_envs"], g["cluster_envs"]
+        ref_diff = int(g["sep_diff"])
+    else:
+        perm_idx, ref_envs, old = g["cluster_perm_idx"], g["cluster_envs"], g["envs0"]
+        ref_diff = int(g["cluster_diff"])
+    pidx = torch.tensor(perm_idx.astype(np.int64), device=dev())
+    eps = torch.tensor(g["eps_table"], device=dev())
+    old_t = torch.tensor(old.astype(np.int64), device=dev())
+    new, hist, diff = hp.cluster(u, i, y, pidx, eps, old_t)
+    new = new.cpu().numpy()
+    p = {k: hp.params[k].cpu().numpy() for k in on.PARAM_ORDER}
+    dist = on.cluster_distances(p, d[:, 0], d[:, 1], d[:, 2], on.Flags(g.implicit, g.roe, g.ree))
+    ties = on.near_tie_mask(dist)
+    mism = new != ref_envs
+    assert not (mism & ~ties).any(), f"{(mism & ~ties).sum()} non-tie mismatches"
+    print(f"{case}/{which}: {mism.sum()} mismatches, all among {ties.sum()} fp32 near-ties of {len(new)}")
+    if which == "sep":
+        assert mism.sum() <= max(int(g["sep_near_ties"]), 1) + 2
+    assert np.array_equal(hist.cpu().numpy(), np.bincount(new, minlength=g.K))
+    assert int(diff.item()) == int((new != old).sum())
+    assert abs(int(diff.item()) - ref_diff) <= mism.sum()
+    # stat_envs (train.py:945-957)
+    cw, sw = hp.stat_envs(torch.tensor(new, device=dev()), hist)
+    cnt, cw_ref, sw_ref = on.stat_envs(new, g.K, g.N)
+    assert np.array_equal(cw.cpu().numpy(), cw_ref)
+    assert np.array_equal(sw.cpu().numpy(), sw_ref)
+    if which == "cluster" and mism.sum() == 0:
+        assert np.array_equal(cnt, g["stat_counts"])
+
+
+def test_cluster_without_random_sort_and_hist_only():
+    g = Golden("explicit_d64_k4")
+    hp = make_hotpath(g, "epoch1", g.group("sep"))
+    d = g.data
+    u = torch.tensor(d[:, 0], device=dev())
+    i = torch.tensor(d[:, 1], device=dev())
+    y = torch.tensor(d[:, 2].astype(np.float32), device=dev())
+    new, hist, _ = hp.cluster(u, i, y, None, None, None)
+    p = {k: hp.params[k].cpu().numpy() for k in on.PARAM_ORDER}
+    ref, dist = on.cluster_batch(p, d[:, 0], d[:, 1], d[:, 2], on.Flags(g.implicit, g.roe, g.ree))
+    mism = new.cpu().numpy() != ref
+    assert not (mism & ~on.near_tie_mask(dist)).any()
+    assert np.array_equal(hp.env_hist(new).cpu().numpy(), hist.cpu().numpy())
+
+
+@pytest.mark.parametrize("B,rows", [(0, 10), (1, 1), (1000, 7), (50000, 300), (200000, 1 << 20), (4096, 4096)])
+def test_build_segments_bit_exact(B, rows):
+    """perm must be bit-equal to torch.sort(stable=True)."""
+    from invpref_kdd_2022_b200.engine import build_segments
+    gen = torch.Generator(device="cpu").manual_seed(B + rows)
+    ids = torch.randint(0, rows, (B,), generator=gen, dtype=torch.int64)
+    if B == 4096:
+        ids = torch.randperm(rows, generator=gen)[:B].to(torch.int64)   # all unique
+    perm, seg_row, seg_off = build_segments(ids.to(dev()), rows)
+    rperm, rrow, roff = on.stable_segments(ids.numpy())
+    assert np.array_equal(perm.cpu().numpy(), rperm)
+    assert np.array_equal(seg_row.cpu().numpy(), rrow)
+    assert np.array_equal(seg_off.cpu().numpy(), roff)
+    if B:
+        assert np.array_equal(perm.cpu().numpy(), torch.sort(ids, stable=True).indices.numpy())
+
+
+def _synthetic(U, I, N, K, D, implicit, seed):
+    rng = np.random.default_rng(seed)
+    u = np.floor(U * rng.random(N) ** 1.5).astype(np.int64)
+    i = np.floor(I * rng.random(N) ** 3).astype(np.int64)
+    y = (rng.integers(0, 2, N) if implicit else rng.integers(1, 6, N)).astype(np.float32)
+    e = rng.integers(0, K, N).astype(np.int64)
+    w = rng.random(N).astype(np.float32)
+    p = {"Uinv": rng.normal(0, 0.1, (U, D)), "Iinv": rng.normal(0, 0.1, (I, D)), "Uenv": rng.normal(0, 0.3, (U, D)),
+         "Ienv": rng.normal(0, 0.3, (I, D)), "E": rng.normal(0, 0.5, (K, D)), "W": rng.normal(0, 0.3, (K, D)),
+         "b": rng.normal(0, 0.1, (K,))}
+    p = {k: v.astype(np.float32) for k, v in p.items()}
+    return u, i, y, e, w, p
+
+
+@pytest.mark.parametrize("implicit,K,D,U,I,N", [
+    (False, 4, 64, 3000, 40, 60000),     # hot items: segments of several thousand -> chunked path
+    (True, 6, 40, 500, 2000, 30000),
+    (False, 2, 30, 64, 3, 5000),         # D=30 (float2 rows), 3 items only
+    (True, 5, 128, 200, 100, 4000),      # two vectors per lane
+    (False, 3, 17, 100, 50, 3000),       # odd D (scalar loads)
+    (False, 8, 256, 50, 60, 2000),       # maximum K and D
+    (True, 1, 8, 20, 20, 500),           # single environment
+])
+def test_train_step_matches_oracle_all_geometries(implicit, K, D, U, I, N):
+    """Step vs the fp64 numpy oracle on shapes the fixtures do not cover: long (chunked) segments, every
+    vector geometry, max K / D, reg flags on."""
+    from invpref_kdd_2022_b200.engine import HotPath
+    u, i, y, e, w, p = _synthetic(U, I, N, K, D, implicit, 11 * K + D)
+    flags = on.Flags(implicit, False, True)
+    hyp = on.Hyper(0.8, 1.7, 1.1, 0.6, 0.03, alpha=1.3, lr=1e-2, use_class_rw=True, use_rec_rw=True)
+    p64 = {k: v.astype(np.float64) for k, v in p.items()}
+    st = on.new_adam_state(p64, np.float64)
+    lo, g64 = on.train_step(p64, st, u, i, y, e, w, hyp, flags, np.float64)
+    p32 = {k: v.copy() for k, v in p.items()}
+    on.train_step(p32, on.new_adam_state(p32), u, i, y, e, w, hyp, flags, np.float32)   # fp32 noise floor
+    hp = HotPath({k: torch.tensor(v, device=dev()) for k, v in p.items()}, implicit, False, True, lr=1e-2)
+    grads = {k: torch.zeros_like(hp.params[k]) for k in on.PARAM_ORDER}
+    t = lambda a: torch.tensor(a, device=dev())
+    loss = hp.train_step(t(u), t(i), t(y), t(e), t(w), c_inv=0.8, c_ea=1.7, c_env=1.1, c_L2=0.6, c_L1=0.03, alpha=1.3,
+                         use_class_rw=True, use_rec_rw=True, grads_out=grads).cpu().numpy()
+    for j, k in enumerate(on.LOSS_KEYS):
+        assert abs(loss[j] - float(lo[k])) <= TOL * abs(float(lo[k])), k
+    for k in on.PARAM_ORDER:
+        assert nerr(grads[k].cpu().numpy(), g64[k]) <= TOL, (k, nerr(grads[k].cpu().numpy(), g64[k]))
+        # Adam amplifies noise on tiny gradients: gate relative to an fp32 run of the oracle itself
+        assert nerr(hp.params[k].cpu().numpy(), p64[k]) <= max(TOL, 3 * nerr(p32[k], p64[k])), k
+        assert nerr(hp.m[k].cpu().numpy(), st["m"][k]) <= TOL, k
+        assert nerr(hp.v[k].cpu().numpy(), st["v"][k]) <= 2 * TOL, k
+
+
+def test_train_step_is_deterministic_and_dense():
+    """Two runs from the same state are bit-identical (no atomics in the float path), and rows that a
+    later batch does not touch still move by momentum (dense Adam, SURVEY.md §7 hard part 2)."""
+    from invpref_kdd_2022_b200.engine import HotPath
+    u, i, y, e, w, p = _synthetic(5000, 50, 80000, 4, 64, False, 3)
+    t = lambda a: torch.tensor(a, device=dev())
+    outs = []
+    for _ in range(2):
+        hp = HotPath({k: t(v) for k, v in p.items()}, False, True, False, lr=1e-2)
+        kw = dict(c_inv=1.0, c_ea=1.0, c_env=1.0, c_L2=0.1, c_L1=0.01, alpha=1.0, use_class_rw=False, use_rec_rw=False)
+        l1 = hp.train_step(t(u), t(i), t(y), t(e), None, **kw).clone()
+        before = hp.params["Uinv"].clone()
+        # second step touches only the first 100 interactions: every other touched row moves by momentum
+        l2 = hp.train_step(t(u[:100]), t(i[:100]), t(y[:100]), t(e[:100]), None, **kw).clone()
+        outs.append((l1, l2, {k: hp.params[k].clone() for k in on.PARAM_ORDER}))
+        moved = (hp.params["Uinv"] != before).any(dim=1).cpu().numpy()
+        touched1 = np.zeros(5000, bool); touched1[u] = True
+        touched2 = np.zeros(5000, bool); touched2[u[:100]] = True
+        assert moved[touched1 & ~touched2].all()
+        assert not moved[~touched1 & ~touched2].any()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for k in on.PARAM_ORDER:
+        assert torch.equal(outs[0][2][k], outs[1][2][k]), k
+
+
+def test_backward_matches_oracle():
+    """invpref_backward (autograd path): gradients of sum(a*s_inv) + sum(b*s_env) + sum(c*logp)."""
+    from invpref_kdd_2022_b200.engine import HotPath
+    for implicit in (False, True):
+        u, i, y, e, w, p = _synthetic(300, 40, 5000, 4, 40, implicit, 5)
+        rng = np.random.default_rng(0)
+        ga, gb, gc = rng.normal(size=5000), rng.normal(size=5000), rng.normal(size=(5000, 4))
+        tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()}
+        a, c = tp["Uinv"][u], tp["Iinv"][i]
+        pref = a * c
+        z1 = pref.sum(1)
+        z2 = (tp["Uenv"][u] * tp["Ienv"][i] * tp["E"][e]).sum(1)
+        if implicit:
+            s_inv = torch.sigmoid(z1); s_env = s_inv * torch.sigmoid(z2)
+        else:
+            s_inv = z1; s_env = z1 + z2
+        alpha = 0.7
+        rev = pref.detach() + (-alpha) * (pref - pref.detach())      # gradient reversal (functions.py:13-16)
+        logp = torch.log_softmax(rev @ tp["W"].T + tp["b"], dim=1)
+        (s_inv * torch.tensor(ga) + s_env * torch.tensor(gb)).sum().add((logp * torch.tensor(gc)).sum()).backward()
+        hp = HotPath({k: torch.tensor(v, device=dev()) for k, v in p.items()}, implicit, False, True)
+        grads = {k: torch.zeros_like(hp.params[k]) for k in on.PARAM_ORDER}
+        t = lambda x, dt=None: torch.tensor(x, device=dev(), dtype=dt)
+        hp.backward(t(u), t(i), t(e), alpha, t(ga, torch.float32), t(gb, torch.float32), t(gc, torch.float32), grads)
+        for k in on.PARAM_ORDER:
+            ref = tp[k].grad.numpy()
+            if k == "W" or k == "b":
+                pass
+            assert nerr(grads[k].cpu().numpy(), ref) <= TOL, (implicit, k, nerr(grads[k].cpu().numpy(), ref))
+
+
+def test_error_paths():
+    from invpref_kdd_2022_b200 import _lib
+    from invpref_kdd_2022_b200.engine import HotPath
+    u, i, y, e, w, p = _synthetic(10, 10, 50, 2, 8, False, 1)
+    with pytest.raises(RuntimeError):
+        HotPath({k: torch.tensor(v) for k, v in p.items()}, False, False, True)       # CPU tensors: no fallback
+    desc = _lib.make_desc(10, 10, 9, 8, 0, 0, 0)
+    with pytest.raises(RuntimeError, match="environments"):
+        _lib.workspace_bytes(desc, 10)
+    desc = _lib.make_desc(10, 10, 2, 300, 0, 0, 0)
+    with pytest.raises(RuntimeError, match="dimension"):
+        _lib.workspace_bytes(desc, 10)
+    hp = HotPath({k: torch.tensor(v, device=dev()) for k, v in p.items()}, False, False, True)
+    t = lambda a: torch.tensor(a, device=dev())
+    with pytest.raises(RuntimeError):   # re-weighting requested without weights
+        hp.train_step(t(u), t(i), t(y), t(e), None, c_inv=1, c_ea=1, c_env=1, c_L2=0, c_L1=0, alpha=1,
+                      use_class_rw=True, use_rec_rw=False)
+    assert hp.step == 0
