@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- InvPref hot path on B200: train interactions/s (fwd + bwd + Adam) and env re-assignment
+samples/s, with the HBM roofline fraction and the reference's CPU path beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c4|c3|c2] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definitions:
+  value      whole-job train interactions/s, inputs + cached sort-segment plans resident in HBM;
+  e2e        the same through the public call with HOST (pinned) batch buffers: H2D of the batch, plan
+             build, step, D2H of the six losses, every step;
+  roofline   algorithmic bytes / CUDA-event time, for the whole fused step and for its
+             dominant kernel, against MEASURED_PEAKS.json;
+  cluster    env re-assignment samples/s and its roofline;
+  cpu_baseline  the oracle's torch-eager port (same ATen op sequence as the reference trainer) timed on
+             the box's host cores on a bounded, proportionally scaled sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# SURVEY.md §8d workloads.  Coefficients: the Yahoo explicit / MovieLens / MIND driver values.
+WORKLOADS = {
+    "c5": dict(name="synthetic 10M users x 1M items, dim 64, K=4, explicit, B=4194304", U=10_000_000, I=1_000_000,
+               D=64, K=4, B=4_194_304, implicit=False, roe=True, ree=False, crw=True, rrw=True, lr=1e-3,
+               coef=dict(c_inv=0.007375309563638757, c_ea=7.207790368836971, c_env=7.30272189219841,
+                         c_L2=5.105587170019545, c_L1=0.004098813161410509)),
+    "c4": dict(name="MIND-shaped synthetic, 50000 x 51283, dim 40, K=6, implicit, B=262144", U=50_000, I=51_283,
+               D=40, K=6, B=262_144, implicit=True, roe=True, ree=False, crw=True, rrw=False, lr=1e-3,
+               coef=dict(c_inv=0.41343891722673093, c_ea=9.833594297680568, c_env=7.521558049068597,
+                         c_L2=4.324061954456766, c_L1=0.33322012936680223)),
+    "c3": dict(name="MovieLens-shaped synthetic, 6040 x 3706, dim 40, K=2, implicit, B=65536", U=6_040, I=3_706,
+               D=40, K=2, B=65_536, implicit=True, roe=True, ree=True, crw=False, rrw=True, lr=1e-2,
+               coef=dict(c_inv=8.909348155983732, c_ea=1.233057369609993, c_env=8.064376793624795,
+                         c_L2=3.4987474005653665, c_L1=0.9355983539586914)),
+    "c2": dict(name="Yahoo!R3-shaped explicit, 15400 x 1000, dim 40, K=5, B=131072", U=15_400, I=1_000,
+               D=40, K=5, B=131_072, implicit=False, roe=True, ree=False, crw=False, rrw=False, lr=1e-3,
+               coef=dict(c_inv=0.007375309563638757, c_ea=7.207790368836971, c_env=7.30272189219841,
+                         c_L2=5.105587170019545, c_L1=0.004098813161410509)),
+}
+
+
+def synth_batches(w, nb, seed=20220814, scale=1.0):
+    """SURVEY.md §8d generators: mild user skew (r^1.5), hot-item skew (r^3)."""
+    U, I, B = max(int(w["U"] * scale), 8), max(int(w["I"] * scale), 8), max(int(w["B"] * scale), 8)
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(nb):
+        u = np.floor(U * rng.random(B) ** 1.5).astype(np.int64)
+        i = np.floor(I * rng.random(B) ** 3).astype(np.int64)
+        y = (rng.integers(0, 2, B) if w["implicit"] else rng.integers(1, 6, B)).astype(np.float32)
+        e = rng.integers(0, w["K"], B).astype(np.int64)
+        out.append((u, i, y, e))
+    return U, I, B, out
+
+
+def step_bytes(B, D, K, P):
+    """algorithmic bytes of one train step."""
+    return B * (32 * D + 56 + 8 * K) + 24 * P
+
+
+def cluster_bytes_per_sample(D):
+    """16 D + 44."""
+    return 16 * D + 44
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_tables(w, dev, U=None, I=None, seed=17373331):
+    U, I = U or w["U"], I or w["I"]
+    g = torch.Generator(device=dev).manual_seed(seed)
+    shp = {"Uinv": (U, w["D"]), "Iinv": (I, w["D"]), "Uenv": (U, w["D"]), "Ienv": (I, w["D"]),
+           "E": (w["K"], w["D"]), "W": (w["K"], w["D"]), "b": (w["K"],)}
+    out = {}
+    for k, s in shp.items():
+        std = 0.01 if k not in ("W", "b") else 0.1
+        out[k] = torch.randn(s, generator=g, device=dev, dtype=torch.float32) * std
+    return out
+
+
+def cpu_baseline(w, threads, budget_s=25.0, scale=None, steps=2, warmup=1):
+    """The oracle's torch-eager port on the host cores, on a proportionally scaled replica of the
+    workload (U, I and B divided by the same factor, so dense-Adam work per interaction is unchanged)."""
+    from oracle import invpref_numpy as on
+    from oracle import invpref_torch_cpu as ot
+    torch.set_num_threads(threads)
+    if scale is None:
+        scale = min(1.0, 262_144 / w["B"])
+    U, I, B, batches = synth_batches(w, 1, scale=scale)
+    P = ot.random_params(U, I, w["K"], w["D"])
+    hp = on.Hyper(alpha=1.0, lr=w["lr"], use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
+    tr = ot.CpuTrainer(P, on.Flags(w["implicit"], w["roe"], w["ree"]), hp)
+    u, i, y, e = (torch.from_numpy(a) for a in batches[0])
+    wts = torch.rand(B)
+    times = []
+    t_all = time.perf_counter()
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        tr.train_a_batch(u, i, y, e, wts, 1.0)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_all > budget_s and len(times) >= 1:
+            break
+    t_step = statistics.median(times)
+    pidx = torch.randint(0, tr.eps_table.shape[0], (B,))
+    t0 = time.perf_counter()
+    tr.cluster_a_batch(u, i, y, pidx)
+    t_cl = time.perf_counter() - t0
+    sample = (f"1/{round(1 / scale)}-scale replica (U={U}, I={I}, B={B}, D={w['D']}, K={w['K']}): "
+              f"{len(times)} train_a_batch after {warmup} warm-up; 1 cluster_a_batch")
+    return {"value": B / t_step, "unit": "interactions/s", "cores": threads, "kind": "port", "sample": sample,
+            "ms_per_step": t_step * 1e3, "cluster_samples_per_s": B / t_cl}
+
+
+def run_reference(args, w):
+    threads = os.cpu_count() or 1
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_baseline(w, threads, budget_s=150.0, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "train interactions/sec (fwd+bwd+Adam)", "value": r["value"],
+            "unit": "interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": w["name"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cluster": {"value": r["cluster_samples_per_s"], "unit": "samples/s"},
+            "e2e": {"value": r["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours_single(args, w):
+    from invpref_kdd_2022_b200 import _lib
+    from invpref_kdd_2022_b200.engine import HotPath
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    K, D = w["K"], w["D"]
+    nb = max(1, min(args.nbatch, args.steps + args.warmup))
+    U, I, B, batches = synth_batches(w, nb)
+    hp = HotPath(make_tables(w, dev), w["implicit"], w["roe"], w["ree"], lr=w["lr"])
+    P = sum(t.numel() for t in hp.params.values())
+    dbatches = []
+    for (u, i, y, e) in batches:
+        u, i, y, e = (torch.from_numpy(a).to(dev) for a in (u, i, y, e))
+        cw, sw = hp.stat_envs(e, hp.env_hist(e))
+        dbatches.append((u, i, y, e, sw))
+    plans = [hp.new_plan(b[0], b[1]) for b in dbatches]
+    kw = dict(alpha=1.0, use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
+    losses = torch.zeros((args.steps + args.warmup, 6), device=dev)
+
+    def step(s, plan=True):
+        b = dbatches[s % nb]
+        hp.train_step(b[0], b[1], b[2], b[3], b[4], plan=plans[s % nb] if plan else None, loss_out=losses[s], **kw)
+
+    for s in range(args.warmup):
+        step(s)
+    torch.cuda.synchronize()
+    _lib.profile_enable(args.steps)
+    clocks = ClockSampler(dev.index)
+    clocks.start()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for s in range(args.warmup, args.warmup + args.steps):
+        step(s)
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    phases = np.asarray(_lib.profile_read_all())
+    _lib.profile_enable(0)
+    assert torch.isfinite(losses).all(), "non-finite loss in the timed region"
+    peak, peak_src = measured_peaks()
+    sbytes = step_bytes(B, D, K, P)
+    ph_ms = dict(zip(_lib.PHASES, phases.mean(axis=0).tolist())) if len(phases) else {}
+    # dominant kernel: the dense Adam sweep over user rows without a gradient (theta, m, v read + write)
+    n_seg_u = int(plans[0][:4].view(torch.int32)[0].item())          # plan header: unique users of batch 0
+    sweep_bytes = (U - n_seg_u) * 2 * D * 4 * 6
+    roof = {"bound": "hbm", "kernel": "fused train step (all kernels)", "achieved": sbytes / (ms * 1e-3) / 1e9,
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None}
+    roof["frac"] = roof["achieved"] / peak
+    if ph_ms.get("sweep_users"):
+        a = sweep_bytes / (ph_ms["sweep_users"] * 1e-3) / 1e9
+        roof["dominant_kernel"] = {"kernel": "sweep_kernel (user tables)", "bytes_per_launch": sweep_bytes,
+                                   "ms_per_launch": ph_ms["sweep_users"], "achieved": a, "frac": a / peak}
+    roof["phase_ms"] = ph_ms
+
+    # ---- env re-assignment: all nb batches as one slice, as train.py:912-936 does ----
+    cu, ci, cy, ce = (torch.cat([b[j] for b in dbatches]) for j in range(4))
+    Nc = cu.numel()
+    import itertools
+    base = torch.Tensor([1e-10 * (1e-1 ** k) for k in range(K)])
+    eps = torch.Tensor(list(itertools.permutations(base))).to(dev)                    # train.py:763-769
+    pidx = torch.from_numpy(np.random.default_rng(1).integers(0, eps.shape[0], Nc)).to(dev)
+    for _ in range(2):
+        hp.cluster(cu, ci, cy, pidx, eps, ce)
+    torch.cuda.synchronize()
+    reps = 5
+    ev0.record()
+    for _ in range(reps):
+        new_e, hist, diff = hp.cluster(cu, ci, cy, pidx, eps, ce)
+        hp.stat_envs(new_e, hist)
+    ev1.record()
+    torch.cuda.synchronize()
+    cms = ev0.elapsed_time(ev1) / reps
+    cb = cluster_bytes_per_sample(D) * Nc
+    cluster = {"value": Nc / (cms * 1e-3), "unit": "samples/s", "samples": Nc, "ms": cms,
+               "roofline": {"bound": "hbm", "achieved": cb / (cms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": cb / (cms * 1e-3) / 1e9 / peak}}
+
+    # ---- e2e: host (pinned) batch -> H2D -> plan build + step -> D2H of the six losses, every step ----
+    hb = [tuple(t.cpu().pin_memory() for t in b) for b in dbatches[:min(nb, 4)]]
+    stage = [torch.empty_like(t, device=dev) for t in dbatches[0]]
+    h_loss = torch.empty(6).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_step(s):
+        for dst, src in zip(stage, hb[s % len(hb)]):
+            dst.copy_(src, non_blocking=True)
+        out = hp.train_step(stage[0], stage[1], stage[2], stage[3], stage[4], plan=None, **kw)
+        h_loss.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(h_loss[5])
+
+    e2e_step(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        e2e_step(s)
+    e2e_ms = (time.perf_counter() - t0) / e2e_steps * 1e3
+    h2d = sum(t.numel() * t.element_size() for t in hb[0])
+    e2e = {"value": B / (e2e_ms * 1e-3), "unit": "interactions/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 24, "steps": e2e_steps,
+           "note": "host pinned batch (u,i,y,e,w) copied H2D, sort-segment plan rebuilt, step, 6 losses read back"}
+
+    line = {"metric": "train interactions/sec (fwd+bwd+Adam)", "value": B / (ms * 1e-3), "unit": "interactions/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "global_batch": B, "params": P, "distinct_batches": nb,
+                       "l2": "inputs larger than L2 (tables %.1f GB + Adam state)" % (P * 4 / 1e9)
+                       if P * 4 > 2.5e8 else "tables fit in L2 (no flush): launch-bound config",
+                       "parallelism": "1 GPU"},
+            "roofline": roof, "cluster": cluster, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(w, os.cpu_count() or 1)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--nbatch", type=int, default=8, help="distinct synthetic batches cycled through")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU baseline)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        from invpref_kdd_2022_b200 import dist_bench
+        dist_bench.run(args, w)
+        return
+    run_ours_single(args, w)
+
+
+if __name__ == "__main__":
+    main()

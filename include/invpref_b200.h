@@ -172,6 +172,18 @@ int invpref_env_hist(const int64_t* envs, int64_t N, int32_t n_envs, int64_t* hi
 /* Number of kernels the library has launched in this process (bench.py's gpu_launches). */
 int64_t invpref_launch_count(void);
 
+/* ---- per-phase device timing (bench.py's roofline) ----------------------------------------------
+ * invpref_profile_enable(n > 0): the next n calls of invpref_train_step record CUDA events between
+ * their kernels on the call's stream (no synchronisation); n = 0 disables and frees the events.
+ * invpref_profile_read(step, out_ms_host): after the caller has synchronised the stream, elapsed
+ * milliseconds of each phase of recorded step `step` (0-based), INVPREF_NUM_PHASES floats in the
+ * order: plan build, forward, item chunks, user chunks, item rows, user rows, item sweep, user sweep,
+ * tail.  invpref_profile_steps(): number of steps recorded since the last enable. */
+#define INVPREF_NUM_PHASES 9
+int invpref_profile_enable(int max_steps);
+int invpref_profile_steps(void);
+int invpref_profile_read(int step, float* out_ms_host);
+
 #ifdef __cplusplus
 }
 #endif

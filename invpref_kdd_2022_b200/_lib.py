@@ -22,8 +22,11 @@ EXPORTS = (
     "invpref_strerror", "invpref_abi_version", "invpref_workspace_bytes", "invpref_plan_bytes",
     "invpref_build_plan", "invpref_build_segments", "invpref_forward", "invpref_predict",
     "invpref_backward", "invpref_train_step", "invpref_cluster", "invpref_stat_envs",
-    "invpref_env_hist", "invpref_launch_count",
+    "invpref_env_hist", "invpref_launch_count", "invpref_profile_enable", "invpref_profile_steps",
+    "invpref_profile_read",
 )
+PHASES = ("plan", "forward", "chunks_items", "chunks_users", "rows_items", "rows_users", "sweep_items",
+          "sweep_users", "tail")
 
 
 class Desc(C.Structure):
@@ -83,6 +86,8 @@ def load() -> C.CDLL:
     lib.invpref_cluster.argtypes = [C.POINTER(Desc), C.POINTER(Params), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]
     lib.invpref_stat_envs.argtypes = [vp, i64, C.c_int32, vp, vp, vp, vp]
     lib.invpref_env_hist.argtypes = [vp, i64, C.c_int32, vp, vp]
+    lib.invpref_profile_enable.argtypes = [C.c_int]
+    lib.invpref_profile_read.argtypes = [C.c_int, C.POINTER(C.c_float)]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("invpref_strerror", "invpref_abi_version", "invpref_launch_count"):
@@ -143,3 +148,18 @@ def plan_bytes(desc: Desc, max_batch: int) -> int:
 
 def launch_count() -> int:
     return int(load().invpref_launch_count())
+
+
+def profile_enable(max_steps: int) -> None:
+    check(load().invpref_profile_enable(int(max_steps)), "profile_enable")
+
+
+def profile_read_all():
+    """[steps][phase] milliseconds of the recorded train steps (call after torch.cuda.synchronize())."""
+    lib = load()
+    out = []
+    buf = (C.c_float * len(PHASES))()
+    for s in range(lib.invpref_profile_steps()):
+        check(lib.invpref_profile_read(s, buf), "profile_read")
+        out.append([float(x) for x in buf])
+    return out

@@ -4,10 +4,32 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <vector>
+
 namespace invpref {
 long long g_launch_count = 0;
 
 namespace {
+
+// per-phase CUDA events of the profiled train steps (invpref_profile_*)
+constexpr int NEV = INVPREF_NUM_PHASES + 1;
+std::vector<cudaEvent_t> g_prof_events;
+int g_prof_max = 0, g_prof_n = 0;
+
+struct PhaseMark {
+    cudaEvent_t* ev;
+    cudaStream_t st;
+    int idx;
+    PhaseMark(cudaStream_t s) : ev(nullptr), st(s), idx(0) {
+        if (g_prof_n < g_prof_max) ev = &g_prof_events[(size_t)g_prof_n * NEV];
+    }
+    void mark() {
+        if (ev && idx < NEV) cudaEventRecord(ev[idx++], st);
+    }
+    void done() {
+        if (ev) ++g_prof_n;
+    }
+};
 
 inline bool aligned_for(const void* p, int vec) { return ((uintptr_t)p % (size_t)(vec * 4)) == 0; }
 
@@ -74,6 +96,30 @@ const char* invpref_strerror(int status) {
 int invpref_abi_version(void) { return INVPREF_ABI_VERSION; }
 
 int64_t invpref_launch_count(void) { return (int64_t)g_launch_count; }
+
+int invpref_profile_enable(int max_steps) {
+    for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
+    g_prof_events.clear();
+    g_prof_max = 0;
+    g_prof_n = 0;
+    if (max_steps <= 0) return INVPREF_OK;
+    if (max_steps > 4096) return INVPREF_ERR_BAD_ARG;
+    g_prof_events.resize((size_t)max_steps * NEV);
+    for (auto& e : g_prof_events)
+        if (cudaEventCreate(&e) != cudaSuccess) return INVPREF_ERR_CUDA;
+    g_prof_max = max_steps;
+    return INVPREF_OK;
+}
+
+int invpref_profile_steps(void) { return g_prof_n; }
+
+int invpref_profile_read(int step, float* out_ms_host) {
+    if (step < 0 || step >= g_prof_n || !out_ms_host) return INVPREF_ERR_BAD_ARG;
+    cudaEvent_t* ev = &g_prof_events[(size_t)step * NEV];
+    for (int i = 0; i < INVPREF_NUM_PHASES; ++i)
+        if (cudaEventElapsedTime(&out_ms_host[i], ev[i], ev[i + 1]) != cudaSuccess) return INVPREF_ERR_CUDA;
+    return INVPREF_OK;
+}
 
 int invpref_workspace_bytes(const invpref_desc* desc, int64_t max_batch, size_t* out_bytes) {
     Geometry g;
@@ -170,6 +216,8 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     Workspace w;
     if (ws_bytes < workspace_bytes_impl(desc, g, B, &w, (char*)ws)) return INVPREF_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    PhaseMark pm(st);
+    pm.mark();
 
     const char* plan_base = (const char*)plan;
     if (plan_base == nullptr) {
@@ -179,6 +227,7 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     }
     PlanSide pu, pi;
     carve_plan(desc, B, (char*)plan_base, &pu, &pi);
+    pm.mark();
 
     // (1)+(2) fused forward, losses, per-interaction gradients, dW/db/dE partials
     FwdTrainArgs f;
@@ -195,6 +244,7 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     f.up_s_inv = f.up_s_env = f.up_logp = nullptr; f.generic = 0;
     const int fgrid = fwd_train_grid(B);
     if ((rc = launch_fwd_train(g, f, fgrid, st)) != INVPREF_OK) return rc;
+    pm.mark();
 
     // (3)+(4) segmented backward feeding Adam, per side
     const AdamScalars as = make_adam(hyper);
@@ -216,11 +266,17 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     si.reg2 = su.reg2; si.reg1 = su.reg1; si.adam = as;
 
     if ((rc = launch_bwd_chunks(g, si, st)) != INVPREF_OK) return rc;
+    pm.mark();
     if ((rc = launch_bwd_chunks(g, su, st)) != INVPREF_OK) return rc;
+    pm.mark();
     if ((rc = launch_bwd_rows(g, si, EPI_ADAM, st)) != INVPREF_OK) return rc;
+    pm.mark();
     if ((rc = launch_bwd_rows(g, su, EPI_ADAM, st)) != INVPREF_OK) return rc;
+    pm.mark();
     if ((rc = launch_sweep(g, si, st)) != INVPREF_OK) return rc;
+    pm.mark();
     if ((rc = launch_sweep(g, su, st)) != INVPREF_OK) return rc;
+    pm.mark();
 
     // losses, E / W / b gradients and their Adam update
     TailArgs t;
@@ -234,7 +290,10 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     t.gE = grads_out ? grads_out->E : nullptr; t.gW = grads_out ? grads_out->W : nullptr;
     t.gb = grads_out ? grads_out->b : nullptr;
     t.loss_out = loss_out; t.adam = as; t.epi = EPI_ADAM;
-    return launch_tail(t, st);
+    rc = launch_tail(t, st);
+    pm.mark();
+    pm.done();
+    return rc;
 }
 
 int invpref_backward(const invpref_desc* desc, const invpref_params* params, const invpref_batch* batch, double alpha,

@@ -1,0 +1,218 @@
+"""InvPref trainers with the reference's constructor and method signatures (reference
+``train.py:16-342`` ImplicitTrainManager, ``train.py:693-1019`` ExplicitTrainManager); every batch is
+ONE call into ``libinvpref_b200.so`` instead of ~250 ATen ops, and ``cluster()`` is one kernel over the
+whole dataset instead of K forwards per batch.
+
+Kept from the reference, because results depend on them:
+  * batches are the sequential, unshuffled slices of ``utils.mini_batch`` (utils.py:12-19);
+  * the initial environments come from ``np.random.randint`` at construction (train.py:711) and the
+    tie-break indices from one ``np.random.randint(0, K!, b)`` per cluster batch (train.py:870-871), drawn
+    on the host from numpy's global stream in the reference's order;
+  * alpha schedule (train.py:891-894), stat_envs weighting (train.py:945-957), loss-dict keys and the
+    per-epoch ``np.mean`` of per-batch python floats (utils.py:181-183).
+"""
+from __future__ import annotations
+
+import itertools
+import math
+
+import numpy as np
+import torch
+
+from ._lib import LOSS_KEYS
+from .utils import _mean_merge_dict_func, merge_dict, mini_batch, transfer_loss_dict_to_line_str
+
+
+class _InvPrefTrainManager:
+    implicit = False
+
+    def __init__(
+            self, model, evaluator, device: torch.device, training_data: torch.Tensor, batch_size: int,
+            epochs: int, cluster_interval: int, evaluate_interval: int, lr: float,
+            invariant_coe: float, env_aware_coe: float, env_coe: float, L2_coe: float, L1_coe: float,
+            alpha: float = None, use_class_re_weight: bool = False, test_begin_epoch: int = 0,
+            begin_cluster_epoch: int = None, stop_cluster_epoch: int = None, cluster_use_random_sort: bool = True,
+            use_recommend_re_weight: bool = True, cache_plans: bool = True
+    ):
+        self.model = model
+        self.evaluator = evaluator
+        self.envs_num: int = model.env_num
+        self.device = device
+        n = training_data.shape[0]
+        # contiguous copies of the three columns (the reference keeps stride-3 views, train.py:708-710)
+        self.users_tensor = training_data[:, 0].contiguous().to(device)
+        self.items_tensor = training_data[:, 1].contiguous().to(device)
+        self.scores_tensor = training_data[:, 2].float().contiguous().to(device)
+        self.envs = torch.LongTensor(np.random.randint(0, self.envs_num, n)).to(device)       # train.py:711
+        self.cluster_interval, self.evaluate_interval = cluster_interval, evaluate_interval
+        self.batch_size, self.epochs = batch_size, epochs
+        self.lr = lr
+        self.invariant_coe, self.env_aware_coe, self.env_coe = invariant_coe, env_aware_coe, env_coe
+        self.L2_coe, self.L1_coe = L2_coe, L1_coe
+        self.epoch_cnt: int = 0
+        self.batch_num = math.ceil(n / batch_size)
+        self.each_env_count = dict()
+        if alpha is None:                                                                      # train.py:740-745
+            self.alpha, self.update_alpha = 0., True
+        else:
+            self.alpha, self.update_alpha = alpha, False
+        self.use_class_re_weight = use_class_re_weight
+        self.use_recommend_re_weight = use_recommend_re_weight
+        self.sample_weights = torch.zeros(n, dtype=torch.float32, device=device)
+        self.class_weights = torch.zeros(self.envs_num, dtype=torch.float32, device=device)
+        self.test_begin_epoch = test_begin_epoch
+        self.begin_cluster_epoch, self.stop_cluster_epoch = begin_cluster_epoch, stop_cluster_epoch
+        self.eps_random_tensor = self._init_eps().to(device)
+        self.cluster_use_random_sort = cluster_use_random_sort
+        self.const_env_tensor_list = [torch.full((n,), k, dtype=torch.int64, device=device)
+                                      for k in range(self.envs_num)]                           # train.py:758-761
+        # fused engine bound to the model's parameter storages; holds the Adam state (train.py:718)
+        self.engine = model.hot_path(lr=lr)
+        self.engine.lr = float(lr)
+        self.optimizer = self.engine           # exposes .m / .v / .step (exp_avg, exp_avg_sq, step)
+        self.cache_plans = cache_plans
+        self._plans = {}
+        self._loss_rows = None
+
+    def _init_eps(self) -> torch.Tensor:
+        """train.py:763-769, same torch expression so the fp32 table is bit-identical."""
+        base_eps = 1e-10
+        eps_list = [base_eps * (1e-1 ** idx) for idx in range(self.envs_num)]
+        temp = torch.Tensor(eps_list)
+        return torch.Tensor(list(itertools.permutations(temp)))
+
+    # ---- train ----------------------------------------------------------------------------------
+    def _plan_for(self, key, users, items):
+        if not self.cache_plans or key is None:
+            return None
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self.engine.new_plan(users, items)
+            self._plans[key] = plan
+        return plan
+
+    def _step(self, users, items, scores, envs, weights, alpha, loss_out=None, plan_key=None):
+        users, items, envs = users.contiguous(), items.contiguous(), envs.contiguous()
+        assert users.shape == items.shape == scores.shape == envs.shape          # train.py:789-790
+        return self.engine.train_step(
+            users, items, scores.contiguous(), envs, weights.contiguous() if weights is not None else None,
+            c_inv=self.invariant_coe, c_ea=self.env_aware_coe, c_env=self.env_coe, c_L2=self.L2_coe,
+            c_L1=self.L1_coe, alpha=alpha, use_class_rw=self.use_class_re_weight,
+            use_rec_rw=self.use_recommend_re_weight, plan=self._plan_for(plan_key, users, items), loss_out=loss_out)
+
+    def train_a_batch(self, batch_users_tensor, batch_items_tensor, batch_scores_tensor, batch_envs_tensor,
+                      batch_sample_weights, alpha) -> dict:
+        """train.py:771-844.  One fused step; returns the six losses as python floats (one sync)."""
+        out = self._step(batch_users_tensor, batch_items_tensor, batch_scores_tensor, batch_envs_tensor,
+                         batch_sample_weights, alpha)
+        vals = out.cpu().tolist()
+        return dict(zip(LOSS_KEYS, vals))
+
+    def train_a_epoch(self) -> dict:
+        """train.py:881-910.  Losses stay on the device until the end of the epoch (one sync per epoch
+        instead of six per batch); the returned dict is the same np.mean of per-batch floats."""
+        self.model.train()
+        if self._loss_rows is None or self._loss_rows.shape[0] != self.batch_num:
+            self._loss_rows = torch.zeros((self.batch_num, 6), dtype=torch.float32, device=self.device)
+        for batch_index, (u, i, y, e, w) in enumerate(mini_batch(
+                self.batch_size, self.users_tensor, self.items_tensor, self.scores_tensor, self.envs,
+                self.sample_weights)):
+            if self.update_alpha:                                                 # train.py:891-894
+                p = float(batch_index + (self.epoch_cnt + 1) * self.batch_num) / float(
+                    (self.epoch_cnt + 1) * self.batch_num)
+                self.alpha = 2. / (1. + np.exp(-10. * p)) - 1.
+            self._step(u, i, y, e, w, self.alpha, loss_out=self._loss_rows[batch_index], plan_key=batch_index)
+        self.epoch_cnt += 1
+        rows = self._loss_rows.cpu().tolist()
+        return merge_dict([dict(zip(LOSS_KEYS, r)) for r in rows], _mean_merge_dict_func)
+
+    # ---- EM re-assignment ---------------------------------------------------------------------------
+    def cluster_a_batch(self, batch_users_tensor, batch_items_tensor, batch_scores_tensor) -> torch.Tensor:
+        """train.py:846-879 for one batch (draws its tie-break indices like the reference)."""
+        perm = None
+        if self.cluster_use_random_sort:
+            idx = np.random.randint(0, self.eps_random_tensor.shape[0], batch_users_tensor.shape[0])
+            perm = torch.from_numpy(idx.astype(np.int64)).to(self.device)
+        new_envs, _, _ = self.engine.cluster(batch_users_tensor.contiguous(), batch_items_tensor.contiguous(),
+                                             batch_scores_tensor.contiguous(), perm,
+                                             self.eps_random_tensor if perm is not None else None, None)
+        return new_envs
+
+    def cluster(self) -> int:
+        """train.py:912-936.  The host draws one randint per cluster batch, in order (so the numpy stream
+        advances exactly as in the reference); the device does the whole dataset in one launch."""
+        self.model.eval()
+        n = self.users_tensor.shape[0]
+        perm = None
+        if self.cluster_use_random_sort:
+            draws = [np.random.randint(0, self.eps_random_tensor.shape[0], min(self.batch_size, n - lo))
+                     for lo in range(0, n, self.batch_size)]
+            perm = torch.from_numpy(np.concatenate(draws).astype(np.int64)).to(self.device)
+        new_envs, hist, diff = self.engine.cluster(self.users_tensor, self.items_tensor, self.scores_tensor, perm,
+                                                   self.eps_random_tensor if perm is not None else None, self.envs)
+        self.envs = new_envs
+        self._hist = hist
+        return int(diff.item())
+
+    def update_each_env_count(self):
+        cnt = self.engine.env_hist(self.envs).cpu().tolist()
+        self.each_env_count.update({k: c for k, c in enumerate(cnt)})
+
+    def stat_envs(self) -> dict:
+        """train.py:945-957: histogram, class_weights (frequency, float64 -> fp32), sample_weights."""
+        hist = self.engine.env_hist(self.envs)
+        self.class_weights, self.sample_weights = self.engine.stat_envs(self.envs, hist)
+        return {k: int(c) for k, c in enumerate(hist.cpu().tolist())}
+
+    # ---- epoch loop -----------------------------------------------------------------------------------
+    def train(self, silent: bool = False, auto: bool = False):
+        """train.py:959-1019; returns the same triple of (results, epochs) tuples."""
+        test_result_list, test_epoch_list = [], []
+        cluster_diff_num_list, cluster_epoch_list, envs_cnt_list = [], [], []
+        loss_result_list, train_epoch_index_list = [], []
+        verbose = not silent and not auto
+
+        def evaluate():
+            res = self.evaluator.evaluate()
+            test_result_list.append(res)
+            test_epoch_list.append(self.epoch_cnt)
+            if verbose:
+                print('test at epoch:', self.epoch_cnt)
+                print(transfer_loss_dict_to_line_str(res))
+
+        evaluate()
+        self.stat_envs()
+        while self.epoch_cnt < self.epochs:
+            loss_dict = self.train_a_epoch()
+            train_epoch_index_list.append(self.epoch_cnt)
+            loss_result_list.append(loss_dict)
+            if verbose:
+                print('train epoch:', self.epoch_cnt)
+                print(transfer_loss_dict_to_line_str(loss_dict))
+            if (self.epoch_cnt % self.evaluate_interval) == 0 and self.epoch_cnt >= self.test_begin_epoch:
+                evaluate()
+            if (self.epoch_cnt % self.cluster_interval) == 0:
+                window = (self.begin_cluster_epoch is None or self.begin_cluster_epoch <= self.epoch_cnt) \
+                    and (self.stop_cluster_epoch is None or self.stop_cluster_epoch > self.epoch_cnt)
+                diff_num = self.cluster() if window else 0
+                cluster_diff_num_list.append(diff_num)
+                envs_cnt = self.stat_envs()
+                cluster_epoch_list.append(self.epoch_cnt)
+                envs_cnt_list.append(envs_cnt)
+                if verbose:
+                    print('cluster at epoch:', self.epoch_cnt)
+                    print('diff num:', diff_num)
+                    print(transfer_loss_dict_to_line_str(envs_cnt))
+        return (loss_result_list, train_epoch_index_list), \
+               (test_result_list, test_epoch_list), \
+               (cluster_diff_num_list, envs_cnt_list, cluster_epoch_list)
+
+
+class ExplicitTrainManager(_InvPrefTrainManager):
+    """reference train.py:693-1019 (MSE recommend loss / MSE cluster distance)."""
+    implicit = False
+
+
+class ImplicitTrainManager(_InvPrefTrainManager):
+    """reference train.py:16-342 (BCE recommend loss / BCE cluster distance)."""
+    implicit = True
