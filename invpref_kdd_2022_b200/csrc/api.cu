@@ -51,6 +51,7 @@ AdamScalars make_adam(const invpref_hyper* h) {
     s.one_minus_b2 = (float)(1.0 - h->beta2);
     s.step_size = (float)(h->lr / bc1);
     s.bc2_sqrt = (float)sqrt(bc2);
+    s.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
     s.eps = (float)h->eps;
     return s;
 }

@@ -77,7 +77,7 @@ __device__ __forceinline__ void stage_EW(const BwdSideArgs& a, float* sE, float*
 }
 
 template <int VEC, int NV>
-__global__ void __launch_bounds__(BLOCK) bwd_chunks_kernel(BwdSideArgs a) {
+__global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_kernel(BwdSideArgs a) {
     extern __shared__ float smem[];
     float* sE = smem;
     float* sW = smem + a.K * a.D;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(BLOCK) bwd_chunks_kernel(BwdSideArgs a) {
 }
 
 template <int VEC, int NV, int EPI>
-__global__ void __launch_bounds__(BLOCK) bwd_rows_kernel(BwdSideArgs a) {
+__global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
     extern __shared__ float smem[];
     float* sE = smem;
     float* sW = smem + a.K * a.D;
