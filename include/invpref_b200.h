@@ -89,7 +89,22 @@ typedef struct {
     int64_t step;            /* 1-based Adam step of THIS update */
     int32_t use_class_rw;    /* train.py:814-815 */
     int32_t use_rec_rw;      /* train.py:817-819 */
+    /* Data-parallel use (one process per GPU, the batch split across ranks): every 1/B factor of the
+     * loss means and regularisers uses global_batch (0 = batch->B), so per-rank losses and gradients
+     * are partial sums that add up to the single-GPU values. */
+    int64_t global_batch;
+    int32_t flags;           /* INVPREF_EXPORT_* | INVPREF_SKIP_PARAM_REG */
+    int32_t _pad;
 } invpref_hyper;
+
+/* invpref_hyper.flags.  An EXPORT flag makes invpref_train_step write the (partial) gradients of that
+ * group of tensors into grads_out INSTEAD of applying Adam to them (rows without a gradient are not
+ * written: zero the buffers first), so that the caller can reduce them across ranks and then call
+ * invpref_adam_dense.  Tables of an exported group are not double-buffered (params_out may alias). */
+#define INVPREF_EXPORT_USER_GRADS 1   /* Uinv, Uenv */
+#define INVPREF_EXPORT_ITEM_GRADS 2   /* Iinv, Ienv */
+#define INVPREF_EXPORT_SMALL_GRADS 4  /* E, W, b; loss_out then holds this rank's partial sums */
+#define INVPREF_SKIP_PARAM_REG 8      /* leave out the classifier's own L1/L2 term (all ranks but one) */
 
 const char* invpref_strerror(int status);
 int invpref_abi_version(void);
@@ -168,6 +183,20 @@ int invpref_stat_envs(const int64_t* envs, int64_t N, int32_t n_envs, const int6
 
 /* Histogram of envs (train.py:949), accumulated into hist (int64[K]). */
 int invpref_env_hist(const int64_t* envs, int64_t N, int32_t n_envs, int64_t* hist, void* stream);
+
+/* ---- building blocks of the multi-GPU paths (no reference counterpart: the reference is single-GPU) ----
+ * Dense torch.optim.Adam on one flat fp32 tensor with a materialised gradient (after a cross-rank
+ * reduction): theta, m, v updated in place.  Uses lr/betas/eps/step of `hyper`. */
+int invpref_adam_dense(float* theta, float* m, float* v, const float* grad, int64_t n, const invpref_hyper* hyper,
+                       void* stream);
+
+/* out[j, :] = table[rows[j], :] for j < n (row-sharded tables: rows a peer asked for). */
+int invpref_gather_rows(const float* table, const int64_t* rows, int64_t n, int32_t dim, float* out, void* stream);
+
+/* table[rows[j], :] += src[j, :] for j < n.  rows must be unique within one call (no atomics); callers
+ * apply peers one after the other in rank order, which fixes the summation order. */
+int invpref_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, int32_t dim, float* table,
+                             void* stream);
 
 /* Number of kernels the library has launched in this process (bench.py's gpu_launches). */
 int64_t invpref_launch_count(void);

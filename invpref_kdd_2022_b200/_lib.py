@@ -23,7 +23,7 @@ EXPORTS = (
     "invpref_build_plan", "invpref_build_segments", "invpref_forward", "invpref_predict",
     "invpref_backward", "invpref_train_step", "invpref_cluster", "invpref_stat_envs",
     "invpref_env_hist", "invpref_launch_count", "invpref_profile_enable", "invpref_profile_steps",
-    "invpref_profile_read",
+    "invpref_profile_read", "invpref_adam_dense", "invpref_gather_rows", "invpref_scatter_add_rows",
 )
 PHASES = ("plan", "forward", "chunks_items", "chunks_users", "rows_items", "rows_users", "sweep_items",
           "sweep_users", "tail")
@@ -52,7 +52,10 @@ class Hyper(C.Structure):
     _fields_ = [("c_inv", C.c_double), ("c_ea", C.c_double), ("c_env", C.c_double), ("c_L2", C.c_double),
                 ("c_L1", C.c_double), ("alpha", C.c_double), ("lr", C.c_double), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("step", C.c_int64), ("use_class_rw", C.c_int32),
-                ("use_rec_rw", C.c_int32)]
+                ("use_rec_rw", C.c_int32), ("global_batch", C.c_int64), ("flags", C.c_int32), ("_pad", C.c_int32)]
+
+
+EXPORT_USER_GRADS, EXPORT_ITEM_GRADS, EXPORT_SMALL_GRADS, SKIP_PARAM_REG = 1, 2, 4, 8
 
 
 _lib = None
@@ -86,6 +89,9 @@ def load() -> C.CDLL:
     lib.invpref_cluster.argtypes = [C.POINTER(Desc), C.POINTER(Params), vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]
     lib.invpref_stat_envs.argtypes = [vp, i64, C.c_int32, vp, vp, vp, vp]
     lib.invpref_env_hist.argtypes = [vp, i64, C.c_int32, vp, vp]
+    lib.invpref_adam_dense.argtypes = [vp, vp, vp, vp, i64, C.POINTER(Hyper), vp]
+    lib.invpref_gather_rows.argtypes = [vp, vp, i64, C.c_int32, vp, vp]
+    lib.invpref_scatter_add_rows.argtypes = [vp, vp, i64, C.c_int32, vp, vp]
     lib.invpref_profile_enable.argtypes = [C.c_int]
     lib.invpref_profile_read.argtypes = [C.c_int, C.POINTER(C.c_float)]
     for name in EXPORTS:

@@ -211,9 +211,18 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     if (B < 1 || B > 0x7fffffffLL || !batch->users || !batch->items || !batch->envs || !batch->scores)
         return INVPREF_ERR_BAD_ARG;
     if ((hyper->use_class_rw || hyper->use_rec_rw) && !batch->weights) return INVPREF_ERR_BAD_ARG;
-    if (pin->Uinv == pout->Uinv || pin->Iinv == pout->Iinv || pin->Uenv == pout->Uenv || pin->Ienv == pout->Ienv)
-        return INVPREF_ERR_BAD_ARG;   // tables are double-buffered
-    if (hyper->step < 1) return INVPREF_ERR_BAD_ARG;
+    const bool exp_u = hyper->flags & INVPREF_EXPORT_USER_GRADS, exp_i = hyper->flags & INVPREF_EXPORT_ITEM_GRADS;
+    const bool exp_s = hyper->flags & INVPREF_EXPORT_SMALL_GRADS;
+    if ((exp_u || exp_i || exp_s) && !grads_out) return INVPREF_ERR_BAD_ARG;
+    if ((!exp_u && (pin->Uinv == pout->Uinv || pin->Uenv == pout->Uenv)) ||
+        (!exp_i && (pin->Iinv == pout->Iinv || pin->Ienv == pout->Ienv)))
+        return INVPREF_ERR_BAD_ARG;   // tables that Adam updates in this call are double-buffered
+    if (hyper->step < 1 || hyper->global_batch < 0) return INVPREF_ERR_BAD_ARG;
+    // grads_out: with EXPORT flags only the exported groups are written; without any, all (testing aid)
+    const bool any_exp = exp_u || exp_i || exp_s;
+    const bool wr_u = grads_out && (exp_u || !any_exp), wr_i = grads_out && (exp_i || !any_exp);
+    const bool wr_s = grads_out && (exp_s || !any_exp);
+    const int64_t Bg = hyper->global_batch > 0 ? hyper->global_batch : B;   // every 1/B factor uses this
     Workspace w;
     if (ws_bytes < workspace_bytes_impl(desc, g, B, &w, (char*)ws)) return INVPREF_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -240,29 +249,29 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     f.implicit = desc->implicit; f.reg_env_embed = desc->reg_env_embed;
     f.use_class_rw = hyper->use_class_rw; f.use_rec_rw = hyper->use_rec_rw;
     f.c_inv = (float)hyper->c_inv; f.c_ea = (float)hyper->c_ea; f.c_env = (float)hyper->c_env;
-    f.neg_alpha = (float)(-hyper->alpha); f.invB = 1.f / (float)B;
+    f.neg_alpha = (float)(-hyper->alpha); f.invB = 1.f / (float)Bg;
     f.gpack = w.gpack; f.partials = w.partials; f.P = fwd_partial_floats(g);
     f.up_s_inv = f.up_s_env = f.up_logp = nullptr; f.generic = 0;
     const int fgrid = fwd_train_grid(B);
     if ((rc = launch_fwd_train(g, f, fgrid, st)) != INVPREF_OK) return rc;
     pm.mark();
 
-    // (3)+(4) segmented backward feeding Adam, per side
+    // (3)+(4) segmented backward feeding Adam (or exporting the partial gradients), per side
     const AdamScalars as = make_adam(hyper);
-    const double bd2 = (double)B * g.D * 2.0;
+    const double bd2 = (double)Bg * g.D * 2.0;
     BwdSideArgs su, si;
     fill_side(&su, g, w.gpack, pin->E, pin->W);
     su.own_inv_in = pin->Uinv; su.own_env_in = pin->Uenv; su.own_inv_out = pout->Uinv; su.own_env_out = pout->Uenv;
     su.m_inv = adam->m.Uinv; su.m_env = adam->m.Uenv; su.v_inv = adam->v.Uinv; su.v_env = adam->v.Uenv;
     su.partner_inv = pin->Iinv; su.partner_env = pin->Ienv;
-    su.grad_inv = grads_out ? grads_out->Uinv : nullptr; su.grad_env = grads_out ? grads_out->Uenv : nullptr;
+    su.grad_inv = wr_u ? grads_out->Uinv : nullptr; su.grad_env = wr_u ? grads_out->Uenv : nullptr;
     su.plan = pu; su.chunk_part = w.chunk_part_u;
     su.reg2 = (float)(2.0 * hyper->c_L2 / bd2); su.reg1 = (float)(hyper->c_L1 / bd2); su.adam = as;
     fill_side(&si, g, w.gpack, pin->E, pin->W);
     si.own_inv_in = pin->Iinv; si.own_env_in = pin->Ienv; si.own_inv_out = pout->Iinv; si.own_env_out = pout->Ienv;
     si.m_inv = adam->m.Iinv; si.m_env = adam->m.Ienv; si.v_inv = adam->v.Iinv; si.v_env = adam->v.Ienv;
     si.partner_inv = pin->Uinv; si.partner_env = pin->Uenv;
-    si.grad_inv = grads_out ? grads_out->Iinv : nullptr; si.grad_env = grads_out ? grads_out->Ienv : nullptr;
+    si.grad_inv = wr_i ? grads_out->Iinv : nullptr; si.grad_env = wr_i ? grads_out->Ienv : nullptr;
     si.plan = pi; si.chunk_part = w.chunk_part_i;
     si.reg2 = su.reg2; si.reg1 = su.reg1; si.adam = as;
 
@@ -270,31 +279,52 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     pm.mark();
     if ((rc = launch_bwd_chunks(g, su, st)) != INVPREF_OK) return rc;
     pm.mark();
-    if ((rc = launch_bwd_rows(g, si, EPI_ADAM, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_bwd_rows(g, si, exp_i ? EPI_EXPORT : EPI_ADAM, st)) != INVPREF_OK) return rc;
     pm.mark();
-    if ((rc = launch_bwd_rows(g, su, EPI_ADAM, st)) != INVPREF_OK) return rc;
+    if ((rc = launch_bwd_rows(g, su, exp_u ? EPI_EXPORT : EPI_ADAM, st)) != INVPREF_OK) return rc;
     pm.mark();
-    if ((rc = launch_sweep(g, si, st)) != INVPREF_OK) return rc;
+    if (!exp_i && (rc = launch_sweep(g, si, st)) != INVPREF_OK) return rc;
     pm.mark();
-    if ((rc = launch_sweep(g, su, st)) != INVPREF_OK) return rc;
+    if (!exp_u && (rc = launch_sweep(g, su, st)) != INVPREF_OK) return rc;
     pm.mark();
 
-    // losses, E / W / b gradients and their Adam update
+    // losses, E / W / b gradients and their Adam update (or export)
     TailArgs t;
-    t.partials = w.partials; t.n_partials = fgrid; t.P = f.P; t.B = B; t.D = g.D; t.K = g.K;
-    t.reg_only_embed = desc->reg_only_embed; t.reg_env_embed = desc->reg_env_embed;
+    t.partials = w.partials; t.n_partials = fgrid; t.P = f.P; t.B = Bg; t.D = g.D; t.K = g.K;
+    t.reg_only_embed = desc->reg_only_embed || (hyper->flags & INVPREF_SKIP_PARAM_REG);
+    t.reg_env_embed = desc->reg_env_embed;
     t.c_inv = (float)hyper->c_inv; t.c_ea = (float)hyper->c_ea; t.c_env = (float)hyper->c_env;
     t.c_L2 = (float)hyper->c_L2; t.c_L1 = (float)hyper->c_L1;
     t.E_in = pin->E; t.W_in = pin->W; t.b_in = pin->b;
     t.E_out = pout->E; t.W_out = pout->W; t.b_out = pout->b;
     t.mE = adam->m.E; t.mW = adam->m.W; t.mb = adam->m.b; t.vE = adam->v.E; t.vW = adam->v.W; t.vb = adam->v.b;
-    t.gE = grads_out ? grads_out->E : nullptr; t.gW = grads_out ? grads_out->W : nullptr;
-    t.gb = grads_out ? grads_out->b : nullptr;
-    t.loss_out = loss_out; t.adam = as; t.epi = EPI_ADAM;
+    t.gE = wr_s ? grads_out->E : nullptr; t.gW = wr_s ? grads_out->W : nullptr;
+    t.gb = wr_s ? grads_out->b : nullptr;
+    t.loss_out = loss_out; t.adam = as; t.epi = exp_s ? EPI_EXPORT : EPI_ADAM;
     rc = launch_tail(t, st);
     pm.mark();
     pm.done();
     return rc;
+}
+
+int invpref_adam_dense(float* theta, float* m, float* v, const float* grad, int64_t n, const invpref_hyper* hyper,
+                       void* stream) {
+    if (!theta || !m || !v || !grad || !hyper || n < 0 || hyper->step < 1) return INVPREF_ERR_BAD_ARG;
+    if (n == 0) return INVPREF_OK;
+    return launch_adam_dense(theta, m, v, grad, n, make_adam(hyper), (cudaStream_t)stream);
+}
+
+int invpref_gather_rows(const float* table, const int64_t* rows, int64_t n, int32_t dim, float* out, void* stream) {
+    if (n < 0 || dim < 1 || (n > 0 && (!table || !rows || !out))) return INVPREF_ERR_BAD_ARG;
+    if (n == 0) return INVPREF_OK;
+    return launch_gather_rows(table, rows, n, dim, out, (cudaStream_t)stream);
+}
+
+int invpref_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, int32_t dim, float* table,
+                             void* stream) {
+    if (n < 0 || dim < 1 || (n > 0 && (!table || !rows || !src))) return INVPREF_ERR_BAD_ARG;
+    if (n == 0) return INVPREF_OK;
+    return launch_scatter_add_rows(src, rows, n, dim, table, (cudaStream_t)stream);
 }
 
 int invpref_backward(const invpref_desc* desc, const invpref_params* params, const invpref_batch* batch, double alpha,

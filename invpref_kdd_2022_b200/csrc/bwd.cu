@@ -111,9 +111,11 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
         const int beg = a.plan.seg_off[s], end = a.plan.seg_off[s + 1];
         const int c0 = a.plan.seg_chunk[s], c1 = a.plan.seg_chunk[s + 1];
         Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
-        if (EPI == EPI_ADAM) {
+        if (EPI == EPI_ADAM || EPI == EPI_EXPORT) {
             load_row<VEC, NV>(th_i, a.own_inv_in, row, D, lane);
             load_row<VEC, NV>(th_e, a.own_env_in, row, D, lane);
+        }
+        if (EPI == EPI_ADAM) {
             load_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
             load_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
             load_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
         } else {
             accumulate_range<VEC, NV>(a, sE, sW, beg, end, lane, gi.x, ge.x);
         }
-        if (EPI == EPI_ADAM) {
+        if (EPI == EPI_ADAM || EPI == EPI_EXPORT) {
             // L1/L2 term of the gathered rows (models.py:469-497): every occurrence counts
             const float cnt = (float)(end - beg);
 #pragma unroll
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
                 store_row<VEC, NV>(gi, a.grad_inv, row, D, lane);
                 store_row<VEC, NV>(ge, a.grad_env, row, D, lane);
             }
+        }
+        if (EPI == EPI_ADAM) {
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) {
                 adam_update(th_i.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.adam);
@@ -156,7 +160,7 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
             store_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
             store_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
             store_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
-        } else {
+        } else if (EPI == EPI_ACCUM) {
             Row<VEC, NV> oi, oe;
             load_row<VEC, NV>(oi, a.grad_inv, row, D, lane);
             load_row<VEC, NV>(oe, a.grad_env, row, D, lane);
@@ -232,7 +236,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
     }
     __syncthreads();
     const double Bf = (double)a.B, Df = (double)D;
-    if (a.epi == EPI_ADAM) {
+    if (a.epi == EPI_ADAM || a.epi == EPI_EXPORT) {
+        const bool do_adam = a.epi == EPI_ADAM;
         // classifier norms (models.py:210-217), only when it is regularised
         double w2 = 0.0, w1 = 0.0, b2 = 0.0, b1 = 0.0;
         if (!a.reg_only_embed) {
@@ -278,21 +283,25 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
             if (!a.reg_only_embed) gW += rW2 * w + rW1 * signf_(w);
             if (a.reg_env_embed) gE += (float)stot[P_CNT + k] * (rE2 * e + rE1 * signf_(e));
             if (a.gW) { a.gW[idx] = gW; a.gE[idx] = gE; }
-            float m = a.mW[idx], v = a.vW[idx];
-            adam_update(w, m, v, gW, a.adam);
-            a.W_out[idx] = w; a.mW[idx] = m; a.vW[idx] = v;
-            m = a.mE[idx]; v = a.vE[idx];
-            adam_update(e, m, v, gE, a.adam);
-            a.E_out[idx] = e; a.mE[idx] = m; a.vE[idx] = v;
+            if (do_adam) {
+                float m = a.mW[idx], v = a.vW[idx];
+                adam_update(w, m, v, gW, a.adam);
+                a.W_out[idx] = w; a.mW[idx] = m; a.vW[idx] = v;
+                m = a.mE[idx]; v = a.vE[idx];
+                adam_update(e, m, v, gE, a.adam);
+                a.E_out[idx] = e; a.mE[idx] = m; a.vE[idx] = v;
+            }
         }
         if (tid < K) {
             float bb = a.b_in[tid];
             float gb = (float)stot[P_DB + tid];
             if (!a.reg_only_embed) gb += rb2 * bb + rb1 * signf_(bb);
             if (a.gb) a.gb[tid] = gb;
-            float m = a.mb[tid], v = a.vb[tid];
-            adam_update(bb, m, v, gb, a.adam);
-            a.b_out[tid] = bb; a.mb[tid] = m; a.vb[tid] = v;
+            if (do_adam) {
+                float m = a.mb[tid], v = a.vb[tid];
+                adam_update(bb, m, v, gb, a.adam);
+                a.b_out[tid] = bb; a.mb[tid] = m; a.vb[tid] = v;
+            }
         }
     } else {
         for (int idx = tid; idx < KD; idx += TAIL_THREADS) {
@@ -326,6 +335,10 @@ int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream
     int grid = grid_groups(a.plan.max_seg, 148 * 8);
     if (epi == EPI_ADAM) {
 #define CALL(V, N) bwd_rows_kernel<V, N, EPI_ADAM><<<grid, BLOCK, smem, stream>>>(a)
+        INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    } else if (epi == EPI_EXPORT) {
+#define CALL(V, N) bwd_rows_kernel<V, N, EPI_EXPORT><<<grid, BLOCK, smem, stream>>>(a)
         INVPREF_DISPATCH_VN(g, CALL);
 #undef CALL
     } else {

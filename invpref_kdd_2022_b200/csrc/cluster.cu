@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a) {
     float* sE = smem;   // [K*D]
     __shared__ unsigned long long sHist[INVPREF_MAX_ENVS + 1];   // [K] histogram, [8] diff
     const int tid = threadIdx.x, lane = tid & (GROUP - 1);
+    const unsigned gmask = group_mask();
     for (int t = tid; t < K * D; t += BLOCK) sE[t] = a.E[t];
     if (tid <= INVPREF_MAX_ENVS) sHist[tid] = 0ull;
     __syncthreads();
@@ -51,9 +52,9 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a) {
                 }
             }
         }
-        z1 = group_sum(z1);
+        z1 = group_sum(z1, gmask);
 #pragma unroll
-        for (int k = 0; k < KT; ++k) z2[k] = group_sum(z2[k]);
+        for (int k = 0; k < KT; ++k) z2[k] = group_sum(z2[k], gmask);
         if (lane == 0) {
             const float* eps = (a.perm_idx != nullptr) ? a.eps_table + a.perm_idx[n] * K : nullptr;
             const float s_inv = a.implicit ? sigmoidf_(z1) : z1;

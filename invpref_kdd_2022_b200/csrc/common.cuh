@@ -259,19 +259,24 @@ __device__ __forceinline__ void store_row(const Row<VEC, NV>& r, float* __restri
     }
 }
 
+// The two 16-lane groups of a warp run loops with different trip counts, so every in-loop shuffle names
+// only its own half-warp: a full-warp mask there would wait for lanes that have already left the loop.
+__device__ __forceinline__ unsigned group_mask() { return 0xffffu << (threadIdx.x & 16); }
+
 // sum over the 16 lanes of a group; every lane gets the result (xor butterfly stays inside the
 // aligned half-warp)
-__device__ __forceinline__ float group_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
+__device__ __forceinline__ float group_sum(float v, unsigned mask) {
+    v += __shfl_xor_sync(mask, v, 8);
+    v += __shfl_xor_sync(mask, v, 4);
+    v += __shfl_xor_sync(mask, v, 2);
+    v += __shfl_xor_sync(mask, v, 1);
     return v;
 }
 
+// all 32 lanes must be converged (used after the loops only)
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
-    return group_sum(v);
+    return group_sum(v, 0xffffffffu);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }

@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
     float* sRed = smem + K * D;       // [2*K*D] reduction buffer for dW, dE
     const int tid = threadIdx.x;
     const int lane = tid & (GROUP - 1);
+    const unsigned gmask = group_mask();
     for (int t = tid; t < K * D; t += BLOCK) sE[t] = a.E[t];
     for (int t = tid; t < 2 * K * D; t += BLOCK) sRed[t] = 0.f;
     __syncthreads();
@@ -91,10 +92,10 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
                 for (int k = 0; k < KT; ++k) lg[k] += Wr[k][x] * p[x];
             }
         }
-        z1 = group_sum(z1);
-        z2 = group_sum(z2);
+        z1 = group_sum(z1, gmask);
+        z2 = group_sum(z2, gmask);
 #pragma unroll
-        for (int k = 0; k < KT; ++k) lg[k] = (k < K) ? group_sum(lg[k]) + bk[k] : -INFINITY;
+        for (int k = 0; k < KT; ++k) lg[k] = (k < K) ? group_sum(lg[k], gmask) + bk[k] : -INFINITY;
         s_sq += sq; s_abs += ab; s_esq += esq; s_eabs += eab;
 
         // log-softmax over K (models.py:208)
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(BLOCK) fwd_only_kernel(FwdOnlyArgs a) {
     float* sE = smem;
     float* sW = smem + K * D;
     const int tid = threadIdx.x, lane = tid & (GROUP - 1);
+    const unsigned gmask = group_mask();
     for (int t = tid; t < K * D; t += BLOCK) { sE[t] = a.E[t]; sW[t] = a.W[t]; }
     __syncthreads();
     const bool want_cls = a.logp != nullptr;
@@ -294,8 +296,8 @@ __global__ void __launch_bounds__(BLOCK) fwd_only_kernel(FwdOnlyArgs a) {
                 }
             }
         }
-        z1 = group_sum(z1);
-        z2 = group_sum(z2);
+        z1 = group_sum(z1, gmask);
+        z2 = group_sum(z2, gmask);
         float s_inv, s_env;
         if (a.implicit) {
             s_inv = sigmoidf_(z1);
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(BLOCK) fwd_only_kernel(FwdOnlyArgs a) {
         }
         if (want_cls) {
 #pragma unroll
-            for (int k = 0; k < KT; ++k) lg[k] = (k < K) ? group_sum(lg[k]) + a.b[k] : -INFINITY;
+            for (int k = 0; k < KT; ++k) lg[k] = (k < K) ? group_sum(lg[k], gmask) + a.b[k] : -INFINITY;
             float mx = lg[0];
 #pragma unroll
             for (int k = 1; k < KT; ++k) mx = fmaxf(mx, lg[k]);
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(BLOCK) predict_kernel(const float* __restrict_
                                                         const int64_t* __restrict__ items, int64_t B, int D,
                                                         float* __restrict__ score) {
     const int tid = threadIdx.x, lane = tid & (GROUP - 1);
+    const unsigned gmask = group_mask();
     const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
     for (int64_t n = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (tid >> 4); n < B; n += ngroups) {
         Row<VEC, NV> ra, rc;
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(BLOCK) predict_kernel(const float* __restrict_
         float z = 0.f;
 #pragma unroll
         for (int x = 0; x < NV * VEC; ++x) z += ra.x[x] * rc.x[x];
-        z = group_sum(z);
+        z = group_sum(z, gmask);
         if (lane == 0) score[n] = z;
     }
 }

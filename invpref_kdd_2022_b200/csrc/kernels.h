@@ -37,7 +37,7 @@ int launch_predict(const Geometry& g, const float* Uinv, const float* Iinv, cons
                    int64_t B, float* score, cudaStream_t stream);
 
 // ---- bwd.cu ----------------------------------------------------------------------------------
-enum { EPI_ADAM = 0, EPI_ACCUM = 1 };
+enum { EPI_ADAM = 0, EPI_ACCUM = 1, EPI_EXPORT = 2 };
 
 // One side (user tables or item tables) of the segmented backward.
 struct BwdSideArgs {
@@ -95,6 +95,13 @@ int launch_cluster(const Geometry& g, const ClusterArgs& a, cudaStream_t stream)
 int launch_env_hist(const int64_t* envs, int64_t N, int K, unsigned long long* hist, cudaStream_t stream);
 int launch_stat_envs(const int64_t* envs, int64_t N, int K, const int64_t* hist, float* class_weights,
                      float* sample_weights, cudaStream_t stream);
+
+// ---- dist.cu ---------------------------------------------------------------------------------
+int launch_adam_dense(float* theta, float* m, float* v, const float* grad, int64_t n, const AdamScalars& s,
+                      cudaStream_t stream);
+int launch_gather_rows(const float* table, const int64_t* rows, int64_t n, int dim, float* out, cudaStream_t stream);
+int launch_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, int dim, float* table,
+                            cudaStream_t stream);
 
 // ---- plan.cu ---------------------------------------------------------------------------------
 int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, PlanSide p, char* tmp,

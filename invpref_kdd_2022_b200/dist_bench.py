@@ -1,0 +1,109 @@
+"""bench.py's multi-GPU leg: one process per GPU under torchrun (NCCL), see parallel.py.
+
+Fixed global workload (strong scaling): the same global batches as the 1-GPU run are split over the ranks.
+Timed region: K steps between a barrier + synchronize on both sides, CUDA events on every rank, MAX over
+ranks; value = K * global_batch / that time.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def run(args, w):
+    from invpref_kdd_2022_b200 import _lib
+    from invpref_kdd_2022_b200.parallel import DistDriver, ReplicatedTrainer, ShardedTrainer
+    import bench as B
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    drv = DistDriver()
+    K, D = w["K"], w["D"]
+    nb = max(1, min(args.nbatch, args.steps + args.warmup))
+    U, I, Bg, batches = B.synth_batches(w, nb)
+    P = 2 * (U + I) * D + 2 * K * D + K
+    sharded = P * 4 > 2.5e8                       # dataset-scale tables are replicated
+    kw = dict(alpha=1.0, use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
+    t = lambda a: torch.from_numpy(a).to(dev)
+
+    if sharded:
+        tr = ShardedTrainer(U, I, K, D, w["implicit"], w["roe"], w["ree"], w["lr"], rank, world, dev,
+                            cache_rows=min(I, Bg // world * 2 + 1024))
+        prepared = []
+        for (u, i, y, e) in batches:
+            sb = drv.run(tr.prepare_gen(t(u), t(i), t(y)))
+            le = t(e)[sb.sel].contiguous()
+            cw, sw = tr.hot.stat_envs(le, tr.hot.env_hist(le)) if le.numel() else (None, torch.zeros(0, device=dev))
+            prepared.append((sb, le, sw))
+
+        def step(s):
+            sb, le, sw = prepared[s % nb]
+            return drv.run(tr.step_gen(sb, le, sw, **kw))
+        mode = f"users+items row-sharded (mod {world}), interactions routed to the user's owner, " \
+               f"item rows/grads all-to-all, E/W/b all-reduce"
+    else:
+        g = torch.Generator(device=dev).manual_seed(17373331)
+        tr = ReplicatedTrainer(B.make_tables(w, dev), w["implicit"], w["roe"], w["ree"], w["lr"], rank, world)
+        prepared = []
+        for (u, i, y, e) in batches:
+            a, b = tr.chunk(0, Bg)
+            le = t(e[a:b])
+            cw, sw = tr.hot.stat_envs(le, tr.hot.env_hist(le)) if le.numel() else (None, torch.zeros(0, device=dev))
+            lu, li = t(u[a:b]), t(i[a:b])
+            plan = tr.hot.new_plan(lu, li) if lu.numel() else None
+            prepared.append((lu, li, t(y[a:b]), le, sw, plan))
+
+        def step(s):
+            lu, li, ly, le, sw, plan = prepared[s % nb]
+            return drv.run(tr.step_gen(lu, li, ly, le, sw, Bg, plan=plan, **kw))
+        mode = f"tables replicated, batch chunked over {world} ranks, flat gradient all-reduce"
+
+    for s in range(args.warmup):
+        step(s)
+    torch.cuda.synchronize()
+    clocks = B.ClockSampler(dev.index)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for s in range(args.warmup, args.warmup + args.steps):
+        loss = step(s)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = _lib.launch_count() - l0
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / args.steps
+    assert torch.isfinite(loss).all()
+    clk = clocks.stop() if rank == 0 else None
+    peak, peak_src = B.measured_peaks()
+    sbytes = B.step_bytes(Bg, D, K, P)
+    if rank == 0:
+        line = {"metric": "train interactions/sec (fwd+bwd+Adam)", "value": Bg / (ms * 1e-3),
+                "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["name"], "global_batch": Bg, "params": P, "distinct_batches": nb,
+                           "l2": "inputs larger than L2" if sharded else "tables fit in L2 (no flush)",
+                           "parallelism": mode},
+                "roofline": {"bound": "hbm", "kernel": "fused train step (all kernels, all ranks)",
+                             "achieved": sbytes / (ms * 1e-3) / 1e9, "peak": peak * world,
+                             "peak_source": peak_src + f" x {world} GPUs", "unit": "GB/s",
+                             "frac": sbytes / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None},
+                "e2e": {"value": Bg / (ms * 1e-3), "unit": "interactions/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0,
+                        "note": "multi-GPU leg times device-resident batches only; see the 1-GPU line for e2e"},
+                "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss[5])}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()

@@ -51,12 +51,23 @@ class HotPath:
         self.loss_buf = torch.zeros(6, dtype=torch.float32, device=self.device)
 
     # ---- buffers -------------------------------------------------------------------------
-    def _ensure_state(self):
+    def _ensure_state(self, shadow_for=TABLES):
         if self.m is None:
             self.m = {k: torch.zeros_like(self.params[k]) for k in PARAM_FIELDS}
             self.v = {k: torch.zeros_like(self.params[k]) for k in PARAM_FIELDS}
         if self.shadow is None:
-            self.shadow = {k: self.params[k].clone() for k in TABLES}
+            self.shadow = {}
+        for k in shadow_for:
+            if k not in self.shadow:
+                self.shadow[k] = self.params[k].clone()
+
+    def adam_dense(self, theta, m, v, grad, step=None):
+        """``invpref_adam_dense``: in-place Adam on flat fp32 tensors with a materialised gradient."""
+        hyper = _lib.Hyper(0, 0, 0, 0, 0, 0, self.lr, self.betas[0], self.betas[1], self.eps,
+                           int(step if step is not None else self.step), 0, 0, 0, 0, 0)
+        _lib.check(self.lib.invpref_adam_dense(_lib.ptr(theta, torch.float32), _lib.ptr(m, torch.float32),
+                                               _lib.ptr(v, torch.float32), _lib.ptr(grad, torch.float32),
+                                               theta.numel(), C.byref(hyper), _lib.stream_ptr()), "adam_dense")
 
     def workspace(self, batch: int) -> torch.Tensor:
         if self._ws is None or batch > self._ws_batch:
@@ -79,18 +90,24 @@ class HotPath:
     # ---- fused train step ---------------------------------------------------------------------
     def train_step(self, users, items, scores, envs, weights, *, c_inv, c_ea, c_env, c_L2, c_L1, alpha,
                    use_class_rw, use_rec_rw, plan: Optional[torch.Tensor] = None,
-                   loss_out: Optional[torch.Tensor] = None, grads_out: Optional[Dict[str, torch.Tensor]] = None):
-        """train.py:771-844 in one library call.  Returns the device tensor holding the six losses."""
-        self._ensure_state()
+                   loss_out: Optional[torch.Tensor] = None, grads_out: Optional[Dict[str, torch.Tensor]] = None,
+                   global_batch: int = 0, flags: int = 0):
+        """train.py:771-844 in one library call.  Returns the device tensor holding the six losses.
+
+        ``flags`` / ``global_batch``: data-parallel use, see ``invpref_hyper`` in the header; tables of an
+        exported group are neither updated nor swapped."""
+        self._ensure_state([k for k in TABLES
+                            if not (flags & (_lib.EXPORT_USER_GRADS if k[0] == "U" else _lib.EXPORT_ITEM_GRADS))])
         B = users.numel()
         ws = self.workspace(B)
         self.step += 1
         hyper = _lib.Hyper(float(c_inv), float(c_ea), float(c_env), float(c_L2), float(c_L1), float(alpha), self.lr,
                            self.betas[0], self.betas[1], self.eps, self.step, int(bool(use_class_rw)),
-                           int(bool(use_rec_rw)))
+                           int(bool(use_rec_rw)), int(global_batch), int(flags), 0)
         p_in = _lib.make_params(self.params)
         out = dict(self.params)
-        out.update(self.shadow)
+        swap = [k for k in TABLES if not (flags & (_lib.EXPORT_USER_GRADS if k[0] == "U" else _lib.EXPORT_ITEM_GRADS))]
+        out.update({k: self.shadow[k] for k in swap})
         p_out = _lib.make_params(out)
         adam = _lib.Adam(_lib.make_params(self.m), _lib.make_params(self.v))
         batch = _lib.Batch(_lib.ptr(users, torch.int64), _lib.ptr(items, torch.int64), _lib.ptr(envs, torch.int64),
@@ -106,7 +123,7 @@ class HotPath:
             self.step -= 1
         _lib.check(rc, "train_step")
         # the updated rows are in the other buffer set: swap
-        for k in TABLES:
+        for k in swap:
             self.params[k], self.shadow[k] = self.shadow[k], self.params[k]
         if self.on_swap is not None:
             self.on_swap(self.params)

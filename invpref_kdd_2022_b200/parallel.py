@@ -1,0 +1,363 @@
+"""Multi-GPU InvPref: one process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch).
+
+The reference is single-GPU; this layer is new.  Interactions of every global batch are
+partitioned across ranks -- the loss is a mean over the global batch, so any partition is semantically
+free once every 1/B factor uses the GLOBAL batch size (``invpref_hyper.global_batch``).
+
+``ReplicatedTrainer``  dataset-scale tables (C1-C4): tables replicated, each rank takes a contiguous chunk
+                       of the batch, exports its partial dense gradients, ONE all-reduce over the flat
+                       gradient buffer (+ the six loss partial sums), then the same dense Adam everywhere.
+``ShardedTrainer``     10M-user scale (C5): user rows and item rows are mod-sharded over the ranks together
+                       with their Adam state.  An interaction is routed to the rank that owns its USER row,
+                       so user rows never cross NVLink: the fused segment-reduce -> Adam runs locally on the
+                       user shard.  Item rows are fetched from their owners per step (all-to-all of rows into
+                       a compact per-batch cache; the routing is static per batch and built once), the
+                       per-rank partial item gradients go back the same way, the owner adds them in rank
+                       order (deterministic) and applies dense Adam to its item shard.  E / W / b are
+                       replicated; their gradients and the loss partial sums are all-reduced (a few KB).
+
+Every collective is issued by a small driver from a generator (`yield ("all_to_all", ...)`), so the same step
+code runs under ``torch.distributed`` (``DistDriver``) and under ``SimDriver``, which runs G simulated ranks
+in ONE process on one GPU -- that is how the 1-GPU test-suite checks the sharded arithmetic against the
+single-GPU result without a multi-GPU box.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List
+
+import torch
+
+from . import _lib
+from .engine import HotPath
+
+SMALL = ("E", "W", "b")
+
+
+# ================================ collectives =====================================================
+class DistDriver:
+    """Executes the collectives a step generator yields with torch.distributed (NCCL on GPU, gloo on CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def run(self, gen):
+        dist = self.dist
+        try:
+            req = next(gen)
+            while True:
+                op = req[0]
+                if op == "all_reduce":
+                    dist.all_reduce(req[1], group=self.group)
+                elif op == "all_to_all":
+                    _, out, inp, out_splits, in_splits = req
+                    self._a2a(out, inp, out_splits, in_splits)
+                else:
+                    raise ValueError(op)
+                req = gen.send(None)
+        except StopIteration as stop:
+            return stop.value
+
+    def _a2a(self, out, inp, out_splits, in_splits):
+        dist = self.dist
+        try:
+            dist.all_to_all_single(out, inp, list(out_splits), list(in_splits), group=self.group)
+        except RuntimeError:
+            # gloo builds without alltoall: emulate with all_gather (host-side tests only)
+            sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
+            dist.all_gather(sizes, torch.tensor([inp.shape[0]], dtype=torch.int64), group=self.group)
+            mx = int(max(s.item() for s in sizes))
+            pad = torch.zeros((mx,) + tuple(inp.shape[1:]), dtype=inp.dtype)
+            pad[:inp.shape[0]] = inp
+            bufs = [torch.zeros_like(pad) for _ in range(self.world)]
+            dist.all_gather(bufs, pad, group=self.group)
+            splits = [torch.zeros(self.world, dtype=torch.int64) for _ in range(self.world)]
+            dist.all_gather(splits, torch.tensor(list(in_splits), dtype=torch.int64), group=self.group)
+            o = 0
+            for p in range(self.world):
+                sp = splits[p].tolist()
+                start = sum(sp[:self.rank])
+                out[o:o + sp[self.rank]] = bufs[p][start:start + sp[self.rank]]
+                o += sp[self.rank]
+
+
+class SimDriver:
+    """Runs the generators of G simulated ranks in lockstep inside one process (tests / debugging)."""
+
+    def __init__(self, world):
+        self.world = world
+
+    def run_all(self, gens: List):
+        G = self.world
+        reqs = [next(g) for g in gens]
+        done = [False] * G
+        results = [None] * G
+        while True:
+            op = reqs[0][0]
+            assert all(r[0] == op for r in reqs), "ranks diverged"
+            if op == "all_reduce":
+                tot = reqs[0][1].clone()
+                for r in reqs[1:]:
+                    tot += r[1]
+                for r in reqs:
+                    r[1].copy_(tot)
+            elif op == "all_to_all":
+                for dst in range(G):
+                    _, out, _, out_splits, _ = reqs[dst]
+                    o = 0
+                    for src in range(G):
+                        _, _, inp, _, in_splits = reqs[src]
+                        start = sum(in_splits[:dst])
+                        n = in_splits[dst]
+                        assert n == out_splits[src]
+                        out[o:o + n] = inp[start:start + n]
+                        o += n
+            for k in range(G):
+                try:
+                    reqs[k] = gens[k].send(None)
+                except StopIteration as stop:
+                    done[k], results[k] = True, stop.value
+            if all(done):
+                return results
+            assert not any(done), "ranks finished at different points"
+
+
+# ================================ replicated tables ===============================================
+class ReplicatedTrainer:
+    """Tables replicated; batch chunked over ranks; one all-reduce of the flat gradient per step."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], implicit, reg_only_embed, reg_env_embed, lr, rank, world):
+        dev = params["Uinv"].device
+        self.rank, self.world = rank, world
+        sizes = [params[k].numel() for k in _lib.PARAM_FIELDS]
+        pad = [(-n) % 4 for n in sizes]                       # keep every view 16-byte aligned
+        total = sum(n + p for n, p in zip(sizes, pad))
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.gflat = torch.zeros(total + 8, dtype=torch.float32, device=dev)     # + six loss partial sums
+        self.mflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.vflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.params, self.grads = {}, {}
+        o = 0
+        for k, n, p in zip(_lib.PARAM_FIELDS, sizes, pad):
+            self.flat[o:o + n].copy_(params[k].reshape(-1))
+            self.params[k] = self.flat[o:o + n].view(params[k].shape)
+            self.grads[k] = self.gflat[o:o + n].view(params[k].shape)
+            o += n + p
+        self.loss = self.gflat[total:total + 6]
+        self.hot = HotPath(self.params, implicit, reg_only_embed, reg_env_embed, lr=lr)
+        # every group is exported, so the step never touches per-tensor Adam state: Adam runs on the flat
+        # buffers below (adam_dense); the library still wants valid pointers
+        self.hot.m = self.grads
+        self.hot.v = self.grads
+        self.flags = _lib.EXPORT_USER_GRADS | _lib.EXPORT_ITEM_GRADS | _lib.EXPORT_SMALL_GRADS | \
+            (0 if rank == 0 else _lib.SKIP_PARAM_REG)
+
+    def chunk(self, lo, hi):
+        """Contiguous chunk of the global batch rows [lo, hi) for this rank."""
+        n = hi - lo
+        per = (n + self.world - 1) // self.world
+        a = min(lo + self.rank * per, hi)
+        return a, min(a + per, hi)
+
+    def step_gen(self, users, items, scores, envs, weights, global_batch, plan=None, **kw):
+        """users..weights: this rank's chunk (may be empty).  Yields collectives; returns the loss tensor."""
+        self.gflat.zero_()
+        if users.numel() > 0:
+            self.hot.train_step(users, items, scores, envs, weights, plan=plan, loss_out=self.loss,
+                                grads_out=self.grads, global_batch=global_batch, flags=self.flags, **kw)
+        else:
+            self.hot.step += 1
+        yield ("all_reduce", self.gflat)
+        self.hot.adam_dense(self.flat, self.mflat, self.vflat, self.gflat[:self.flat.numel()])
+        return self.loss
+
+
+# ================================ row-sharded tables ==============================================
+class ItemRoute:
+    """Static routing of one local batch: which item rows this rank needs from which owner, and which of
+    its own rows every peer needs.  Built once per batch (the batch slicing is fixed, utils.py:12-19)."""
+
+    def __init__(self):
+        self.slots = None          # int64 [b]   cache slot of every local interaction's item
+        self.n_cache = 0           # rows in the cache (= unique items of the local batch)
+        self.recv_splits = None    # list[G]     cache rows coming from each owner
+        self.send_splits = None    # list[G]     rows of my shard going to each requester
+        self.send_rows = None      # int64 [sum(send_splits)] owner-local row indices, grouped by requester
+
+
+def build_route_gen(items_global: torch.Tensor, world: int, route: ItemRoute):
+    """Generator: builds `route` for the local interactions' GLOBAL item ids (collectives are yielded)."""
+    dev = items_global.device
+    uniq, inverse = torch.unique(items_global, sorted=True, return_inverse=True)
+    owner = uniq % world
+    order = torch.sort(owner, stable=True).indices               # cache order: grouped by owner, id ascending
+    slot_of_uniq = torch.empty_like(order)
+    slot_of_uniq[order] = torch.arange(order.numel(), device=dev)
+    route.slots = slot_of_uniq[inverse].contiguous()
+    route.n_cache = int(uniq.numel())
+    counts = torch.bincount(owner, minlength=world)
+    route.recv_splits = [int(c) for c in counts.tolist()]
+    want_rows = (uniq[order] // world).contiguous()               # owner-local rows, in cache order
+    send_counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    yield ("all_to_all", send_counts, counts.to(torch.int64), [1] * world, [1] * world)
+    route.send_splits = [int(c) for c in send_counts.tolist()]
+    route.send_rows = torch.empty(sum(route.send_splits), dtype=torch.int64, device=dev)
+    yield ("all_to_all", route.send_rows, want_rows, route.send_splits, route.recv_splits)
+    return route
+
+
+class ShardedBatch:
+    """One rank's share of one global batch, prepared once."""
+
+    def __init__(self):
+        self.sel = None       # int64 [b] positions inside the global batch (order preserved)
+        self.users = None     # int64 [b] LOCAL user rows (u // G)
+        self.route = ItemRoute()
+        self.scores = None
+        self.plan = None
+        self.global_batch = 0
+
+
+class ShardedTrainer:
+    """User and item tables mod-sharded by row over `world` ranks (row r of rank g holds id r*world + g)."""
+
+    def __init__(self, n_users, n_items, n_envs, dim, implicit, reg_only_embed, reg_env_embed, lr, rank, world,
+                 device, cache_rows, init=None, seed=17373331):
+        self.rank, self.world, self.dev = rank, world, device
+        self.U, self.I, self.K, self.D = n_users, n_items, n_envs, dim
+        self.U_loc = (n_users - rank + world - 1) // world
+        self.I_loc = (n_items - rank + world - 1) // world
+        self.cache_rows = max(int(cache_rows), 1)
+        f32 = dict(dtype=torch.float32, device=device)
+        # owned shards
+        if init is not None:      # init: full tables (tests) -> take my rows
+            uinv, uenv = init["Uinv"][rank::world].clone(), init["Uenv"][rank::world].clone()
+            self.Iinv, self.Ienv = init["Iinv"][rank::world].clone(), init["Ienv"][rank::world].clone()
+            small = [init[k].reshape(-1).clone() for k in SMALL]
+        else:
+            g = torch.Generator(device=device).manual_seed(seed + rank)
+            uinv = torch.randn((self.U_loc, dim), generator=g, **f32) * 0.01
+            uenv = torch.randn((self.U_loc, dim), generator=g, **f32) * 0.01
+            self.Iinv = torch.randn((self.I_loc, dim), generator=g, **f32) * 0.01
+            self.Ienv = torch.randn((self.I_loc, dim), generator=g, **f32) * 0.01
+            g0 = torch.Generator(device=device).manual_seed(seed)          # replicated tensors: same on all ranks
+            small = [torch.randn(n, generator=g0, **f32) * s for n, s in
+                     ((n_envs * dim, 0.01), (n_envs * dim, 0.1), (n_envs, 0.1))]
+        self.mI = [torch.zeros_like(self.Iinv), torch.zeros_like(self.Ienv)]
+        self.vI = [torch.zeros_like(self.Iinv), torch.zeros_like(self.Ienv)]
+        self.gI = [torch.zeros_like(self.Iinv), torch.zeros_like(self.Ienv)]
+        # replicated small tensors in one flat buffer [E | W | b], gradients + six loss sums likewise
+        KD = n_envs * dim
+        self.small = torch.cat(small)
+        self.gsmall = torch.zeros(2 * KD + n_envs + 6, **f32)
+        self.msmall, self.vsmall = torch.zeros_like(self.small), torch.zeros_like(self.small)
+        views = lambda t: {"E": t[:KD].view(n_envs, dim), "W": t[KD:2 * KD].view(n_envs, dim),
+                           "b": t[2 * KD:2 * KD + n_envs]}
+        self.loss = self.gsmall[2 * KD + n_envs:]
+        # per-batch item cache (what the local kernels see as "the item tables") and its gradient
+        self.cache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
+        self.gcache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
+        params = {"Uinv": uinv, "Uenv": uenv, "Iinv": self.cache[0], "Ienv": self.cache[1]}
+        params.update(views(self.small))
+        self.hot = HotPath(params, implicit, reg_only_embed, reg_env_embed, lr=lr)
+        self.hot.m = {"Uinv": torch.zeros_like(uinv), "Uenv": torch.zeros_like(uenv), "Iinv": self.cache[0],
+                      "Ienv": self.cache[1]}
+        self.hot.v = {"Uinv": torch.zeros_like(uinv), "Uenv": torch.zeros_like(uenv), "Iinv": self.cache[0],
+                      "Ienv": self.cache[1]}
+        self.hot.m.update(views(self.msmall))
+        self.hot.v.update(views(self.vsmall))
+        self.grads = {"Uinv": uinv, "Uenv": uenv, "Iinv": self.gcache[0], "Ienv": self.gcache[1]}   # U*: unused
+        self.grads.update(views(self.gsmall))
+        self.flags = _lib.EXPORT_ITEM_GRADS | _lib.EXPORT_SMALL_GRADS | (0 if rank == 0 else _lib.SKIP_PARAM_REG)
+        self.send_buf = None
+        self.recv_g = None
+
+    # ---- setup -------------------------------------------------------------------------------------
+    def prepare_gen(self, users_g, items_g, scores_g):
+        """Generator: this rank's share of a global batch (GLOBAL ids, full batch given on every rank)."""
+        sb = ShardedBatch()
+        sb.global_batch = int(users_g.numel())
+        sb.sel = torch.nonzero(users_g % self.world == self.rank).reshape(-1)
+        sb.users = (users_g[sb.sel] // self.world).contiguous()
+        sb.scores = scores_g[sb.sel].contiguous()
+        yield from build_route_gen(items_g[sb.sel], self.world, sb.route)
+        if sb.route.n_cache > self.cache_rows:
+            raise RuntimeError(f"item cache too small: {sb.route.n_cache} > {self.cache_rows}")
+        if sb.users.numel() > 0:
+            sb.plan = self.hot.new_plan(sb.users, sb.route.slots)
+        return sb
+
+    def _buf(self, name, rows):
+        cur = getattr(self, name)
+        if cur is None or cur[0].shape[0] < rows:
+            cur = [torch.empty((max(rows, 1), self.D), dtype=torch.float32, device=self.dev) for _ in range(2)]
+            setattr(self, name, cur)
+        return cur
+
+    def _gather(self, table, rows, out):
+        _lib.check(self.hot.lib.invpref_gather_rows(_lib.ptr(table), _lib.ptr(rows), rows.numel(), self.D,
+                                                    _lib.ptr(out), _lib.stream_ptr()), "gather_rows")
+
+    def _scatter_add(self, src, rows, table):
+        _lib.check(self.hot.lib.invpref_scatter_add_rows(_lib.ptr(src), _lib.ptr(rows), rows.numel(), self.D,
+                                                         _lib.ptr(table), _lib.stream_ptr()), "scatter_add_rows")
+
+    def fetch_gen(self, sb: ShardedBatch):
+        """All-to-all of item rows: owners pack the requested rows, requesters receive them as the cache."""
+        r = sb.route
+        ns = int(r.send_rows.numel())
+        send = self._buf("send_buf", ns)
+        for t, (table, buf) in enumerate(zip((self.Iinv, self.Ienv), send)):
+            if ns:
+                self._gather(table, r.send_rows, buf)
+            yield ("all_to_all", self.cache[t][:r.n_cache], buf[:ns], r.recv_splits, r.send_splits)
+
+    # ---- train step -----------------------------------------------------------------------------------
+    def step_gen(self, sb: ShardedBatch, envs, weights, **kw):
+        """envs / weights: this rank's slices (aligned with sb.sel).  Returns the loss tensor (global values
+        after the all-reduce)."""
+        r = sb.route
+        yield from self.fetch_gen(sb)
+        self.gsmall.zero_()
+        if sb.users.numel() > 0:
+            self.hot.train_step(sb.users, r.slots, sb.scores, envs, weights, plan=sb.plan, loss_out=self.loss,
+                                grads_out=self.grads, global_batch=sb.global_batch, flags=self.flags, **kw)
+        else:
+            self.hot.step += 1
+        # partial item gradients back to the owners (reverse routing)
+        ns = int(r.send_rows.numel())
+        recv = self._buf("recv_g", ns)
+        for t in range(2):
+            yield ("all_to_all", recv[t][:ns], self.gcache[t][:r.n_cache], r.send_splits, r.recv_splits)
+        # owner: add the peers' partials in rank order (deterministic), then dense Adam on the shard
+        for t, (m, v, table) in enumerate(zip(self.mI, self.vI, (self.Iinv, self.Ienv))):
+            self.gI[t].zero_()
+            o = 0
+            for p in range(self.world):
+                n = r.send_splits[p]
+                if n:
+                    self._scatter_add(recv[t][o:o + n], r.send_rows[o:o + n], self.gI[t])
+                o += n
+            self.hot.adam_dense(table.view(-1), m.view(-1), v.view(-1), self.gI[t].view(-1))
+        # replicated E / W / b: all-reduce of a few KB (gradients + loss partial sums), same Adam on every rank
+        yield ("all_reduce", self.gsmall)
+        n_small = self.small.numel()
+        self.hot.adam_dense(self.small, self.msmall, self.vsmall, self.gsmall[:n_small])
+        return self.loss
+
+    # ---- EM re-assignment -------------------------------------------------------------------------------
+    def cluster_gen(self, sb: ShardedBatch, perm_idx, eps_table, old_envs):
+        """train.py:846-879 on this rank's share of a batch; hist / diff are all-reduced by the caller."""
+        yield from self.fetch_gen(sb)
+        if sb.users.numel() == 0:
+            z = torch.zeros(0, dtype=torch.int64, device=self.dev)
+            return z, torch.zeros(self.K, dtype=torch.int64, device=self.dev), torch.zeros(1, dtype=torch.int64,
+                                                                                           device=self.dev)
+        return self.hot.cluster(sb.users, sb.route.slots, sb.scores, perm_idx, eps_table, old_envs)
+
+    # ---- inspection (tests) -----------------------------------------------------------------------------
+    def local_tables(self):
+        return {"Uinv": self.hot.params["Uinv"], "Uenv": self.hot.params["Uenv"], "Iinv": self.Iinv,
+                "Ienv": self.Ienv, "E": self.hot.params["E"], "W": self.hot.params["W"], "b": self.hot.params["b"]}

@@ -36,7 +36,7 @@ def test_struct_layouts():
     assert C.sizeof(_lib.Params) == 56
     assert C.sizeof(_lib.Adam) == 112
     assert C.sizeof(_lib.Batch) == 48
-    assert C.sizeof(_lib.Hyper) == 96
+    assert C.sizeof(_lib.Hyper) == 112
 
 
 def test_size_queries_and_argument_checks():
