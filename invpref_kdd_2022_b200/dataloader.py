@@ -1,0 +1,110 @@
+"""Data loaders with the attribute surface the drivers / evaluators use (reference ``dataloader.py:118-243``
+``YahooImplicitBCELossDataLoader`` and ``:388-483`` ``ExplicitDataLoader``): CSV ``user_id,item_id,score`` with a
+header line -> ``int64 [N, 3]``; table sizes = max id + 1.  Host-side ingest, vectorised with numpy (the
+reference parses line by line in Python); off the hot path.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+
+def _read_csv(path: str) -> np.ndarray:
+    import pandas as pd
+    return pd.read_csv(path).values.astype(np.int64)
+
+
+def _csr(rows: np.ndarray, cols: np.ndarray, n_rows: int):
+    """Per-row sorted unique column lists as (offsets [n_rows+1], cols [nnz])."""
+    key = np.unique(rows.astype(np.int64) * (int(cols.max()) + 1 if cols.size else 1) + cols)
+    width = int(cols.max()) + 1 if cols.size else 1
+    r, c = key // width, key % width
+    off = np.zeros(n_rows + 1, dtype=np.int64)
+    np.add.at(off, r + 1, 1)
+    return np.cumsum(off), c
+
+
+class ExplicitDataLoader:
+    """reference dataloader.py:388-483."""
+
+    def __init__(self, dataset_path: str, device: torch.device, train: np.ndarray = None, test: np.ndarray = None):
+        self.dataset_path, self.device = dataset_path, device
+        self._train_data = train if train is not None else _read_csv(os.path.join(dataset_path, "train.csv"))
+        self._test_data = test if test is not None else _read_csv(os.path.join(dataset_path, "test.csv"))
+        self._user_num = int(self._train_data[:, 0].max()) + 1          # dataloader.py:406-407
+        self._item_num = int(self._train_data[:, 1].max()) + 1
+        self._test_pairs_tensor = torch.LongTensor(self._test_data[:, 0:2]).to(device)
+        self._test_scores_tensor = torch.Tensor(self._test_data[:, 2].astype(np.float64)).to(device)
+
+    user_num = property(lambda self: self._user_num)
+    item_num = property(lambda self: self._item_num)
+    train_data_np = property(lambda self: self._train_data)
+    test_data_np = property(lambda self: self._test_data)
+    train_data_len = property(lambda self: self._train_data.shape[0])
+    test_data_len = property(lambda self: self._test_data.shape[0])
+    all_test_pairs_tensor = property(lambda self: self._test_pairs_tensor)
+    all_test_scores_tensor = property(lambda self: self._test_scores_tensor)
+
+
+class YahooImplicitBCELossDataLoader:
+    """reference dataloader.py:118-243: train triples with 0/1 scores, test positives per user, the set of
+    train positives per user (masked at evaluation), optional test item pool."""
+
+    def __init__(self, dataset_path: str, device: torch.device, has_item_pool_file: bool = False,
+                 train: np.ndarray = None, test: np.ndarray = None):
+        self.dataset_path, self.device = dataset_path, device
+        self._train_data = train if train is not None else _read_csv(os.path.join(dataset_path, "train.csv"))
+        self._test_data = test if test is not None else _read_csv(os.path.join(dataset_path, "test.csv"))
+        self.has_item_pool = has_item_pool_file
+        tr, te = self._train_data, self._test_data
+        self._user_num = int(max(tr[:, 0].max(), te[:, 0].max())) + 1     # dataloader.py:179-180
+        self._item_num = int(max(tr[:, 1].max(), te[:, 1].max())) + 1
+        pos = tr[tr[:, 2] > 0]
+        self.mask_off, self.mask_items = _csr(pos[:, 0], pos[:, 1], self._user_num)
+        self.gt_off, self.gt_items = _csr(te[:, 0], te[:, 1], self._user_num)
+        # test users ascending (utils.py:228-233 sorts the user list)
+        self.test_user_list = np.unique(te[:, 0]).tolist()
+        self.test_users_tensor = torch.LongTensor(self.test_user_list).to(device)
+        if has_item_pool_file:
+            pool = _read_csv(os.path.join(dataset_path, "test_item_pool.csv"))
+            self.pool_off, self.pool_items = _csr(pool[:, 0], pool[:, 1], self._user_num)
+
+    def _row(self, off, items, user_id):
+        return set(items[off[user_id]:off[user_id + 1]].tolist())
+
+    def user_mask_items(self, user_id: int) -> set:
+        return self._row(self.mask_off, self.mask_items, user_id)
+
+    def user_highlight_items(self, user_id: int) -> set:
+        if not self.has_item_pool:
+            raise NotImplementedError('Not has item pool!')
+        return self._row(self.pool_off, self.pool_items, user_id)
+
+    def get_user_ground_truth(self, user_id: int) -> set:
+        return self._row(self.gt_off, self.gt_items, user_id)
+
+    user_num = property(lambda self: self._user_num)
+    item_num = property(lambda self: self._item_num)
+    train_data_np = property(lambda self: self._train_data)
+    test_data_np = property(lambda self: self._test_data)
+    train_data_len = property(lambda self: self._train_data.shape[0])
+    test_data_len = property(lambda self: self._test_data.shape[0])
+    all_test_users_by_sorted_tensor = property(lambda self: self.test_users_tensor)
+    all_test_users_by_sorted_list = property(lambda self: self.test_user_list)
+
+    @property
+    def get_sorted_all_test_users_ground_truth(self) -> list:
+        return [self.get_user_ground_truth(u) for u in self.test_user_list]
+
+
+def synthetic_interactions(n_users, n_items, n, implicit, seed=20220814):
+    """SURVEY.md §8d generators, for the configs whose train.csv is not in the reference checkout
+    (MovieLens, MIND: .MISSING_LARGE_BLOBS)."""
+    rng = np.random.default_rng(seed)
+    u = np.floor(n_users * rng.random(n) ** 1.5).astype(np.int64)
+    i = np.floor(n_items * rng.random(n) ** 3).astype(np.int64)
+    u[0], i[0] = n_users - 1, n_items - 1
+    y = rng.integers(0, 2, n) if implicit else rng.integers(1, 6, n)
+    return np.stack([u, i, y], axis=1).astype(np.int64)

@@ -1,0 +1,42 @@
+"""Coat_InvPref_explicit: InvPrefExplicit with the hyper-parameters of the reference driver
+(reference Coat_InvPref_explicit.py:17-67).  Run: ``python -m invpref_kdd_2022_b200.drivers.Coat_InvPref_explicit [--epochs N] [--synthetic]``."""
+import sys
+
+from . import _common
+
+MODEL_CONFIG: dict = {'env_num': 4, 'factor_num': 30, 'reg_only_embed': True, 'reg_env_embed': False}
+
+TRAIN_CONFIG: dict = {'batch_size': 1024,
+ 'epochs': 1000,
+ 'cluster_interval': 30,
+ 'evaluate_interval': 10,
+ 'lr': 0.01,
+ 'invariant_coe': 2.050646960185343,
+ 'env_aware_coe': 8.632289952059462,
+ 'env_coe': 5.100067503854663,
+ 'L2_coe': 7.731619515414727,
+ 'L1_coe': 0.0015415961377493945,
+ 'alpha': 1.7379692382330174,
+ 'use_class_re_weight': True,
+ 'use_recommend_re_weight': True,
+ 'test_begin_epoch': 0,
+ 'begin_cluster_epoch': None,
+ 'stop_cluster_epoch': None}
+
+EVALUATE_CONFIG: dict = {'eval_metric': 'mse'}
+
+RANDOM_SEED_LIST = [17373331, 17373511, 17373423]
+
+DATASET_PATH = '/Coat_explicit_all_data/'
+METRIC_LIST = ['mse', 'rmse', 'mae']
+SHAPE = (290, 300, 6960)          # (users, items, train interactions) of the dataset this config was tuned on
+
+
+def main(device, model_config: dict, train_config: dict, evaluate_config: dict, data_loader, random_seed: int,
+         silent: bool = False, auto: bool = False, query: bool = True):
+    return _common.run_main(False, device, model_config, train_config, evaluate_config, data_loader,
+                            random_seed, silent=silent, auto=auto, query=query, metric_list=METRIC_LIST)
+
+
+if __name__ == '__main__':
+    _common.cli(sys.modules[__name__], implicit=False, shape=SHAPE)

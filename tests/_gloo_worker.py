@@ -1,0 +1,61 @@
+"""Worker of tests/test_dist_gloo.py: one of WORLD_SIZE CPU processes talking over gloo."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from invpref_kdd_2022_b200.parallel import DistDriver, ItemRoute, build_route_gen  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    drv = DistDriver()
+    n_items, dim = 97, 4
+    g = torch.Generator().manual_seed(100 + rank)
+    items = torch.randint(0, n_items, (300 + 50 * rank,), generator=g)
+    route = ItemRoute()
+    drv.run(build_route_gen(items, world, route))
+    # row-sharded "table": row r of rank p holds global id r*world + p; value = id in every column
+    shard = (torch.arange(n_items)[rank::world].float()[:, None] * torch.ones(dim)).contiguous()
+    cache = torch.zeros((route.n_cache, dim))
+
+    def fetch():
+        yield ("all_to_all", cache, shard[route.send_rows].contiguous(), route.recv_splits, route.send_splits)
+
+    drv.run(fetch())
+    ok_fetch = bool(torch.equal(cache[route.slots][:, 0], items.float()))
+    # gradients back: every requester sends ones for each cached row; the owner counts requesters per row
+    recv = torch.zeros((int(route.send_rows.numel()), dim))
+
+    def back():
+        yield ("all_to_all", recv, torch.ones((route.n_cache, dim)), route.send_splits, route.recv_splits)
+
+    drv.run(back())
+    gshard = torch.zeros_like(shard)
+    o = 0
+    for p in range(world):
+        n = route.send_splits[p]
+        gshard[route.send_rows[o:o + n]] += recv[o:o + n]
+        o += n
+    # expected: number of ranks whose local batch contains the item
+    present = torch.zeros(n_items)
+    present[torch.unique(items)] = 1
+
+    def red():
+        yield ("all_reduce", present)
+
+    drv.run(red())
+    ok_back = bool(torch.equal(gshard[:, 0], present[rank::world]))
+    print(json.dumps({"rank": rank, "fetch": ok_fetch, "back": ok_back, "n_cache": route.n_cache,
+                      "recv": route.recv_splits, "send": route.send_splits}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""GPU: the driver mains run end to end (model + evaluator + trainer as in the reference's main()) and the
+evaluators agree with straightforward restatements of the reference's metric definitions."""
+import numpy as np
+import pytest
+import torch
+
+from _golden import Golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_coat_explicit_driver_main_on_real_interactions():
+    """Coat explicit (the reference's own CPU-runnable config), real train interactions from the fixture."""
+    from invpref_kdd_2022_b200.dataloader import ExplicitDataLoader
+    from invpref_kdd_2022_b200.drivers import Coat_InvPref_explicit as drv
+    g = Golden("coat_explicit")
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(0)
+    test = g.data[rng.permutation(g.N)[:1500]]
+    loader = ExplicitDataLoader("", dev, train=g.data, test=test)
+    assert (loader.user_num, loader.item_num) == (290, 300)
+    tc = dict(drv.TRAIN_CONFIG, epochs=40, evaluate_interval=10, cluster_interval=20)
+    best, idx, res = drv.main(dev, drv.MODEL_CONFIG, tc, drv.EVALUATE_CONFIG, loader, 17373331, silent=True,
+                              auto=True, query=False)
+    assert set(res) == {"mse", "rmse", "mae"} and np.isfinite(best)
+    assert abs(res["rmse"] ** 2 - res["mse"]) < 1e-6 * res["mse"]
+    assert idx[0] > 0                      # training lowers the test MSE below the epoch-0 value
+
+
+def _reference_style_metrics(rating, mask_sets, gt_sets, ks):
+    """evaluate.py:11-56 restated with python sets / numpy on the host."""
+    rating = rating.copy()
+    for r, s in enumerate(mask_sets):
+        rating[r, list(s)] = -(1 << 10)
+    top = np.argsort(-rating, axis=1, kind="stable")[:, :max(ks)]
+    out = {"ndcg": {}, "recall": {}, "precision": {}}
+    for k in ks:
+        pre = rec = nd = 0.0
+        for r, gt in enumerate(gt_sets):
+            hit = np.array([1.0 if it in gt else 0.0 for it in top[r, :k]])
+            pre += hit.sum() / k
+            rec += hit.sum() / len(gt)
+            idcg = sum(1.0 / np.log2(j + 2) for j in range(min(k, len(gt))))
+            nd += (hit / np.log2(np.arange(2, k + 2))).sum() / (idcg if idcg > 0 else 1.0)
+        n = len(gt_sets)
+        out["ndcg"][k], out["recall"][k], out["precision"][k] = nd / n, rec / n, pre / n
+    return out
+
+
+def test_implicit_evaluator_matches_metric_definitions():
+    from invpref_kdd_2022_b200.dataloader import YahooImplicitBCELossDataLoader, synthetic_interactions
+    from invpref_kdd_2022_b200.evaluate import ImplicitTestManager
+    from invpref_kdd_2022_b200.models import InvPrefImplicit
+    dev = torch.device("cuda:0")
+    tr = synthetic_interactions(120, 90, 4000, True, seed=1)
+    te = synthetic_interactions(120, 90, 600, True, seed=2)
+    te = te[te[:, 2] > 0]
+    loader = YahooImplicitBCELossDataLoader("", dev, train=tr, test=te)
+    torch.manual_seed(0)
+    model = InvPrefImplicit(loader.user_num, loader.item_num, 2, 16).to(dev)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(30.0)
+    ev = ImplicitTestManager(model, loader, test_batch_size=50, top_k_list=[7, 3, 5])
+    got = ev.evaluate()
+    users = loader.all_test_users_by_sorted_list
+    assert users == sorted(set(te[:, 0].tolist()))
+    rating = model.predict(loader.all_test_users_by_sorted_tensor).detach().cpu().numpy()
+    ref = _reference_style_metrics(rating, [loader.user_mask_items(u) for u in users],
+                                   loader.get_sorted_all_test_users_ground_truth, [3, 5, 7])
+    for m in ref:
+        assert list(got[m]) == [3, 5, 7]
+        for k in ref[m]:
+            assert abs(got[m][k] - ref[m][k]) < 1e-9, (m, k)
+
+
+def test_implicit_driver_main_synthetic():
+    from invpref_kdd_2022_b200.dataloader import YahooImplicitBCELossDataLoader, synthetic_interactions
+    from invpref_kdd_2022_b200.drivers import Yahoo_InvPref_Implicit as drv
+    dev = torch.device("cuda:0")
+    tr = synthetic_interactions(500, 200, 30000, True, seed=3)
+    te = synthetic_interactions(500, 200, 3000, True, seed=4)
+    loader = YahooImplicitBCELossDataLoader("", dev, train=tr, test=te[te[:, 2] > 0])
+    tc = dict(drv.TRAIN_CONFIG, epochs=6, evaluate_interval=3, cluster_interval=2)
+    best, idx = drv.main(dev, drv.MODEL_CONFIG, tc, drv.EVALUATE_CONFIG, loader, 17373331, silent=True, auto=True,
+                         query=False)
+    assert 0.0 <= best <= 1.0 and len(idx) >= 1
