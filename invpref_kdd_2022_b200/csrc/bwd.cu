@@ -251,6 +251,16 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
             b2 = block_sum_double(b2, sbuf);
             b1 = block_sum_double(b1, sbuf);
         }
+        // env-embedding norms over the gathered rows (models.py:499-504) = sum_k count_k * |E_k|
+        double e2 = 0.0, e1 = 0.0;
+        if (a.reg_env_embed) {
+            for (int idx = tid; idx < KD; idx += TAIL_THREADS) {
+                const double x = a.E_in[idx], c = stot[P_CNT + idx / D];
+                e2 += c * x * x; e1 += c * fabs(x);
+            }
+            e2 = block_sum_double(e2, sbuf);
+            e1 = block_sum_double(e1, sbuf);
+        }
         if (tid == 0 && a.loss_out != nullptr) {
             const float inv_loss = (float)(stot[0] / Bf);
             const float ea_loss = (float)(stot[1] / Bf);
@@ -261,8 +271,8 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
                 L1 += w1 / (Df * K) + b1 / K;
             }
             if (a.reg_env_embed) {
-                L2 += stot[5] / (Bf * Df);
-                L1 += stot[6] / (Bf * Df);
+                L2 += e2 / (Bf * Df);
+                L1 += e1 / (Bf * Df);
             }
             const float L2f = (float)L2, L1f = (float)L1;
             a.loss_out[0] = inv_loss;

