@@ -206,8 +206,8 @@ int64_t invpref_launch_count(void);
  * their kernels on the call's stream (no synchronisation); n = 0 disables and frees the events.
  * invpref_profile_read(step, out_ms_host): after the caller has synchronised the stream, elapsed
  * milliseconds of each phase of recorded step `step` (0-based), INVPREF_NUM_PHASES floats in the
- * order: plan build, forward, item chunks, user chunks, item rows, user rows, item sweep, user sweep,
- * tail.  invpref_profile_steps(): number of steps recorded since the last enable. */
+ * order: plan build, forward (empty on the fused path), user chunks, user rows (fused user pass:
+ * forward + user-side reduce + Adam), item chunks, item rows, item sweep, user sweep, tail.  invpref_profile_steps(): number of steps recorded since the last enable. */
 #define INVPREF_NUM_PHASES 9
 int invpref_profile_enable(int max_steps);
 int invpref_profile_steps(void);

@@ -25,7 +25,8 @@ EXPORTS = (
     "invpref_env_hist", "invpref_launch_count", "invpref_profile_enable", "invpref_profile_steps",
     "invpref_profile_read", "invpref_adam_dense", "invpref_gather_rows", "invpref_scatter_add_rows",
 )
-PHASES = ("plan", "forward", "chunks_items", "chunks_users", "rows_items", "rows_users", "sweep_items",
+# execution order; on the fused path "forward" is empty and chunks_users / rows_users are the fused user pass
+PHASES = ("plan", "forward", "chunks_users", "rows_users", "chunks_items", "rows_items", "sweep_items",
           "sweep_users", "tail")
 
 

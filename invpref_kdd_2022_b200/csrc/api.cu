@@ -1,5 +1,6 @@
 // extern "C" entry points of libinvpref_b200.so (see include/invpref_b200.h).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -62,6 +63,15 @@ void carve_plan(const invpref_desc* d, int64_t B, char* plan, PlanSide* pu, Plan
     *pi = carve_plan_side(plan + plan_side_bytes(Bp, d->n_users), Bp, d->n_items);
     pu->B = B;
     pi->B = B;
+}
+
+// INVPREF_FUSED=0 selects the unfused path (forward kernel + separate user-side rows kernel) for A/B runs
+bool use_fused_user_pass(const Geometry& g) {
+    static const bool enabled = [] {
+        const char* e = getenv("INVPREF_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    return enabled && upass_supported(g);
 }
 
 int build_plan_impl(const invpref_desc* d, const int64_t* users, const int64_t* items, int64_t B, char* plan,
@@ -239,24 +249,7 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     carve_plan(desc, B, (char*)plan_base, &pu, &pi);
     pm.mark();
 
-    // (1)+(2) fused forward, losses, per-interaction gradients, dW/db/dE partials
-    FwdTrainArgs f;
-    f.Uinv = pin->Uinv; f.Iinv = pin->Iinv; f.Uenv = pin->Uenv; f.Ienv = pin->Ienv;
-    f.E = pin->E; f.W = pin->W; f.b = pin->b;
-    f.users = batch->users; f.items = batch->items; f.envs = batch->envs;
-    f.scores = batch->scores; f.weights = batch->weights; f.B = B;
-    f.D = g.D; f.K = g.K; f.GS = g.GS;
-    f.implicit = desc->implicit; f.reg_env_embed = desc->reg_env_embed;
-    f.use_class_rw = hyper->use_class_rw; f.use_rec_rw = hyper->use_rec_rw;
-    f.c_inv = (float)hyper->c_inv; f.c_ea = (float)hyper->c_ea; f.c_env = (float)hyper->c_env;
-    f.neg_alpha = (float)(-hyper->alpha); f.invB = 1.f / (float)Bg;
-    f.gpack = w.gpack; f.partials = w.partials; f.P = fwd_partial_floats(g);
-    f.up_s_inv = f.up_s_env = f.up_logp = nullptr; f.generic = 0;
-    const int fgrid = fwd_train_grid(B);
-    if ((rc = launch_fwd_train(g, f, fgrid, st)) != INVPREF_OK) return rc;
-    pm.mark();
-
-    // (3)+(4) segmented backward feeding Adam (or exporting the partial gradients), per side
+    // (3)+(4) arguments of the segmented backward feeding Adam (or exporting partial gradients), per side
     const AdamScalars as = make_adam(hyper);
     const double bd2 = (double)Bg * g.D * 2.0;
     BwdSideArgs su, si;
@@ -275,13 +268,50 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     si.plan = pi; si.chunk_part = w.chunk_part_i;
     si.reg2 = su.reg2; si.reg1 = su.reg1; si.adam = as;
 
+    const int P = fwd_partial_floats(g);
+    int n_partials;
+    if (use_fused_user_pass(g)) {
+        // (1)+(2)+(3u)+(4u) fused USER PASS: forward, losses, user-side segment reduce, Adam on user rows
+        UserPassArgs up;
+        up.side = su;
+        up.b = pin->b; up.envs = batch->envs; up.scores = batch->scores; up.weights = batch->weights;
+        up.implicit = desc->implicit; up.use_class_rw = hyper->use_class_rw; up.use_rec_rw = hyper->use_rec_rw;
+        up.c_inv = (float)hyper->c_inv; up.c_ea = (float)hyper->c_ea; up.c_env = (float)hyper->c_env;
+        up.neg_alpha = (float)(-hyper->alpha); up.invB = 1.f / (float)Bg;
+        up.gpack_out = w.gpack; up.partials = w.partials; up.P = P;
+        const int ugrid = upass_rows_grid(pu.max_seg);
+        n_partials = ugrid + UPASS_CHUNK_CTAS;
+        pm.mark();   // "forward" phase is empty on this path
+        if ((rc = launch_upass_chunks(g, up, ugrid, st)) != INVPREF_OK) return rc;
+        pm.mark();
+        if ((rc = launch_upass_rows(g, up, exp_u ? EPI_EXPORT : EPI_ADAM, ugrid, st)) != INVPREF_OK) return rc;
+        pm.mark();
+    } else {
+        // (1)+(2) forward, losses, per-interaction gradients, dW/db/dE partials; then the user side
+        FwdTrainArgs f;
+        f.Uinv = pin->Uinv; f.Iinv = pin->Iinv; f.Uenv = pin->Uenv; f.Ienv = pin->Ienv;
+        f.E = pin->E; f.W = pin->W; f.b = pin->b;
+        f.users = batch->users; f.items = batch->items; f.envs = batch->envs;
+        f.scores = batch->scores; f.weights = batch->weights; f.B = B;
+        f.D = g.D; f.K = g.K; f.GS = g.GS;
+        f.implicit = desc->implicit; f.reg_env_embed = desc->reg_env_embed;
+        f.use_class_rw = hyper->use_class_rw; f.use_rec_rw = hyper->use_rec_rw;
+        f.c_inv = (float)hyper->c_inv; f.c_ea = (float)hyper->c_ea; f.c_env = (float)hyper->c_env;
+        f.neg_alpha = (float)(-hyper->alpha); f.invB = 1.f / (float)Bg;
+        f.gpack = w.gpack; f.partials = w.partials; f.P = P;
+        f.up_s_inv = f.up_s_env = f.up_logp = nullptr; f.generic = 0;
+        n_partials = fwd_train_grid(B);
+        if ((rc = launch_fwd_train(g, f, n_partials, st)) != INVPREF_OK) return rc;
+        pm.mark();
+        if ((rc = launch_bwd_chunks(g, su, st)) != INVPREF_OK) return rc;
+        pm.mark();
+        if ((rc = launch_bwd_rows(g, su, exp_u ? EPI_EXPORT : EPI_ADAM, st)) != INVPREF_OK) return rc;
+        pm.mark();
+    }
+    // item pass: reads the g-pack and the OLD user rows
     if ((rc = launch_bwd_chunks(g, si, st)) != INVPREF_OK) return rc;
     pm.mark();
-    if ((rc = launch_bwd_chunks(g, su, st)) != INVPREF_OK) return rc;
-    pm.mark();
     if ((rc = launch_bwd_rows(g, si, exp_i ? EPI_EXPORT : EPI_ADAM, st)) != INVPREF_OK) return rc;
-    pm.mark();
-    if ((rc = launch_bwd_rows(g, su, exp_u ? EPI_EXPORT : EPI_ADAM, st)) != INVPREF_OK) return rc;
     pm.mark();
     if (!exp_i && (rc = launch_sweep(g, si, st)) != INVPREF_OK) return rc;
     pm.mark();
@@ -290,7 +320,7 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
 
     // losses, E / W / b gradients and their Adam update (or export)
     TailArgs t;
-    t.partials = w.partials; t.n_partials = fgrid; t.P = f.P; t.B = Bg; t.D = g.D; t.K = g.K;
+    t.partials = w.partials; t.n_partials = n_partials; t.P = P; t.B = Bg; t.D = g.D; t.K = g.K;
     t.reg_only_embed = desc->reg_only_embed || (hyper->flags & INVPREF_SKIP_PARAM_REG);
     t.reg_env_embed = desc->reg_env_embed;
     t.c_inv = (float)hyper->c_inv; t.c_ea = (float)hyper->c_ea; t.c_env = (float)hyper->c_env;

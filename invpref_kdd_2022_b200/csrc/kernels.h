@@ -59,6 +59,26 @@ int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stre
 int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream_t stream);
 int launch_sweep(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);
 
+// ---- upass.cu: fused forward + user-side backward + Adam ---------------------------------------------
+constexpr int UPASS_CHUNK_CTAS = 74;   // CTAs of the (usually idle) long-user-segment kernel
+
+struct UserPassArgs {
+    BwdSideArgs side;        // own = user tables, partner = item tables, plan = user side
+    const float* b;
+    const int64_t* envs;
+    const float *scores, *weights;
+    int implicit, use_class_rw, use_rec_rw;
+    float c_inv, c_ea, c_env, neg_alpha, invB;
+    float* gpack_out;        // [B, GS], written for the item pass
+    float* partials;         // [rows grid + UPASS_CHUNK_CTAS, P]
+    int P;
+};
+
+bool upass_supported(const Geometry& g);
+int upass_rows_grid(int64_t max_seg);
+int launch_upass_chunks(const Geometry& g, const UserPassArgs& a, int cta_offset, cudaStream_t stream);
+int launch_upass_rows(const Geometry& g, const UserPassArgs& a, int epi, int grid, cudaStream_t stream);
+
 struct TailArgs {
     const float* partials;
     int n_partials, P;
