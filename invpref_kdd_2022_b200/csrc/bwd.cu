@@ -29,8 +29,18 @@ __device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const flo
     const int D = a.D, K = a.K, GS = a.GS;
     const int32_t* __restrict__ perm = a.plan.perm;
     const int32_t* __restrict__ partner = a.plan.partner;
-#pragma unroll 2
+    // software pipeline: the partner rows / g-pack of interaction k+PF are requested into L2 now; their
+    // indices were loaded one iteration earlier, so the (in-order) warp never waits for them
+    constexpr int PF = 4;
+    int pid_q = 0, n_q = 0;
+    if (beg + PF < end) { pid_q = partner[beg + PF]; n_q = perm[beg + PF]; }
     for (int k = beg; k < end; ++k) {
+        if (k + PF < end) {
+            prefetch_row(a.partner_inv, pid_q, D, lane);
+            prefetch_row(a.partner_env, pid_q, D, lane);
+            if (lane == 8) prefetch_l2(a.gpack + (int64_t)n_q * GS);
+        }
+        if (k + 1 + PF < end) { pid_q = partner[k + 1 + PF]; n_q = perm[k + 1 + PF]; }
         const int n = perm[k];
         const int pid = partner[k];
         const float4* gp = reinterpret_cast<const float4*>(a.gpack + (int64_t)n * GS);
@@ -230,9 +240,17 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
     const int tid = threadIdx.x;
     const int K = a.K, D = a.D, KD = a.K * a.D;
     for (int idx = tid; idx < a.P; idx += TAIL_THREADS) {
-        double s = 0.0;
-        for (int b = 0; b < a.n_partials; ++b) s += (double)a.partials[(int64_t)b * a.P + idx];
-        stot[idx] = s;
+        // four interleaved accumulators (fixed assignment => still deterministic) keep four loads in flight
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int b = 0;
+        for (; b + 3 < a.n_partials; b += 4) {
+            s0 += (double)a.partials[(int64_t)b * a.P + idx];
+            s1 += (double)a.partials[(int64_t)(b + 1) * a.P + idx];
+            s2 += (double)a.partials[(int64_t)(b + 2) * a.P + idx];
+            s3 += (double)a.partials[(int64_t)(b + 3) * a.P + idx];
+        }
+        for (; b < a.n_partials; ++b) s0 += (double)a.partials[(int64_t)b * a.P + idx];
+        stot[idx] = (s0 + s1) + (s2 + s3);
     }
     __syncthreads();
     const double Bf = (double)a.B, Df = (double)D;

@@ -16,10 +16,16 @@ constexpr int GROUP = 16;
 constexpr int BLOCK = 256;                 // threads per CTA for the row kernels (16 groups)
 constexpr int GROUPS_PER_BLOCK = BLOCK / GROUP;
 
-// Segments longer than LONG_T interactions are pre-reduced in CHUNK-sized pieces by separate
-// groups (fixed shape => deterministic), the owner row then sums the partials in order.
-constexpr int LONG_T = 512;
-constexpr int CHUNK = 256;
+// Segments longer than 2*chunk interactions are pre-reduced in chunk-sized pieces by separate groups
+// (fixed shape => deterministic), the owner row then sums the partials in order.  A segment is reduced
+// serially by one group, so the chunk bounds the critical path: small batches (B = 64K..256K with a few
+// hot rows) need small chunks to spread the hot rows over the machine, large ones amortise better with
+// big chunks.  chunk is a function of the batch size only.
+inline int chunk_for(int64_t B) {
+    int64_t c = 16;
+    while (c < 256 && c * 8192 < B) c *= 2;
+    return (int)c;
+}
 
 struct Geometry {
     int D, K;
@@ -104,7 +110,13 @@ struct PlanSide {
 };
 
 inline int64_t plan_max_seg(int64_t B, int64_t rows) { return B < rows ? B : rows; }
-inline int64_t plan_max_chunks(int64_t B) { return B / CHUNK + B / LONG_T + 2; }
+// Upper bound on the chunk count of a batch of AT MOST B interactions (monotonic in B, so a workspace sized
+// for the largest batch also fits every shorter one): chunks <= 1.5 * B' / chunk_for(B') for any B' <= B.
+inline int64_t plan_max_chunks(int64_t B) {
+    int64_t small = B / 16 < 16384 ? B / 16 : 16384;
+    int64_t big = B / 256;
+    return 3 * (small > big ? small : big) / 2 + 4;
+}
 
 inline size_t plan_side_bytes(int64_t B, int64_t rows) {
     int64_t S = plan_max_seg(B, rows);
@@ -138,7 +150,7 @@ inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
 }
 
 // ---- workspace layout ------------------------------------------------------------------------
-constexpr int FWD_MAX_BLOCKS = 148 * 8;
+constexpr int FWD_MAX_BLOCKS = 148 * 4 + 74;   // upper bound on CTAs that write a partial-sum vector
 
 struct Workspace {
     float* gpack;        // [B * GS]

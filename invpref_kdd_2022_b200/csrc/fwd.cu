@@ -370,7 +370,7 @@ int grid_for_groups(int64_t B, int max_blocks) {
 
 }  // namespace
 
-int fwd_train_grid(int64_t B) { return grid_for_groups(B, FWD_MAX_BLOCKS); }
+int fwd_train_grid(int64_t B) { return grid_for_groups(B, 148 * 4); }
 
 int launch_fwd_train(const Geometry& g, const FwdTrainArgs& a, int grid, cudaStream_t stream) {
     size_t smem = (size_t)(4 + GROUPS_PER_BLOCK) * g.K * g.D * sizeof(float);

@@ -58,19 +58,19 @@ __global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const 
     }
 }
 
-__global__ void chunk_counts_kernel(PlanSide p) {
+__global__ void chunk_counts_kernel(PlanSide p, int chunk) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s > p.max_seg) return;
     int32_t n_seg = p.counters[0];
     int32_t c = 0;
     if (s < n_seg) {
         int32_t len = p.seg_off[s + 1] - p.seg_off[s];
-        if (len > LONG_T) c = (len + CHUNK - 1) / CHUNK;
+        if (len > 2 * chunk) c = (len + chunk - 1) / chunk;
     }
     p.seg_chunk[s] = c;
 }
 
-__global__ void write_chunks_kernel(PlanSide p) {
+__global__ void write_chunks_kernel(PlanSide p, int chunk) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int32_t n_seg = p.counters[0];
     if (s == 0) p.counters[1] = p.seg_chunk[n_seg];
@@ -79,8 +79,8 @@ __global__ void write_chunks_kernel(PlanSide p) {
     if (c1 == c0) return;
     int32_t beg = p.seg_off[s], end = p.seg_off[s + 1];
     for (int32_t c = c0; c < c1; ++c) {
-        int32_t b = beg + (c - c0) * CHUNK;
-        int32_t e = b + CHUNK < end ? b + CHUNK : end;
+        int32_t b = beg + (c - c0) * chunk;
+        int32_t e = b + chunk < end ? b + chunk : end;
         reinterpret_cast<int4*>(p.chunk_desc)[c] = make_int4((int32_t)s, b, e, 0);
     }
 }
@@ -166,10 +166,10 @@ int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_
     cb = t.cub_bytes;
     cub::DeviceScan::InclusiveSum(t.cub_tmp, cb, t.scan, t.scan, (int)B, stream);
     write_segments_kernel<<<grid_for(B), 256, 0, stream>>>(t.keys_out, t.scan, p.perm, other_ids, other_rows, B, p);
-    chunk_counts_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p);
+    chunk_counts_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B));
     cb = t.cub_bytes;
     cub::DeviceScan::ExclusiveSum(t.cub_tmp, cb, p.seg_chunk, p.seg_chunk, (int)(p.max_seg + 1), stream);
-    write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p);
+    write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p, chunk_for(B));
     count_launch(5 + 6);   // 5 of ours + CUB's (radix passes, 2 scans; approximate)
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

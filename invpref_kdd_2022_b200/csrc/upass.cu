@@ -392,7 +392,7 @@ bool upass_supported(const Geometry& g) { return upass_smem(g) <= 96 * 1024; }
 int upass_rows_grid(int64_t max_seg) {
     int64_t need = (max_seg + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
     if (need < 1) need = 1;
-    return (int)(need < FWD_MAX_BLOCKS - UPASS_CHUNK_CTAS ? need : FWD_MAX_BLOCKS - UPASS_CHUNK_CTAS);
+    return (int)(need < 148 * 4 ? need : 148 * 4);
 }
 
 int launch_upass_chunks(const Geometry& g, const UserPassArgs& a, int cta_offset, cudaStream_t stream) {
