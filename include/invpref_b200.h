@@ -105,6 +105,9 @@ typedef struct {
 #define INVPREF_EXPORT_ITEM_GRADS 2   /* Iinv, Ienv */
 #define INVPREF_EXPORT_SMALL_GRADS 4  /* E, W, b; loss_out then holds this rank's partial sums */
 #define INVPREF_SKIP_PARAM_REG 8      /* leave out the classifier's own L1/L2 term (all ranks but one) */
+#define INVPREF_DEFER_USER_SWEEP 16   /* skip the dense Adam sweep over user rows without a gradient: the
+                                         caller runs invpref_user_sweep itself (e.g. on a second stream, so
+                                         that it overlaps the NVLink exchange of the item gradients) */
 
 const char* invpref_strerror(int status);
 int invpref_abi_version(void);
@@ -189,6 +192,12 @@ int invpref_env_hist(const int64_t* envs, int64_t N, int32_t n_envs, int64_t* hi
  * reduction): theta, m, v updated in place.  Uses lr/betas/eps/step of `hyper`. */
 int invpref_adam_dense(float* theta, float* m, float* v, const float* grad, int64_t n, const invpref_hyper* hyper,
                        void* stream);
+
+/* The deferred part of invpref_train_step (INVPREF_DEFER_USER_SWEEP): dense Adam (zero gradient) on every
+ * user row that has no segment in `plan` (built for a batch of B interactions), reading params_in and writing
+ * params_out / the Adam state.  Must use the same step / lr / betas / eps as the train step it completes. */
+int invpref_user_sweep(const invpref_desc* desc, const invpref_params* params_in, invpref_params* params_out,
+                       invpref_adam* adam, const invpref_hyper* hyper, const void* plan, int64_t B, void* stream);
 
 /* out[j, :] = table[rows[j], :] for j < n (row-sharded tables: rows a peer asked for). */
 int invpref_gather_rows(const float* table, const int64_t* rows, int64_t n, int32_t dim, float* out, void* stream);

@@ -24,6 +24,7 @@ EXPORTS = (
     "invpref_backward", "invpref_train_step", "invpref_cluster", "invpref_stat_envs",
     "invpref_env_hist", "invpref_launch_count", "invpref_profile_enable", "invpref_profile_steps",
     "invpref_profile_read", "invpref_adam_dense", "invpref_gather_rows", "invpref_scatter_add_rows",
+    "invpref_user_sweep",
 )
 # execution order; on the fused path "forward" is empty and chunks_users / rows_users are the fused user pass
 PHASES = ("plan", "forward", "chunks_users", "rows_users", "chunks_items", "rows_items", "sweep_items",
@@ -56,7 +57,7 @@ class Hyper(C.Structure):
                 ("use_rec_rw", C.c_int32), ("global_batch", C.c_int64), ("flags", C.c_int32), ("_pad", C.c_int32)]
 
 
-EXPORT_USER_GRADS, EXPORT_ITEM_GRADS, EXPORT_SMALL_GRADS, SKIP_PARAM_REG = 1, 2, 4, 8
+EXPORT_USER_GRADS, EXPORT_ITEM_GRADS, EXPORT_SMALL_GRADS, SKIP_PARAM_REG, DEFER_USER_SWEEP = 1, 2, 4, 8, 16
 
 
 _lib = None
@@ -91,6 +92,8 @@ def load() -> C.CDLL:
     lib.invpref_stat_envs.argtypes = [vp, i64, C.c_int32, vp, vp, vp, vp]
     lib.invpref_env_hist.argtypes = [vp, i64, C.c_int32, vp, vp]
     lib.invpref_adam_dense.argtypes = [vp, vp, vp, vp, i64, C.POINTER(Hyper), vp]
+    lib.invpref_user_sweep.argtypes = [C.POINTER(Desc), C.POINTER(Params), C.POINTER(Params), C.POINTER(Adam),
+                                       C.POINTER(Hyper), vp, i64, vp]
     lib.invpref_gather_rows.argtypes = [vp, vp, i64, C.c_int32, vp, vp]
     lib.invpref_scatter_add_rows.argtypes = [vp, vp, i64, C.c_int32, vp, vp]
     lib.invpref_profile_enable.argtypes = [C.c_int]

@@ -315,7 +315,7 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     pm.mark();
     if (!exp_i && (rc = launch_sweep(g, si, st)) != INVPREF_OK) return rc;
     pm.mark();
-    if (!exp_u && (rc = launch_sweep(g, su, st)) != INVPREF_OK) return rc;
+    if (!exp_u && !(hyper->flags & INVPREF_DEFER_USER_SWEEP) && (rc = launch_sweep(g, su, st)) != INVPREF_OK) return rc;
     pm.mark();
 
     // losses, E / W / b gradients and their Adam update (or export)
@@ -335,6 +335,24 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     pm.mark();
     pm.done();
     return rc;
+}
+
+int invpref_user_sweep(const invpref_desc* desc, const invpref_params* pin, invpref_params* pout, invpref_adam* adam,
+                       const invpref_hyper* hyper, const void* plan, int64_t B, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, pin)) != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, pout)) != INVPREF_OK) return rc;
+    if (!adam || !hyper || !plan || B < 0 || hyper->step < 1) return INVPREF_ERR_BAD_ARG;
+    if (pin->Uinv == pout->Uinv || pin->Uenv == pout->Uenv) return INVPREF_ERR_BAD_ARG;
+    PlanSide pu, pi;
+    carve_plan(desc, B, (char*)plan, &pu, &pi);
+    BwdSideArgs su = {};
+    su.own_inv_in = pin->Uinv; su.own_env_in = pin->Uenv; su.own_inv_out = pout->Uinv; su.own_env_out = pout->Uenv;
+    su.m_inv = adam->m.Uinv; su.m_env = adam->m.Uenv; su.v_inv = adam->v.Uinv; su.v_env = adam->v.Uenv;
+    su.plan = pu; su.D = g.D; su.K = g.K; su.GS = g.GS; su.adam = make_adam(hyper);
+    return launch_sweep(g, su, (cudaStream_t)stream);
 }
 
 int invpref_adam_dense(float* theta, float* m, float* v, const float* grad, int64_t n, const invpref_hyper* hyper,

@@ -45,7 +45,7 @@ def run(args, w):
 
         def step(s):
             sb, le, sw = prepared[s % nb]
-            return drv.run(tr.step_gen(sb, le, sw, **kw))
+            return drv.run(tr.step_gen(sb, le, sw, next_sb=prepared[(s + 1) % nb][0], **kw))
         mode = f"users+items row-sharded (mod {world}), interactions routed to the user's owner, " \
                f"item rows/grads all-to-all, E/W/b all-reduce"
     else:
@@ -68,6 +68,8 @@ def run(args, w):
     for s in range(args.warmup):
         step(s)
     torch.cuda.synchronize()
+    if sharded:
+        tr.phase_events = []
     clocks = B.ClockSampler(dev.index)
     if rank == 0:
         clocks.start()
@@ -87,6 +89,14 @@ def run(args, w):
     ms = float(ms.item()) / args.steps
     assert torch.isfinite(loss).all()
     clk = clocks.stop() if rank == 0 else None
+    phases = {}
+    if sharded and tr.phase_events:
+        evs = tr.phase_events
+        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+            if n1 != "start":
+                phases[n1] = phases.get(n1, 0.0) + e0.elapsed_time(e1) / args.steps
+        info = [sb.route.n_cache for sb, _, _ in prepared], [int(sb.users.numel()) for sb, _, _ in prepared]
+        phases["cache_rows"], phases["local_batch"] = info[0][0], info[1][0]
     peak, peak_src = B.measured_peaks()
     sbytes = B.step_bytes(Bg, D, K, P)
     if rank == 0:
@@ -104,6 +114,7 @@ def run(args, w):
                 "e2e": {"value": Bg / (ms * 1e-3), "unit": "interactions/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0,
                         "note": "multi-GPU leg times device-resident batches only; see the 1-GPU line for e2e"},
-                "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss[5])}
+                "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss[5]),
+                "rank0_phase_ms": phases}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

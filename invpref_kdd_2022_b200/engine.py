@@ -129,6 +129,19 @@ class HotPath:
             self.on_swap(self.params)
         return loss_out
 
+    def user_sweep(self, plan: torch.Tensor, B: int):
+        """The deferred dense sweep of the step that just ran with ``DEFER_USER_SWEEP`` (call it after
+        ``train_step`` returned, i.e. after the buffer swap: it reads the old set and writes the current one)."""
+        hyper = _lib.Hyper(0, 0, 0, 0, 0, 0, self.lr, self.betas[0], self.betas[1], self.eps, int(self.step), 0, 0,
+                           0, 0, 0)
+        old = dict(self.params)
+        old.update({k: self.shadow[k] for k in ("Uinv", "Uenv")})
+        p_in, p_out = _lib.make_params(old), _lib.make_params(self.params)
+        adam = _lib.Adam(_lib.make_params(self.m), _lib.make_params(self.v))
+        _lib.check(self.lib.invpref_user_sweep(C.byref(self.desc), C.byref(p_in), C.byref(p_out), C.byref(adam),
+                                               C.byref(hyper), _lib.ptr(plan), int(B), _lib.stream_ptr()),
+                   "user_sweep")
+
     # ---- forward / backward (autograd-compatible path) ----------------------------------------
     def forward(self, users, items, envs, want_logp=True):
         B = users.numel()

@@ -273,6 +273,15 @@ class ShardedTrainer:
         self.flags = _lib.EXPORT_ITEM_GRADS | _lib.EXPORT_SMALL_GRADS | (0 if rank == 0 else _lib.SKIP_PARAM_REG)
         self.send_buf = None
         self.recv_g = None
+        self._fetched = None                      # batch whose item rows are currently in the cache
+        self.side = torch.cuda.Stream(device=device)
+        self.phase_events = None                  # set to [] to record (name, event) marks per step (bench)
+
+    def _mark(self, name):
+        if self.phase_events is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phase_events.append((name, ev))
 
     # ---- setup -------------------------------------------------------------------------------------
     def prepare_gen(self, users_g, items_g, scores_g):
@@ -285,8 +294,7 @@ class ShardedTrainer:
         yield from build_route_gen(items_g[sb.sel], self.world, sb.route)
         if sb.route.n_cache > self.cache_rows:
             raise RuntimeError(f"item cache too small: {sb.route.n_cache} > {self.cache_rows}")
-        if sb.users.numel() > 0:
-            sb.plan = self.hot.new_plan(sb.users, sb.route.slots)
+        sb.plan = self.hot.new_plan(sb.users, sb.route.slots)      # also for an empty share (sweep needs it)
         return sb
 
     def _buf(self, name, rows):
@@ -315,22 +323,41 @@ class ShardedTrainer:
             yield ("all_to_all", self.cache[t][:r.n_cache], buf[:ns], r.recv_splits, r.send_splits)
 
     # ---- train step -----------------------------------------------------------------------------------
-    def step_gen(self, sb: ShardedBatch, envs, weights, **kw):
+    def step_gen(self, sb: ShardedBatch, envs, weights, next_sb: ShardedBatch = None, **kw):
         """envs / weights: this rank's slices (aligned with sb.sel).  Returns the loss tensor (global values
-        after the all-reduce)."""
+        after the all-reduce).
+
+        Overlap: the dense Adam sweep over the local user rows without a gradient (the largest local kernel,
+        pure HBM streaming) runs on a side stream while the main stream exchanges the item gradients over
+        NVLink, updates the item shard and the replicated tensors, and already fetches the item rows of
+        `next_sb` (the batch order is fixed, so the next batch is known)."""
         r = sb.route
-        yield from self.fetch_gen(sb)
+        self._mark("start")
+        if self._fetched is not sb:
+            yield from self.fetch_gen(sb)
+        self._fetched = None
+        self._mark("fetch")
         self.gsmall.zero_()
+        self.hot._ensure_state(("Uinv", "Uenv"))
+        main = torch.cuda.current_stream()
         if sb.users.numel() > 0:
             self.hot.train_step(sb.users, r.slots, sb.scores, envs, weights, plan=sb.plan, loss_out=self.loss,
-                                grads_out=self.grads, global_batch=sb.global_batch, flags=self.flags, **kw)
-        else:
+                                grads_out=self.grads, global_batch=sb.global_batch,
+                                flags=self.flags | _lib.DEFER_USER_SWEEP, **kw)
+        else:       # no interaction routed here: every local user row still moves by momentum
             self.hot.step += 1
+            for k in ("Uinv", "Uenv"):
+                self.hot.params[k], self.hot.shadow[k] = self.hot.shadow[k], self.hot.params[k]
+        self._mark("local_step")
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self.hot.user_sweep(sb.plan, sb.users.numel())
         # partial item gradients back to the owners (reverse routing)
         ns = int(r.send_rows.numel())
         recv = self._buf("recv_g", ns)
         for t in range(2):
             yield ("all_to_all", recv[t][:ns], self.gcache[t][:r.n_cache], r.send_splits, r.recv_splits)
+        self._mark("grad_a2a")
         # owner: add the peers' partials in rank order (deterministic), then dense Adam on the shard
         for t, (m, v, table) in enumerate(zip(self.mI, self.vI, (self.Iinv, self.Ienv))):
             self.gI[t].zero_()
@@ -341,10 +368,18 @@ class ShardedTrainer:
                     self._scatter_add(recv[t][o:o + n], r.send_rows[o:o + n], self.gI[t])
                 o += n
             self.hot.adam_dense(table.view(-1), m.view(-1), v.view(-1), self.gI[t].view(-1))
+        self._mark("item_adam")
         # replicated E / W / b: all-reduce of a few KB (gradients + loss partial sums), same Adam on every rank
         yield ("all_reduce", self.gsmall)
         n_small = self.small.numel()
         self.hot.adam_dense(self.small, self.msmall, self.vsmall, self.gsmall[:n_small])
+        self._mark("small")
+        if next_sb is not None:       # the cache is free again: fetch the next batch's item rows now
+            yield from self.fetch_gen(next_sb)
+            self._fetched = next_sb
+        self._mark("prefetch_next")
+        main.wait_stream(self.side)
+        self._mark("sweep_wait")
         return self.loss
 
     # ---- EM re-assignment -------------------------------------------------------------------------------
