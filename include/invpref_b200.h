@@ -68,6 +68,19 @@ typedef struct {
 typedef struct {
     invpref_params m;
     invpref_params v;
+    /* Optional LAZY dense Adam for the user tables (all three NULL/0 = plain dense mode).
+     * torch.optim.Adam moves every row every step, also rows without a gradient (momentum).  In lazy mode a
+     * user row that is not in the batch is left untouched in memory; user_last_step[r] remembers the step
+     * it is updated to, and the skipped zero-gradient steps are replayed in registers -- with each step's
+     * own bias corrections from `sched`, same arithmetic, same order, hence bit-identical -- when the row
+     * is next touched by a batch, or by invpref_flush_users.  In this mode the user tables are updated IN
+     * PLACE (params_out->Uinv/Uenv must alias params_in): the rows every reader of the step needs are
+     * stashed in the workspace by the user pass.  Anything outside invpref_train_step that reads the user
+     * tables (invpref_cluster, invpref_forward, predict, state_dict) needs invpref_flush_users first. */
+    int32_t* user_last_step;   /* [n_users], zero-initialised */
+    float* sched;              /* [sched_cap][2]: (lr/bc1, 1/sqrt(bc2)) of every step so far; entry t is
+                                  written by the train step with hyper.step == t */
+    int64_t sched_cap;
 } invpref_adam;
 
 /* One mini-batch = rows [s*B, (s+1)*B) of the training tensors (utils.py:12-19). */
@@ -192,6 +205,11 @@ int invpref_env_hist(const int64_t* envs, int64_t N, int32_t n_envs, int64_t* hi
  * reduction): theta, m, v updated in place.  Uses lr/betas/eps/step of `hyper`. */
 int invpref_adam_dense(float* theta, float* m, float* v, const float* grad, int64_t n, const invpref_hyper* hyper,
                        void* stream);
+
+/* Lazy mode (invpref_adam.user_last_step != NULL): bring every user row up to step hyper->step (the last
+ * completed train step), in place. */
+int invpref_flush_users(const invpref_desc* desc, invpref_params* params, invpref_adam* adam,
+                        const invpref_hyper* hyper, void* stream);
 
 /* The deferred part of invpref_train_step (INVPREF_DEFER_USER_SWEEP): dense Adam (zero gradient) on every
  * user row that has no segment in `plan` (built for a batch of B interactions), reading params_in and writing

@@ -24,7 +24,7 @@ EXPORTS = (
     "invpref_backward", "invpref_train_step", "invpref_cluster", "invpref_stat_envs",
     "invpref_env_hist", "invpref_launch_count", "invpref_profile_enable", "invpref_profile_steps",
     "invpref_profile_read", "invpref_adam_dense", "invpref_gather_rows", "invpref_scatter_add_rows",
-    "invpref_user_sweep",
+    "invpref_user_sweep", "invpref_flush_users",
 )
 # execution order; on the fused path "forward" is empty and chunks_users / rows_users are the fused user pass
 PHASES = ("plan", "forward", "chunks_users", "rows_users", "chunks_items", "rows_items", "sweep_items",
@@ -42,7 +42,8 @@ class Params(C.Structure):
 
 
 class Adam(C.Structure):
-    _fields_ = [("m", Params), ("v", Params)]
+    _fields_ = [("m", Params), ("v", Params), ("user_last_step", C.c_void_p), ("sched", C.c_void_p),
+                ("sched_cap", C.c_int64)]
 
 
 class Batch(C.Structure):
@@ -92,6 +93,7 @@ def load() -> C.CDLL:
     lib.invpref_stat_envs.argtypes = [vp, i64, C.c_int32, vp, vp, vp, vp]
     lib.invpref_env_hist.argtypes = [vp, i64, C.c_int32, vp, vp]
     lib.invpref_adam_dense.argtypes = [vp, vp, vp, vp, i64, C.POINTER(Hyper), vp]
+    lib.invpref_flush_users.argtypes = [C.POINTER(Desc), C.POINTER(Params), C.POINTER(Adam), C.POINTER(Hyper), vp]
     lib.invpref_user_sweep.argtypes = [C.POINTER(Desc), C.POINTER(Params), C.POINTER(Params), C.POINTER(Adam),
                                        C.POINTER(Hyper), vp, i64, vp]
     lib.invpref_gather_rows.argtypes = [vp, vp, i64, C.c_int32, vp, vp]

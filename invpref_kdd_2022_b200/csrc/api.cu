@@ -80,7 +80,8 @@ int build_plan_impl(const invpref_desc* d, const int64_t* users, const int64_t* 
     carve_plan(d, B, plan, &pu, &pi);
     int rc = build_plan_side(users, items, d->n_items, pu, tmp, tmp_bytes, st);
     if (rc != INVPREF_OK) return rc;
-    return build_plan_side(items, users, d->n_users, pi, tmp, tmp_bytes, st);
+    if ((rc = build_plan_side(items, users, d->n_users, pi, tmp, tmp_bytes, st)) != INVPREF_OK) return rc;
+    return fill_partner_segments(pu, pi, st);
 }
 
 }  // namespace
@@ -224,7 +225,14 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     const bool exp_u = hyper->flags & INVPREF_EXPORT_USER_GRADS, exp_i = hyper->flags & INVPREF_EXPORT_ITEM_GRADS;
     const bool exp_s = hyper->flags & INVPREF_EXPORT_SMALL_GRADS;
     if ((exp_u || exp_i || exp_s) && !grads_out) return INVPREF_ERR_BAD_ARG;
-    if ((!exp_u && (pin->Uinv == pout->Uinv || pin->Uenv == pout->Uenv)) ||
+    const bool lazy = adam->user_last_step != nullptr;
+    if (lazy) {
+        // lazy user rows: fused pass only, in place, Adam (not export), schedule table with room for this step
+        if (exp_u || !adam->sched || hyper->step >= adam->sched_cap || !use_fused_user_pass(g) ||
+            pin->Uinv != pout->Uinv || pin->Uenv != pout->Uenv || (hyper->flags & INVPREF_DEFER_USER_SWEEP))
+            return INVPREF_ERR_BAD_ARG;
+    }
+    if ((!exp_u && !lazy && (pin->Uinv == pout->Uinv || pin->Uenv == pout->Uenv)) ||
         (!exp_i && (pin->Iinv == pout->Iinv || pin->Ienv == pout->Ienv)))
         return INVPREF_ERR_BAD_ARG;   // tables that Adam updates in this call are double-buffered
     if (hyper->step < 1 || hyper->global_batch < 0) return INVPREF_ERR_BAD_ARG;
@@ -267,6 +275,13 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     si.grad_inv = wr_i ? grads_out->Iinv : nullptr; si.grad_env = wr_i ? grads_out->Ienv : nullptr;
     si.plan = pi; si.chunk_part = w.chunk_part_i;
     si.reg2 = su.reg2; si.reg1 = su.reg1; si.adam = as;
+    su.last_step = nullptr; su.sched = nullptr; su.step = (int)hyper->step; su.stash = nullptr;
+    si.last_step = nullptr; si.sched = nullptr; si.step = (int)hyper->step; si.stash = nullptr;
+    if (lazy) {
+        su.last_step = adam->user_last_step; su.sched = (const float2*)adam->sched; su.stash = w.stash;
+        si.stash = w.stash;     // the item pass reads the user rows of this step from the stash
+        if ((rc = launch_sched_write((float2*)adam->sched, (int)hyper->step, as, st)) != INVPREF_OK) return rc;
+    }
 
     const int P = fwd_partial_floats(g);
     int n_partials;
@@ -315,7 +330,8 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     pm.mark();
     if (!exp_i && (rc = launch_sweep(g, si, st)) != INVPREF_OK) return rc;
     pm.mark();
-    if (!exp_u && !(hyper->flags & INVPREF_DEFER_USER_SWEEP) && (rc = launch_sweep(g, su, st)) != INVPREF_OK) return rc;
+    if (!exp_u && !lazy && !(hyper->flags & INVPREF_DEFER_USER_SWEEP) && (rc = launch_sweep(g, su, st)) != INVPREF_OK)
+        return rc;
     pm.mark();
 
     // losses, E / W / b gradients and their Adam update (or export)
@@ -335,6 +351,27 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     pm.mark();
     pm.done();
     return rc;
+}
+
+int invpref_flush_users(const invpref_desc* desc, invpref_params* params, invpref_adam* adam,
+                        const invpref_hyper* hyper, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, params)) != INVPREF_OK) return rc;
+    if (!adam || !hyper || !adam->user_last_step || !adam->sched || hyper->step < 0 || hyper->step >= adam->sched_cap)
+        return INVPREF_ERR_BAD_ARG;
+    if (hyper->step == 0) return INVPREF_OK;
+    BwdSideArgs su = {};
+    su.own_inv_in = params->Uinv; su.own_env_in = params->Uenv;
+    su.own_inv_out = params->Uinv; su.own_env_out = params->Uenv;
+    su.m_inv = adam->m.Uinv; su.m_env = adam->m.Uenv; su.v_inv = adam->v.Uinv; su.v_env = adam->v.Uenv;
+    su.plan.rows = desc->n_users; su.D = g.D; su.K = g.K; su.GS = g.GS;
+    invpref_hyper h1 = *hyper;
+    if (h1.step < 1) h1.step = 1;
+    su.adam = make_adam(&h1);
+    su.last_step = adam->user_last_step; su.sched = (const float2*)adam->sched; su.step = (int)hyper->step;
+    return launch_flush(g, su, (cudaStream_t)stream);
 }
 
 int invpref_user_sweep(const invpref_desc* desc, const invpref_params* pin, invpref_params* pout, invpref_adam* adam,

@@ -28,7 +28,13 @@ __device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const flo
                                                  float* acc_inv, float* acc_env) {
     const int D = a.D, K = a.K, GS = a.GS;
     const int32_t* __restrict__ perm = a.plan.perm;
-    const int32_t* __restrict__ partner = a.plan.partner;
+    // lazy mode: the partner (user) rows of this step were stashed, caught up, by the user pass, indexed by
+    // the user's segment: row 2*seg = invariant, 2*seg+1 = env-aware
+    const bool stashed = a.stash != nullptr;
+    const int32_t* __restrict__ partner = stashed ? a.plan.pseg : a.plan.partner;
+    const float* __restrict__ pinv = stashed ? a.stash : a.partner_inv;
+    const float* __restrict__ penv = stashed ? a.stash + D : a.partner_env;
+    const int pmul = stashed ? 2 : 1;
     // software pipeline: the partner rows / g-pack of interaction k+PF are requested into L2 now; their
     // indices were loaded one iteration earlier, so the (in-order) warp never waits for them
     constexpr int PF = 4;
@@ -36,8 +42,8 @@ __device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const flo
     if (beg + PF < end) { pid_q = partner[beg + PF]; n_q = perm[beg + PF]; }
     for (int k = beg; k < end; ++k) {
         if (k + PF < end) {
-            prefetch_row(a.partner_inv, pid_q, D, lane);
-            prefetch_row(a.partner_env, pid_q, D, lane);
+            prefetch_row(pinv, (int64_t)pid_q * pmul, D, lane);
+            prefetch_row(penv, (int64_t)pid_q * pmul, D, lane);
             if (lane == 8) prefetch_l2(a.gpack + (int64_t)n_q * GS);
         }
         if (k + 1 + PF < end) { pid_q = partner[k + 1 + PF]; n_q = perm[k + 1 + PF]; }
@@ -55,8 +61,8 @@ __device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const flo
             g[8] = g[9] = g[10] = g[11] = 0.f;
         }
         Row<VEC, NV> pc, pe;
-        load_row<VEC, NV>(pc, a.partner_inv, pid, D, lane);
-        load_row<VEC, NV>(pe, a.partner_env, pid, D, lane);
+        load_row<VEC, NV>(pc, pinv, (int64_t)pid * pmul, D, lane);
+        load_row<VEC, NV>(pe, penv, (int64_t)pid * pmul, D, lane);
         const float g_z1 = g[0], g_z2 = g[1];
         const int e = __float_as_int(g[2]);
 #pragma unroll
@@ -218,6 +224,47 @@ __global__ void __launch_bounds__(BLOCK) sweep_kernel(BwdSideArgs a) {
             store_row<VEC, NV>(z, a.grad_env, row, D, lane);
         }
     }
+}
+
+// Lazy mode: bring every row of this side that is behind up to step a.step (dense zero-gradient Adam steps
+// replayed in registers with each step's own bias corrections), in place.  Run before anything outside the
+// train step reads the table (EM re-assignment, evaluation, state_dict) -- or never, in dense mode.
+template <int VEC, int NV>
+__global__ void __launch_bounds__(BLOCK) flush_kernel(BwdSideArgs a) {
+    const int D = a.D;
+    const int lane = threadIdx.x & (GROUP - 1);
+    const int64_t rows = a.plan.rows;
+    const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
+    for (int64_t row = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4); row < rows; row += ngroups) {
+        const int last = a.last_step[row];
+        if (last >= a.step) continue;
+        Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
+        load_row<VEC, NV, true>(th_i, a.own_inv_in, row, D, lane);
+        load_row<VEC, NV, true>(th_e, a.own_env_in, row, D, lane);
+        load_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+        load_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+        load_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+        load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
+        for (int j = last + 1; j <= a.step; ++j) {
+            const float2 sc = a.sched[j];
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) {
+                adam_zero_step(th_i.x[x], m_i.x[x], v_i.x[x], a.adam, sc.x, sc.y);
+                adam_zero_step(th_e.x[x], m_e.x[x], v_e.x[x], a.adam, sc.x, sc.y);
+            }
+        }
+        store_row<VEC, NV, true>(th_i, a.own_inv_out, row, D, lane);
+        store_row<VEC, NV, true>(th_e, a.own_env_out, row, D, lane);
+        store_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+        store_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+        store_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+        store_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
+        if (lane == 0) a.last_step[row] = a.step;
+    }
+}
+
+__global__ void sched_write_kernel(float2* sched, int step, float step_size, float inv_bc2_sqrt) {
+    sched[step] = make_float2(step_size, inv_bc2_sqrt);
 }
 
 constexpr int TAIL_THREADS = 256;
@@ -383,6 +430,21 @@ int launch_sweep(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream) {
 #define CALL(V, N) sweep_kernel<V, N><<<grid, BLOCK, 0, stream>>>(a)
     INVPREF_DISPATCH_VN(g, CALL);
 #undef CALL
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_flush(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream) {
+    int grid = grid_groups(a.plan.rows, 148 * 16);
+#define CALL(V, N) flush_kernel<V, N><<<grid, BLOCK, 0, stream>>>(a)
+    INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_sched_write(float2* sched, int step, const AdamScalars& s, cudaStream_t stream) {
+    sched_write_kernel<<<1, 1, 0, stream>>>(sched, step, s.step_size, s.inv_bc2_sqrt);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

@@ -101,6 +101,8 @@ struct PlanSide {
     int32_t* counters;    // [0] n_seg, [1] n_chunks, [2] error flag ; 16 ints
     int32_t* perm;        // [B]   sorted position -> original index in the batch
     int32_t* partner;     // [B]   id of the OTHER table's row, in sorted order
+    int32_t* seg_of;      // [B]   segment index on THIS side of interaction n (original order)
+    int32_t* pseg;        // [B]   segment index on the OTHER side of the partner row, in sorted order
     int32_t* seg_row;     // [S]   unique ids ascending                     (S <= min(B, rows))
     int32_t* seg_off;     // [S+1] offsets into perm
     int32_t* seg_chunk;   // [S+1] exclusive scan of per-segment chunk counts (0 for short segments)
@@ -122,7 +124,7 @@ inline size_t plan_side_bytes(int64_t B, int64_t rows) {
     int64_t S = plan_max_seg(B, rows);
     size_t n = 0;
     n += align_up(16 * 4);
-    n += align_up((size_t)B * 4) * 2;
+    n += align_up((size_t)B * 4) * 4;
     n += align_up((size_t)S * 4);
     n += align_up((size_t)(S + 1) * 4) * 2;
     n += align_up((size_t)plan_max_chunks(B) * 16);
@@ -141,6 +143,8 @@ inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
     p.counters = (int32_t*)c;   c += align_up(16 * 4);
     p.perm = (int32_t*)c;       c += align_up((size_t)B * 4);
     p.partner = (int32_t*)c;    c += align_up((size_t)B * 4);
+    p.seg_of = (int32_t*)c;     c += align_up((size_t)B * 4);
+    p.pseg = (int32_t*)c;       c += align_up((size_t)B * 4);
     p.seg_row = (int32_t*)c;    c += align_up((size_t)S * 4);
     p.seg_off = (int32_t*)c;    c += align_up((size_t)(S + 1) * 4);
     p.seg_chunk = (int32_t*)c;  c += align_up((size_t)(S + 1) * 4);
@@ -153,6 +157,7 @@ inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
 constexpr int FWD_MAX_BLOCKS = 148 * 4 + 74;   // upper bound on CTAs that write a partial-sum vector
 
 struct Workspace {
+    float* stash;        // [min(B, n_users) * 2 * D]  lazy mode: caught-up user rows of the batch
     float* gpack;        // [B * GS]
     float* partials;     // [FWD_MAX_BLOCKS * P]   per-CTA partial sums of the forward kernel
     float* chunk_part_u; // [max_chunks * 2 * D]
@@ -172,6 +177,8 @@ inline size_t workspace_bytes_impl(const invpref_desc* d, const Geometry& g, int
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align_up(bytes); return base ? base + o : (char*)nullptr; };
     int64_t Bp = B > 0 ? B : 1;
+    int64_t Su = Bp < d->n_users ? Bp : d->n_users;
+    char* sh = take((size_t)Su * 2 * g.D * 4);
     char* gp = take((size_t)Bp * g.GS * 4);
     char* pa = take((size_t)FWD_MAX_BLOCKS * fwd_partial_floats(g) * 4);
     char* cu = take((size_t)plan_max_chunks(Bp) * 2 * g.D * 4);
@@ -182,6 +189,7 @@ inline size_t workspace_bytes_impl(const invpref_desc* d, const Geometry& g, int
     size_t sb = sort_tmp_bytes_for(Bp, mr);
     char* st = take(sb);
     if (w) {
+        w->stash = (float*)sh;
         w->gpack = (float*)gp; w->partials = (float*)pa; w->chunk_part_u = (float*)cu; w->chunk_part_i = (float*)ci;
         w->plan = pl; w->sort_tmp = st; w->sort_tmp_bytes = sb; w->plan_bytes = pb;
     }
@@ -329,6 +337,16 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
     v = v * s.b2 + (s.one_minus_b2 * g) * g;
     const float denom = fmaf(sqrt_approx(v), s.inv_bc2_sqrt, s.eps);
     p = p - s.step_size * __fdividef(m, denom);
+}
+
+// One dense Adam step with ZERO gradient (what torch.optim.Adam does to a row that is not in the batch),
+// with the bias-correction scalars of that step: used to replay skipped steps of lazily updated rows.
+__device__ __forceinline__ void adam_zero_step(float& p, float& m, float& v, const AdamScalars& s, float step_size,
+                                               float inv_bc2_sqrt) {
+    m = m + (0.f - m) * s.one_minus_b1;
+    v = v * s.b2 + (s.one_minus_b2 * 0.f) * 0.f;
+    const float denom = fmaf(sqrt_approx(v), inv_bc2_sqrt, s.eps);
+    p = p - step_size * __fdividef(m, denom);
 }
 
 #endif  // __CUDACC__

@@ -53,11 +53,19 @@ struct BwdSideArgs {
     int D, K, GS;
     float reg2, reg1;                         // 2*c_L2/(B*D*2), c_L1/(B*D*2)
     AdamScalars adam;
+    // lazy user-row Adam (null = dense): see invpref_adam in the header
+    int32_t* last_step;                       // [rows of this side] step each row is updated to
+    const float2* sched;                      // [step] (lr/bc1, 1/sqrt(bc2))
+    int step;                                 // Adam step of this call
+    float* stash;                             // user pass: OUT [n_seg, 2, D] caught-up rows before this step;
+                                              // item pass: partner rows are read from here via plan.pseg
 };
 
 int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);
 int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream_t stream);
 int launch_sweep(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);
+int launch_flush(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);     // lazy rows -> step a.step
+int launch_sched_write(float2* sched, int step, const AdamScalars& s, cudaStream_t stream);
 
 // ---- upass.cu: fused forward + user-side backward + Adam ---------------------------------------------
 constexpr int UPASS_CHUNK_CTAS = 74;   // CTAs of the (usually idle) long-user-segment kernel
@@ -126,6 +134,7 @@ int launch_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, in
 // ---- plan.cu ---------------------------------------------------------------------------------
 int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, PlanSide p, char* tmp,
                     size_t tmp_bytes, cudaStream_t stream);
+int fill_partner_segments(PlanSide a, PlanSide b, cudaStream_t stream);
 int build_segments_i64(const int64_t* ids, int64_t B, int64_t rows, int64_t* perm, int64_t* seg_row, int64_t* seg_off,
                        int64_t* n_seg, char* ws, size_t ws_bytes, cudaStream_t stream);
 

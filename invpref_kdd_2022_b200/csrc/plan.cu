@@ -41,6 +41,7 @@ __global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const 
     int32_t key = sorted[k];
     int32_t s = segid[k] - 1;
     bool head = (k == 0) || (sorted[k - 1] != key);
+    p.seg_of[perm[k]] = s;
     if (head) {
         p.seg_row[s] = key;
         p.seg_off[s] = (int32_t)k;
@@ -56,6 +57,12 @@ __global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const 
         if (o >= other_rows) o = other_rows - 1;
         p.partner[k] = (int32_t)o;
     }
+}
+
+// pseg[k] = segment index, on the other side, of the partner row of sorted position k
+__global__ void fill_pseg_kernel(PlanSide p, const int32_t* __restrict__ other_seg_of) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < p.B) p.pseg[k] = other_seg_of[p.perm[k]];
 }
 
 __global__ void chunk_counts_kernel(PlanSide p, int chunk) {
@@ -171,6 +178,14 @@ int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_
     cub::DeviceScan::ExclusiveSum(t.cub_tmp, cb, p.seg_chunk, p.seg_chunk, (int)(p.max_seg + 1), stream);
     write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p, chunk_for(B));
     count_launch(5 + 6);   // 5 of ours + CUB's (radix passes, 2 scans; approximate)
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int fill_partner_segments(PlanSide a, PlanSide b, cudaStream_t stream) {
+    if (a.B == 0) return INVPREF_OK;
+    fill_pseg_kernel<<<grid_for(a.B), 256, 0, stream>>>(a, b.seg_of);
+    fill_pseg_kernel<<<grid_for(b.B), 256, 0, stream>>>(b, a.seg_of);
+    count_launch(2);
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 

@@ -171,6 +171,21 @@ __device__ __forceinline__ void finish_range(const UserPassArgs& a, const float*
     }
 }
 
+// Lazy mode: replay the zero-gradient Adam steps last+1 .. upto (inclusive) of one user row in registers.
+template <int VEC, int NV>
+__device__ __forceinline__ void replay_steps(const BwdSideArgs& sd, int last, int upto, Row<VEC, NV>& th_i,
+                                             Row<VEC, NV>& th_e, Row<VEC, NV>& m_i, Row<VEC, NV>& m_e,
+                                             Row<VEC, NV>& v_i, Row<VEC, NV>& v_e) {
+    for (int j = last + 1; j <= upto; ++j) {
+        const float2 sc = sd.sched[j];
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) {
+            adam_zero_step(th_i.x[x], m_i.x[x], v_i.x[x], sd.adam, sc.x, sc.y);
+            adam_zero_step(th_e.x[x], m_e.x[x], v_e.x[x], sd.adam, sc.x, sc.y);
+        }
+    }
+}
+
 struct Smem {
     float *sE, *sW, *sRed, *sDE, *sDW, *sB;
 };
@@ -233,7 +248,7 @@ __device__ __forceinline__ void write_partials(const UserPassArgs& a, const Smem
     for (int t = threadIdx.x; t < 2 * KD; t += BLOCK) out[P_DW + t] = s.sRed[t];
 }
 
-template <int VEC, int NV, int KT>
+template <int VEC, int NV, int KT, bool LAZY>
 __global__ void __launch_bounds__(BLOCK, 2) upass_chunks_kernel(UserPassArgs a, int cta_offset) {
     extern __shared__ float smem[];
     const int D = a.side.D, KD = a.side.K * a.side.D;
@@ -253,6 +268,14 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_chunks_kernel(UserPassArgs a, 
         Row<VEC, NV> ra, rue, gi, ge;
         load_row<VEC, NV>(ra, a.side.own_inv_in, row, D, lane);
         load_row<VEC, NV>(rue, a.side.own_env_in, row, D, lane);
+        if (LAZY) {   // bring the row up to step-1 in registers (the rows kernel does the same and stores it)
+            Row<VEC, NV> m_i, m_e, v_i, v_e;
+            load_row<VEC, NV>(m_i, a.side.m_inv, row, D, lane);
+            load_row<VEC, NV>(m_e, a.side.m_env, row, D, lane);
+            load_row<VEC, NV>(v_i, a.side.v_inv, row, D, lane);
+            load_row<VEC, NV>(v_e, a.side.v_env, row, D, lane);
+            replay_steps<VEC, NV>(a.side, a.side.last_step[row], a.side.step - 1, ra, rue, m_i, m_e, v_i, v_e);
+        }
         float acc0[NV * VEC], Q[KT][NV * VEC];
 #pragma unroll
         for (int x = 0; x < NV * VEC; ++x) {
@@ -268,7 +291,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_chunks_kernel(UserPassArgs a, 
     write_partials(a, s, KD, st, cta_offset + blockIdx.x);
 }
 
-template <int VEC, int NV, int KT, int EPI>
+template <int VEC, int NV, int KT, int EPI, bool LAZY>
 __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
     extern __shared__ float smem[];
     const int D = a.side.D, KD = a.side.K * a.side.D;
@@ -318,8 +341,20 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
         const int beg = seg_off[sgm], end = seg_off[sgm + 1];
         const int c0 = a.side.plan.seg_chunk[sgm], c1 = a.side.plan.seg_chunk[sgm + 1];
         Row<VEC, NV> ra, rue, gi, ge;
+        Row<VEC, NV> m_i, m_e, v_i, v_e;
         load_row<VEC, NV>(ra, a.side.own_inv_in, row, D, lane);
         load_row<VEC, NV>(rue, a.side.own_env_in, row, D, lane);
+        if (LAZY) {
+            // the row may be several steps behind: replay the skipped zero-gradient Adam steps in registers,
+            // then stash the caught-up row (what every reader of this step must see) for the item pass
+            load_row<VEC, NV, true>(m_i, a.side.m_inv, row, D, lane);
+            load_row<VEC, NV, true>(m_e, a.side.m_env, row, D, lane);
+            load_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
+            load_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
+            replay_steps<VEC, NV>(a.side, a.side.last_step[row], a.side.step - 1, ra, rue, m_i, m_e, v_i, v_e);
+            store_row<VEC, NV>(ra, a.side.stash, (int64_t)sgm * 2, D, lane);
+            store_row<VEC, NV>(rue, a.side.stash, (int64_t)sgm * 2 + 1, D, lane);
+        }
         if (c1 > c0) {   // long segment: its forward + reduction ran in upass_chunks_kernel
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
@@ -358,11 +393,12 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
             store_row<VEC, NV>(ge, a.side.grad_env, row, D, lane);
         }
         if (EPI == EPI_ADAM) {
-            Row<VEC, NV> m_i, m_e, v_i, v_e;
-            load_row<VEC, NV, true>(m_i, a.side.m_inv, row, D, lane);
-            load_row<VEC, NV, true>(m_e, a.side.m_env, row, D, lane);
-            load_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
-            load_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
+            if (!LAZY) {
+                load_row<VEC, NV, true>(m_i, a.side.m_inv, row, D, lane);
+                load_row<VEC, NV, true>(m_e, a.side.m_env, row, D, lane);
+                load_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
+                load_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
+            }
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) {
                 adam_update(ra.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.side.adam);
@@ -374,6 +410,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
             store_row<VEC, NV, true>(m_e, a.side.m_env, row, D, lane);
             store_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
             store_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
+            if (LAZY && lane == 0) a.side.last_step[row] = a.side.step;
         }
         row1 = row2; beg1 = beg2; pid1 = pid2; n1 = n2;
         row2 = row3; beg2 = beg3;
@@ -397,37 +434,42 @@ int upass_rows_grid(int64_t max_seg) {
 
 int launch_upass_chunks(const Geometry& g, const UserPassArgs& a, int cta_offset, cudaStream_t stream) {
     const size_t smem = upass_smem(g);
+    const bool lazy = a.side.last_step != nullptr;
+#define LAUNCH(KERNEL)                                                                                           \
+    do {                                                                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        KERNEL<<<UPASS_CHUNK_CTAS, BLOCK, smem, stream>>>(a, cta_offset);                                        \
+    } while (0)
 #define CALL(V, N, KT_)                                                                                          \
     do {                                                                                                         \
-        if (smem > 48 * 1024)                                                                                    \
-            cudaFuncSetAttribute(upass_chunks_kernel<V, N, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
-                                 (int)smem);                                                                     \
-        upass_chunks_kernel<V, N, KT_><<<UPASS_CHUNK_CTAS, BLOCK, smem, stream>>>(a, cta_offset);                \
+        if (lazy) LAUNCH((upass_chunks_kernel<V, N, KT_, true>));                                                \
+        else LAUNCH((upass_chunks_kernel<V, N, KT_, false>));                                                    \
     } while (0)
     INVPREF_DISPATCH_GEOM(g, CALL);
 #undef CALL
+#undef LAUNCH
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 
 int launch_upass_rows(const Geometry& g, const UserPassArgs& a, int epi, int grid, cudaStream_t stream) {
     const size_t smem = upass_smem(g);
+    const bool lazy = a.side.last_step != nullptr;
+    if (lazy && epi != EPI_ADAM) return INVPREF_ERR_BAD_ARG;
+#define LAUNCH(KERNEL)                                                                                           \
+    do {                                                                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        KERNEL<<<grid, BLOCK, smem, stream>>>(a);                                                                \
+    } while (0)
 #define CALL(V, N, KT_)                                                                                          \
     do {                                                                                                         \
-        if (epi == EPI_ADAM) {                                                                                   \
-            if (smem > 48 * 1024)                                                                                \
-                cudaFuncSetAttribute(upass_rows_kernel<V, N, KT_, EPI_ADAM>,                                     \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
-            upass_rows_kernel<V, N, KT_, EPI_ADAM><<<grid, BLOCK, smem, stream>>>(a);                            \
-        } else {                                                                                                 \
-            if (smem > 48 * 1024)                                                                                \
-                cudaFuncSetAttribute(upass_rows_kernel<V, N, KT_, EPI_EXPORT>,                                   \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
-            upass_rows_kernel<V, N, KT_, EPI_EXPORT><<<grid, BLOCK, smem, stream>>>(a);                          \
-        }                                                                                                        \
+        if (lazy) LAUNCH((upass_rows_kernel<V, N, KT_, EPI_ADAM, true>));                                        \
+        else if (epi == EPI_ADAM) LAUNCH((upass_rows_kernel<V, N, KT_, EPI_ADAM, false>));                       \
+        else LAUNCH((upass_rows_kernel<V, N, KT_, EPI_EXPORT, false>));                                          \
     } while (0)
     INVPREF_DISPATCH_GEOM(g, CALL);
 #undef CALL
+#undef LAUNCH
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

@@ -26,7 +26,11 @@ class HotPath:
     """
 
     def __init__(self, params: Dict[str, torch.Tensor], implicit: bool, reg_only_embed: bool, reg_env_embed: bool,
-                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, on_swap=None):
+                 lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, on_swap=None, lazy: bool = False):
+        """``lazy``: lazy dense Adam for the user tables (``invpref_adam.user_last_step`` in the header): rows
+        that are not in a batch are not touched in memory; the skipped zero-gradient steps are replayed,
+        bit-identically, when the row is next used or by ``flush()``.  Every method of this class that reads
+        the user tables flushes first; code that reads ``params`` directly must call ``flush()``."""
         self.lib = _lib.load()
         for k in PARAM_FIELDS:
             t = params[k]
@@ -49,6 +53,53 @@ class HotPath:
         self._ws = None
         self._ws_batch = -1
         self.loss_buf = torch.zeros(6, dtype=torch.float32, device=self.device)
+        self.lazy = bool(lazy)
+        self.last_step = None        # int32 [n_users]
+        self.sched = None            # fp32 [cap, 2]
+        self._dirty = False          # some user rows are behind self.step
+
+    def _adam_struct(self):
+        a = _lib.Adam(_lib.make_params(self.m), _lib.make_params(self.v), None, None, 0)
+        if self.lazy:
+            if self.last_step is None:
+                raise RuntimeError("internal: lazy state not initialised")
+            if self.step + 2 >= self.sched.shape[0]:
+                grown = torch.zeros((self.sched.shape[0] * 4, 2), dtype=torch.float32, device=self.device)
+                grown[:self.sched.shape[0]] = self.sched
+                self.sched = grown
+            a.user_last_step = _lib.ptr(self.last_step, torch.int32)
+            a.sched = _lib.ptr(self.sched, torch.float32)
+            a.sched_cap = self.sched.shape[0]
+        return a
+
+    def _ensure_lazy(self):
+        """Called with self.step == number of COMPLETED steps: every row is current at that step."""
+        if self.lazy and self.last_step is None:
+            self.last_step = torch.full((self.n_users,), int(self.step), dtype=torch.int32, device=self.device)
+            cap = 1 << 14
+            while cap <= self.step + 2:
+                cap *= 4
+            self.sched = torch.zeros((cap, 2), dtype=torch.float32, device=self.device)
+
+    def set_lazy(self, lazy: bool):
+        if bool(lazy) == self.lazy:
+            return
+        self.flush()
+        self.lazy = bool(lazy)
+        self.last_step = None
+        self.sched = None
+
+    def flush(self):
+        """Lazy mode: bring every user row up to the last completed step (no-op otherwise)."""
+        if not (self.lazy and self._dirty):
+            return
+        hyper = _lib.Hyper(0, 0, 0, 0, 0, 0, self.lr, self.betas[0], self.betas[1], self.eps, int(self.step), 0, 0,
+                           0, 0, 0)
+        p = _lib.make_params(self.params)
+        adam = self._adam_struct()
+        _lib.check(self.lib.invpref_flush_users(C.byref(self.desc), C.byref(p), C.byref(adam), C.byref(hyper),
+                                                _lib.stream_ptr()), "flush_users")
+        self._dirty = False
 
     # ---- buffers -------------------------------------------------------------------------
     def _ensure_state(self, shadow_for=TABLES):
@@ -97,19 +148,22 @@ class HotPath:
         ``flags`` / ``global_batch``: data-parallel use, see ``invpref_hyper`` in the header; tables of an
         exported group are neither updated nor swapped."""
         self._ensure_state([k for k in TABLES
-                            if not (flags & (_lib.EXPORT_USER_GRADS if k[0] == "U" else _lib.EXPORT_ITEM_GRADS))])
+                            if not (flags & (_lib.EXPORT_USER_GRADS if k[0] == "U" else _lib.EXPORT_ITEM_GRADS))
+                            and not (self.lazy and k[0] == "U")])
         B = users.numel()
         ws = self.workspace(B)
+        self._ensure_lazy()
         self.step += 1
         hyper = _lib.Hyper(float(c_inv), float(c_ea), float(c_env), float(c_L2), float(c_L1), float(alpha), self.lr,
                            self.betas[0], self.betas[1], self.eps, self.step, int(bool(use_class_rw)),
                            int(bool(use_rec_rw)), int(global_batch), int(flags), 0)
         p_in = _lib.make_params(self.params)
         out = dict(self.params)
-        swap = [k for k in TABLES if not (flags & (_lib.EXPORT_USER_GRADS if k[0] == "U" else _lib.EXPORT_ITEM_GRADS))]
+        swap = [k for k in TABLES if not (flags & (_lib.EXPORT_USER_GRADS if k[0] == "U" else _lib.EXPORT_ITEM_GRADS))
+                and not (self.lazy and k[0] == "U")]           # lazy user tables are updated in place
         out.update({k: self.shadow[k] for k in swap})
         p_out = _lib.make_params(out)
-        adam = _lib.Adam(_lib.make_params(self.m), _lib.make_params(self.v))
+        adam = self._adam_struct()
         batch = _lib.Batch(_lib.ptr(users, torch.int64), _lib.ptr(items, torch.int64), _lib.ptr(envs, torch.int64),
                            _lib.ptr(scores, torch.float32), _lib.ptr(weights, torch.float32), B)
         if loss_out is None:
@@ -122,6 +176,7 @@ class HotPath:
         if rc != 0:
             self.step -= 1
         _lib.check(rc, "train_step")
+        self._dirty = self.lazy
         # the updated rows are in the other buffer set: swap
         for k in swap:
             self.params[k], self.shadow[k] = self.shadow[k], self.params[k]
@@ -137,13 +192,14 @@ class HotPath:
         old = dict(self.params)
         old.update({k: self.shadow[k] for k in ("Uinv", "Uenv")})
         p_in, p_out = _lib.make_params(old), _lib.make_params(self.params)
-        adam = _lib.Adam(_lib.make_params(self.m), _lib.make_params(self.v))
+        adam = self._adam_struct()
         _lib.check(self.lib.invpref_user_sweep(C.byref(self.desc), C.byref(p_in), C.byref(p_out), C.byref(adam),
                                                C.byref(hyper), _lib.ptr(plan), int(B), _lib.stream_ptr()),
                    "user_sweep")
 
     # ---- forward / backward (autograd-compatible path) ----------------------------------------
     def forward(self, users, items, envs, want_logp=True):
+        self.flush()
         B = users.numel()
         s_inv = torch.empty(B, dtype=torch.float32, device=self.device)
         s_env = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -156,6 +212,7 @@ class HotPath:
         return s_inv, s_env, logp
 
     def predict(self, users, items):
+        self.flush()
         B = users.numel()
         out = torch.empty(B, dtype=torch.float32, device=self.device)
         p = _lib.make_params(self.params)
@@ -166,6 +223,7 @@ class HotPath:
 
     def backward(self, users, items, envs, alpha, g_s_inv, g_s_env, g_logp, grads: Dict[str, torch.Tensor], plan=None):
         """Accumulates the autograd gradients of ``forward`` into ``grads`` (dense, deterministic)."""
+        self.flush()
         B = users.numel()
         ws = self.workspace(B)
         p = _lib.make_params(self.params)
@@ -179,6 +237,7 @@ class HotPath:
     # ---- EM re-assignment -------------------------------------------------------------------------
     def cluster(self, users, items, scores, perm_idx, eps_table, old_envs):
         """train.py:846-879 over a whole slice.  Returns (new_envs int64[B], hist int64[K], diff int64[1])."""
+        self.flush()
         B = users.numel()
         new_envs = torch.empty(B, dtype=torch.int64, device=self.device)
         hist = torch.zeros(self.n_envs, dtype=torch.int64, device=self.device)

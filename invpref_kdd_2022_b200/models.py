@@ -125,8 +125,9 @@ class _InvPref(nn.Module):
             if p.data.data_ptr() != t.data_ptr():
                 p.data = t
 
-    def hot_path(self, lr: float = 1e-3) -> HotPath:
-        """The engine bound to this model's parameter storages (created on first use)."""
+    def hot_path(self, lr: float = 1e-3, lazy: bool = None) -> HotPath:
+        """The engine bound to this model's parameter storages (created on first use).  ``lazy``: see
+        ``HotPath``; every read through this module (forward, predict, state_dict) flushes first."""
         cur = {k: p.data for k, p in self.named_hot_params().items()}
         if self._hot is None or any(self._hot.params[k].data_ptr() != cur[k].data_ptr() for k in cur):
             if not cur["Uinv"].is_cuda:
@@ -134,10 +135,17 @@ class _InvPref(nn.Module):
                                    "there is no CPU fallback")
             keep = self._hot
             self._hot = HotPath(cur, self.implicit, self.reg_only_embed, self.reg_env_embed, lr=lr,
-                                on_swap=self._repoint)
+                                on_swap=self._repoint, lazy=bool(lazy))
             if keep is not None and keep.m is not None and keep.params["Uinv"].shape == cur["Uinv"].shape:
                 self._hot.m, self._hot.v, self._hot.step = keep.m, keep.v, keep.step
+        elif lazy is not None:
+            self._hot.set_lazy(lazy)
         return self._hot
+
+    def state_dict(self, *a, **kw):
+        if self._hot is not None:
+            self._hot.flush()           # lazily updated user rows are brought up to date first
+        return super().state_dict(*a, **kw)
 
     def _apply(self, fn, *a, **kw):
         self._hot = None            # .to(device) / .float() re-allocate the storages
@@ -152,6 +160,8 @@ class _InvPref(nn.Module):
         return s_inv.reshape(-1), s_env.reshape(-1), logp.reshape(-1, self.env_num)
 
     def _pair_reg(self, inv: nn.Embedding, env: nn.Embedding, ids, norm: int):
+        if self._hot is not None:
+            self._hot.flush()
         a, b = inv(ids), env(ids)
         den = float(len(ids)) * float(self.factor_num) * 2
         if norm == 2:
@@ -231,5 +241,7 @@ class InvPrefImplicit(_InvPref, GeneralDebiasImplicitRecommender):
         """models.py:393-407: sigmoid(<u_inv, i_inv>) for every item -> [b, item_num].  The reference
         materialises a [b*I, D] repeat; this is the same contraction as one GEMM (evaluation is off the
         hot path)."""
+        if self._hot is not None:
+            self._hot.flush()
         u = self.embed_user_invariant(users_id)
         return torch.sigmoid(u @ self.embed_item_invariant.weight.t())

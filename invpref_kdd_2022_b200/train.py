@@ -32,7 +32,7 @@ class _InvPrefTrainManager:
             invariant_coe: float, env_aware_coe: float, env_coe: float, L2_coe: float, L1_coe: float,
             alpha: float = None, use_class_re_weight: bool = False, test_begin_epoch: int = 0,
             begin_cluster_epoch: int = None, stop_cluster_epoch: int = None, cluster_use_random_sort: bool = True,
-            use_recommend_re_weight: bool = True, cache_plans: bool = True
+            use_recommend_re_weight: bool = True, cache_plans: bool = True, lazy_adam: bool = True
     ):
         self.model = model
         self.evaluator = evaluator
@@ -67,7 +67,9 @@ class _InvPrefTrainManager:
         self.const_env_tensor_list = [torch.full((n,), k, dtype=torch.int64, device=device)
                                       for k in range(self.envs_num)]                           # train.py:758-761
         # fused engine bound to the model's parameter storages; holds the Adam state (train.py:718)
-        self.engine = model.hot_path(lr=lr)
+        # lazy_adam: user rows outside a batch are updated lazily (bit-identical to dense torch.optim.Adam, see
+        # HotPath); train_a_epoch flushes at the end of the epoch, train_a_batch after every call
+        self.engine = model.hot_path(lr=lr, lazy=lazy_adam)
         self.engine.lr = float(lr)
         self.optimizer = self.engine           # exposes .m / .v / .step (exp_avg, exp_avg_sq, step)
         self.cache_plans = cache_plans
@@ -105,6 +107,7 @@ class _InvPrefTrainManager:
         """train.py:771-844.  One fused step; returns the six losses as python floats (one sync)."""
         out = self._step(batch_users_tensor, batch_items_tensor, batch_scores_tensor, batch_envs_tensor,
                          batch_sample_weights, alpha)
+        self.engine.flush()
         vals = out.cpu().tolist()
         return dict(zip(LOSS_KEYS, vals))
 
@@ -123,6 +126,7 @@ class _InvPrefTrainManager:
                 self.alpha = 2. / (1. + np.exp(-10. * p)) - 1.
             self._step(u, i, y, e, w, self.alpha, loss_out=self._loss_rows[batch_index], plan_key=batch_index)
         self.epoch_cnt += 1
+        self.engine.flush()
         rows = self._loss_rows.cpu().tolist()
         return merge_dict([dict(zip(LOSS_KEYS, r)) for r in rows], _mean_merge_dict_func)
 

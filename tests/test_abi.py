@@ -34,7 +34,7 @@ def test_struct_layouts():
     from invpref_kdd_2022_b200 import _lib
     assert C.sizeof(_lib.Desc) == 40
     assert C.sizeof(_lib.Params) == 56
-    assert C.sizeof(_lib.Adam) == 112
+    assert C.sizeof(_lib.Adam) == 136
     assert C.sizeof(_lib.Batch) == 48
     assert C.sizeof(_lib.Hyper) == 112
 
