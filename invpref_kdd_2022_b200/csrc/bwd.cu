@@ -22,7 +22,7 @@ namespace {
 // Sum over sorted positions [beg, end) of this side's per-interaction gradient contributions:
 //   acc_inv += (g_z1 + sum_k (-alpha g_logits[k]) W[k, d]) * partner_inv[d]      (g_p (.) partner)
 //   acc_env += g_z2 * partner_env[d] * E[e, d]
-template <int VEC, int NV>
+template <int VEC, int NV, bool STASH>
 __device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const float* __restrict__ sE,
                                                  const float* __restrict__ sW, int beg, int end, int lane,
                                                  float* acc_inv, float* acc_env) {
@@ -30,11 +30,10 @@ __device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const flo
     const int32_t* __restrict__ perm = a.plan.perm;
     // lazy mode: the partner (user) rows of this step were stashed, caught up, by the user pass, indexed by
     // the user's segment: row 2*seg = invariant, 2*seg+1 = env-aware
-    const bool stashed = a.stash != nullptr;
-    const int32_t* __restrict__ partner = stashed ? a.plan.pseg : a.plan.partner;
-    const float* __restrict__ pinv = stashed ? a.stash : a.partner_inv;
-    const float* __restrict__ penv = stashed ? a.stash + D : a.partner_env;
-    const int pmul = stashed ? 2 : 1;
+    const int32_t* __restrict__ partner = STASH ? a.plan.pseg : a.plan.partner;
+    const float* __restrict__ pinv = STASH ? a.stash : a.partner_inv;
+    const float* __restrict__ penv = STASH ? a.stash + D : a.partner_env;
+    constexpr int pmul = STASH ? 2 : 1;
     // software pipeline: the partner rows / g-pack of interaction k+PF are requested into L2 now; their
     // indices were loaded one iteration earlier, so the (in-order) warp never waits for them
     constexpr int PF = 4;
@@ -42,8 +41,8 @@ __device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const flo
     if (beg + PF < end) { pid_q = partner[beg + PF]; n_q = perm[beg + PF]; }
     for (int k = beg; k < end; ++k) {
         if (k + PF < end) {
-            prefetch_row(pinv, (int64_t)pid_q * pmul, D, lane);
-            prefetch_row(penv, (int64_t)pid_q * pmul, D, lane);
+            prefetch_row(pinv, pid_q * pmul, D, lane);
+            prefetch_row(penv, pid_q * pmul, D, lane);
             if (lane == 8) prefetch_l2(a.gpack + (int64_t)n_q * GS);
         }
         if (k + 1 + PF < end) { pid_q = partner[k + 1 + PF]; n_q = perm[k + 1 + PF]; }
@@ -61,8 +60,8 @@ __device__ __forceinline__ void accumulate_range(const BwdSideArgs& a, const flo
             g[8] = g[9] = g[10] = g[11] = 0.f;
         }
         Row<VEC, NV> pc, pe;
-        load_row<VEC, NV>(pc, pinv, (int64_t)pid * pmul, D, lane);
-        load_row<VEC, NV>(pe, penv, (int64_t)pid * pmul, D, lane);
+        load_row<VEC, NV>(pc, pinv, pid * pmul, D, lane);
+        load_row<VEC, NV>(pe, penv, pid * pmul, D, lane);
         const float g_z1 = g[0], g_z2 = g[1];
         const int e = __float_as_int(g[2]);
 #pragma unroll
@@ -92,7 +91,7 @@ __device__ __forceinline__ void stage_EW(const BwdSideArgs& a, float* sE, float*
     __syncthreads();
 }
 
-template <int VEC, int NV>
+template <int VEC, int NV, bool STASH>
 __global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_kernel(BwdSideArgs a) {
     extern __shared__ float smem[];
     float* sE = smem;
@@ -106,13 +105,13 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_kernel(BwdSideArgs a) {
         Row<VEC, NV> ai, ae;
 #pragma unroll
         for (int x = 0; x < NV * VEC; ++x) { ai.x[x] = 0.f; ae.x[x] = 0.f; }
-        accumulate_range<VEC, NV>(a, sE, sW, desc.y, desc.z, lane, ai.x, ae.x);
+        accumulate_range<VEC, NV, STASH>(a, sE, sW, desc.y, desc.z, lane, ai.x, ae.x);
         store_row<VEC, NV>(ai, a.chunk_part, (int64_t)c * 2, a.D, lane);
         store_row<VEC, NV>(ae, a.chunk_part, (int64_t)c * 2 + 1, a.D, lane);
     }
 }
 
-template <int VEC, int NV, int EPI>
+template <int VEC, int NV, int EPI, bool STASH>
 __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
     extern __shared__ float smem[];
     float* sE = smem;
@@ -149,7 +148,7 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
                 for (int x = 0; x < NV * VEC; ++x) { gi.x[x] += pi.x[x]; ge.x[x] += pe.x[x]; }
             }
         } else {
-            accumulate_range<VEC, NV>(a, sE, sW, beg, end, lane, gi.x, ge.x);
+            accumulate_range<VEC, NV, STASH>(a, sE, sW, beg, end, lane, gi.x, ge.x);
         }
         if (EPI == EPI_ADAM || EPI == EPI_EXPORT) {
             // L1/L2 term of the gathered rows (models.py:469-497): every occurrence counts
@@ -398,9 +397,15 @@ inline int grid_groups(int64_t n, int max_blocks) {
 int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream) {
     size_t smem = (size_t)2 * g.K * g.D * sizeof(float);
     int grid = grid_groups(a.plan.max_chunks, 148 * 8);
-#define CALL(V, N) bwd_chunks_kernel<V, N><<<grid, BLOCK, smem, stream>>>(a)
-    INVPREF_DISPATCH_VN(g, CALL);
+    if (a.stash != nullptr) {
+#define CALL(V, N) bwd_chunks_kernel<V, N, true><<<grid, BLOCK, smem, stream>>>(a)
+        INVPREF_DISPATCH_VN(g, CALL);
 #undef CALL
+    } else {
+#define CALL(V, N) bwd_chunks_kernel<V, N, false><<<grid, BLOCK, smem, stream>>>(a)
+        INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    }
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
@@ -408,16 +413,25 @@ int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stre
 int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream_t stream) {
     size_t smem = (size_t)2 * g.K * g.D * sizeof(float);
     int grid = grid_groups(a.plan.max_seg, 148 * 8);
-    if (epi == EPI_ADAM) {
-#define CALL(V, N) bwd_rows_kernel<V, N, EPI_ADAM><<<grid, BLOCK, smem, stream>>>(a)
+    const bool stash = a.stash != nullptr;
+    if (epi == EPI_ADAM && stash) {
+#define CALL(V, N) bwd_rows_kernel<V, N, EPI_ADAM, true><<<grid, BLOCK, smem, stream>>>(a)
+        INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    } else if (epi == EPI_ADAM) {
+#define CALL(V, N) bwd_rows_kernel<V, N, EPI_ADAM, false><<<grid, BLOCK, smem, stream>>>(a)
+        INVPREF_DISPATCH_VN(g, CALL);
+#undef CALL
+    } else if (epi == EPI_EXPORT && stash) {
+#define CALL(V, N) bwd_rows_kernel<V, N, EPI_EXPORT, true><<<grid, BLOCK, smem, stream>>>(a)
         INVPREF_DISPATCH_VN(g, CALL);
 #undef CALL
     } else if (epi == EPI_EXPORT) {
-#define CALL(V, N) bwd_rows_kernel<V, N, EPI_EXPORT><<<grid, BLOCK, smem, stream>>>(a)
+#define CALL(V, N) bwd_rows_kernel<V, N, EPI_EXPORT, false><<<grid, BLOCK, smem, stream>>>(a)
         INVPREF_DISPATCH_VN(g, CALL);
 #undef CALL
     } else {
-#define CALL(V, N) bwd_rows_kernel<V, N, EPI_ACCUM><<<grid, BLOCK, smem, stream>>>(a)
+#define CALL(V, N) bwd_rows_kernel<V, N, EPI_ACCUM, false><<<grid, BLOCK, smem, stream>>>(a)
         INVPREF_DISPATCH_VN(g, CALL);
 #undef CALL
     }
