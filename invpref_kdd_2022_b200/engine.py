@@ -81,6 +81,16 @@ class HotPath:
                 cap *= 4
             self.sched = torch.zeros((cap, 2), dtype=torch.float32, device=self.device)
 
+    def write_sched(self):
+        """Lazy mode, a step without a local batch (multi-GPU: nothing routed here): only record the step's
+        Adam scalars so that later replays find them."""
+        import math
+        t = int(self.step)
+        self._adam_struct()
+        bc1, bc2 = 1.0 - self.betas[0] ** t, 1.0 - self.betas[1] ** t
+        self.sched[t, 0] = self.lr / bc1
+        self.sched[t, 1] = 1.0 / math.sqrt(bc2)
+
     def set_lazy(self, lazy: bool):
         if bool(lazy) == self.lazy:
             return

@@ -224,7 +224,7 @@ class ShardedTrainer:
     """User and item tables mod-sharded by row over `world` ranks (row r of rank g holds id r*world + g)."""
 
     def __init__(self, n_users, n_items, n_envs, dim, implicit, reg_only_embed, reg_env_embed, lr, rank, world,
-                 device, cache_rows, init=None, seed=17373331):
+                 device, cache_rows, init=None, seed=17373331, lazy=True):
         self.rank, self.world, self.dev = rank, world, device
         self.U, self.I, self.K, self.D = n_users, n_items, n_envs, dim
         self.U_loc = (n_users - rank + world - 1) // world
@@ -261,7 +261,10 @@ class ShardedTrainer:
         self.gcache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
         params = {"Uinv": uinv, "Uenv": uenv, "Iinv": self.cache[0], "Ienv": self.cache[1]}
         params.update(views(self.small))
-        self.hot = HotPath(params, implicit, reg_only_embed, reg_env_embed, lr=lr)
+        # lazy: the local user shard uses lazy dense Adam (bit-identical, see HotPath), so there is no dense
+        # sweep at all; otherwise the sweep runs on a side stream under the NVLink exchange
+        self.lazy = bool(lazy)
+        self.hot = HotPath(params, implicit, reg_only_embed, reg_env_embed, lr=lr, lazy=self.lazy)
         self.hot.m = {"Uinv": torch.zeros_like(uinv), "Uenv": torch.zeros_like(uenv), "Iinv": self.cache[0],
                       "Ienv": self.cache[1]}
         self.hot.v = {"Uinv": torch.zeros_like(uinv), "Uenv": torch.zeros_like(uenv), "Iinv": self.cache[0],
@@ -338,20 +341,32 @@ class ShardedTrainer:
         self._fetched = None
         self._mark("fetch")
         self.gsmall.zero_()
-        self.hot._ensure_state(("Uinv", "Uenv"))
         main = torch.cuda.current_stream()
-        if sb.users.numel() > 0:
-            self.hot.train_step(sb.users, r.slots, sb.scores, envs, weights, plan=sb.plan, loss_out=self.loss,
-                                grads_out=self.grads, global_batch=sb.global_batch,
-                                flags=self.flags | _lib.DEFER_USER_SWEEP, **kw)
-        else:       # no interaction routed here: every local user row still moves by momentum
-            self.hot.step += 1
-            for k in ("Uinv", "Uenv"):
-                self.hot.params[k], self.hot.shadow[k] = self.hot.shadow[k], self.hot.params[k]
-        self._mark("local_step")
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            self.hot.user_sweep(sb.plan, sb.users.numel())
+        if self.lazy:
+            if sb.users.numel() > 0:
+                self.hot.train_step(sb.users, r.slots, sb.scores, envs, weights, plan=sb.plan, loss_out=self.loss,
+                                    grads_out=self.grads, global_batch=sb.global_batch, flags=self.flags, **kw)
+            else:   # no interaction routed here: the local rows just fall one more step behind
+                self.hot._ensure_state(())
+                self.hot._ensure_lazy()
+                self.hot.step += 1
+                self.hot._dirty = True
+                self.hot.write_sched()
+            self._mark("local_step")
+        else:
+            self.hot._ensure_state(("Uinv", "Uenv"))
+            if sb.users.numel() > 0:
+                self.hot.train_step(sb.users, r.slots, sb.scores, envs, weights, plan=sb.plan, loss_out=self.loss,
+                                    grads_out=self.grads, global_batch=sb.global_batch,
+                                    flags=self.flags | _lib.DEFER_USER_SWEEP, **kw)
+            else:       # no interaction routed here: every local user row still moves by momentum
+                self.hot.step += 1
+                for k in ("Uinv", "Uenv"):
+                    self.hot.params[k], self.hot.shadow[k] = self.hot.shadow[k], self.hot.params[k]
+            self._mark("local_step")
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.hot.user_sweep(sb.plan, sb.users.numel())
         # partial item gradients back to the owners (reverse routing)
         ns = int(r.send_rows.numel())
         recv = self._buf("recv_g", ns)
@@ -383,9 +398,14 @@ class ShardedTrainer:
         return self.loss
 
     # ---- EM re-assignment -------------------------------------------------------------------------------
+    def flush(self):
+        """Lazy mode: bring the local user shard up to the last completed step."""
+        self.hot.flush()
+
     def cluster_gen(self, sb: ShardedBatch, perm_idx, eps_table, old_envs):
         """train.py:846-879 on this rank's share of a batch; hist / diff are all-reduced by the caller."""
         yield from self.fetch_gen(sb)
+        self._fetched = None
         if sb.users.numel() == 0:
             z = torch.zeros(0, dtype=torch.int64, device=self.dev)
             return z, torch.zeros(self.K, dtype=torch.int64, device=self.dev), torch.zeros(1, dtype=torch.int64,
@@ -394,5 +414,6 @@ class ShardedTrainer:
 
     # ---- inspection (tests) -----------------------------------------------------------------------------
     def local_tables(self):
+        self.hot.flush()
         return {"Uinv": self.hot.params["Uinv"], "Uenv": self.hot.params["Uenv"], "Iinv": self.Iinv,
                 "Ienv": self.Ienv, "E": self.hot.params["E"], "W": self.hot.params["W"], "b": self.hot.params["b"]}

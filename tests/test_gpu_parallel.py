@@ -44,9 +44,10 @@ def single_gpu(p, batches, implicit, roe, ree, lr):
     return hp, np.asarray(losses)
 
 
+@pytest.mark.parametrize("lazy", [True, False])
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("implicit,roe,ree", [(False, True, False), (True, False, True)])
-def test_sharded_matches_single_gpu(world, implicit, roe, ree):
+def test_sharded_matches_single_gpu(world, implicit, roe, ree, lazy):
     from invpref_kdd_2022_b200.parallel import ShardedTrainer, SimDriver
     dev = torch.device("cuda:0")
     U, I, K, D, B = 1000, 203, 4, 64, 20000
@@ -55,7 +56,7 @@ def test_sharded_matches_single_gpu(world, implicit, roe, ree):
     batches = [(u[a:b], i[a:b], y[a:b], e[a:b], w[a:b]) for a, b in bounds]
     ref, ref_losses = single_gpu(p, batches, implicit, roe, ree, 1e-2)
     init = {k: torch.tensor(v, device=dev) for k, v in p.items()}
-    ranks = [ShardedTrainer(U, I, K, D, implicit, roe, ree, 1e-2, r, world, dev, cache_rows=I, init=init)
+    ranks = [ShardedTrainer(U, I, K, D, implicit, roe, ree, 1e-2, r, world, dev, cache_rows=I, init=init, lazy=lazy)
              for r in range(world)]
     sim = SimDriver(world)
     t = lambda a: torch.tensor(a, device=dev)
