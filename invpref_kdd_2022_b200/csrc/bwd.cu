@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
             const float cnt = (float)(end - beg);
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) {
-                gi.x[x] += cnt * (a.reg2 * th_i.x[x] + a.reg1 * signf_(th_i.x[x]));
-                ge.x[x] += cnt * (a.reg2 * th_e.x[x] + a.reg1 * signf_(th_e.x[x]));
+                gi.x[x] += cnt * (a.reg2 * th_i.x[x] + mul_sign(a.reg1, th_i.x[x]));
+                ge.x[x] += cnt * (a.reg2 * th_e.x[x] + mul_sign(a.reg1, th_e.x[x]));
             }
             if (a.grad_inv != nullptr) {
                 store_row<VEC, NV>(gi, a.grad_inv, row, D, lane);
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(BLOCK) sweep_kernel(BwdSideArgs a) {
         load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
 #pragma unroll
         for (int x = 0; x < NV * VEC; ++x) {
-            adam_update(th_i.x[x], m_i.x[x], v_i.x[x], 0.f, a.adam);
-            adam_update(th_e.x[x], m_e.x[x], v_e.x[x], 0.f, a.adam);
+            adam_zero_step(th_i.x[x], m_i.x[x], v_i.x[x], a.adam, a.adam.step_size, a.adam.inv_bc2_sqrt);
+            adam_zero_step(th_e.x[x], m_e.x[x], v_e.x[x], a.adam, a.adam.step_size, a.adam.inv_bc2_sqrt);
         }
         store_row<VEC, NV, true>(th_i, a.own_inv_out, row, D, lane);
         store_row<VEC, NV, true>(th_e, a.own_env_out, row, D, lane);

@@ -315,6 +315,9 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 __device__ __forceinline__ float signf_(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
+// c * sign(x) with sign(0) = 0 (torch's norm(1) backward), three instructions
+__device__ __forceinline__ float mul_sign(float c, float x) { return (x == 0.f) ? 0.f : copysignf(c, x); }
+
 // Scalars of one dense torch.optim.Adam update (torch/optim/adam.py, single-tensor path):
 // computed on the host in double from the integer step, used as fp32 in the tensor ops.
 struct AdamScalars {
@@ -341,12 +344,15 @@ __device__ __forceinline__ void adam_update(float& p, float& m, float& v, float 
 
 // One dense Adam step with ZERO gradient (what torch.optim.Adam does to a row that is not in the batch),
 // with the bias-correction scalars of that step: used to replay skipped steps of lazily updated rows.
+// It is adam_update with g = 0 written out (m + (0 - m) c = fma(-m, c, m); v b2 + 0 = v b2 since v >= 0), and
+// it is what the dense sweep itself calls, so lazy replay and dense sweep are the same arithmetic by
+// construction.
 __device__ __forceinline__ void adam_zero_step(float& p, float& m, float& v, const AdamScalars& s, float step_size,
                                                float inv_bc2_sqrt) {
-    m = m + (0.f - m) * s.one_minus_b1;
-    v = v * s.b2 + (s.one_minus_b2 * 0.f) * 0.f;
+    m = fmaf(-m, s.one_minus_b1, m);
+    v = v * s.b2;
     const float denom = fmaf(sqrt_approx(v), inv_bc2_sqrt, s.eps);
-    p = p - step_size * __fdividef(m, denom);
+    p = fmaf(-step_size, __fdividef(m, denom), p);
 }
 
 #endif  // __CUDACC__

@@ -383,8 +383,8 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
         for (int x = 0; x < NV * VEC; ++x) {
             sq += ra.x[x] * ra.x[x] + rue.x[x] * rue.x[x];
             ab += fabsf(ra.x[x]) + fabsf(rue.x[x]);
-            gi.x[x] += cnt * (a.side.reg2 * ra.x[x] + a.side.reg1 * signf_(ra.x[x]));
-            ge.x[x] += cnt * (a.side.reg2 * rue.x[x] + a.side.reg1 * signf_(rue.x[x]));
+            gi.x[x] += cnt * (a.side.reg2 * ra.x[x] + mul_sign(a.side.reg1, ra.x[x]));
+            ge.x[x] += cnt * (a.side.reg2 * rue.x[x] + mul_sign(a.side.reg1, rue.x[x]));
         }
         st.sq += cnt * sq;
         st.ab += cnt * ab;
