@@ -86,6 +86,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the captured kernels (one `ncu --set full` capture
+    of this same command, summarised by tools/ncu_summary.py into profiles/ncu_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -264,20 +274,31 @@ def run_ours_single(args, w):
                                  "achieved": a, "frac": a / peak}
     # (2) headline: lazy dense Adam (bit-identical results, tests/test_gpu_lazy.py), flush inside the region
     ms, ph_ms, launches, clk = timed(not args.dense_adam)
-    roof = {"bound": "hbm", "kernel": "fused train step (all kernels)", "achieved": sbytes / (ms * 1e-3) / 1e9,
-            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None,
-            "note": "achieved = ALGORITHMIC bytes of SURVEY.md 8d (B(32D+56+8K) + 24P, i.e. dense Adam traffic for "
-                    "all P parameters) / time.  The lazy-Adam path moves fewer bytes than that convention (rows "
-                    "outside the batch are not touched), so frac can exceed what the DRAM counters show."}
-    roof["frac"] = roof["achieved"] / peak
+    # whole step against SURVEY.md 8d's convention (B(32D+56+8K) + 24P: dense Adam traffic for all P parameters)
+    step_roof = {"bytes_per_step": sbytes, "achieved": sbytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                 "note": "ALGORITHMIC bytes of SURVEY.md 8d / step time.  The lazy-Adam path moves fewer bytes than "
+                         "that convention (rows outside the batch are not touched), so this frac is not a DRAM-counter "
+                         "fraction; dense_adam.roofline_frac is the same figure with every row swept every step."}
+    step_roof["frac"] = step_roof["achieved"] / peak
+    # roofline object = the DOMINANT KERNEL: fused user pass.  Its algorithmic bytes per launch: per unique user
+    # theta/m/v of two tables read + written (48 D) + the stashed row pair (8 D) + last_step (4); per interaction
+    # two item rows (8 D), ids + perm + scalars (36), g-pack write (32).  Timed live by CUDA events recorded
+    # between the library's kernels on its stream (invpref_profile_*), averaged over the timed steps.
+    roof = {"bound": "hbm", "kernel": "upass_rows (fused forward + losses + user-side segment reduce + Adam)",
+            "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None}
     if ph_ms.get("rows_users"):
-        # dominant kernel: fused user pass.  Per unique user: theta/m/v of two tables read + written (48 D), the
-        # stashed row (8 D); per interaction: two item rows (8 D), ids + perm + scalars (36), g-pack write (32)
         ub = n_seg_u * (48 * D + 8 * D + 4) + B * (8 * D + 36 + 32)
         a = ub / (ph_ms["rows_users"] * 1e-3) / 1e9
-        roof["dominant_kernel"] = {"kernel": "upass_rows_kernel (fused forward + user-side reduce + Adam)",
-                                   "bytes_per_launch": ub, "ms_per_launch": ph_ms["rows_users"], "achieved": a,
-                                   "frac": a / peak}
+        roof.update({"achieved": a, "frac": a / peak, "bytes_per_launch": ub, "ms_per_launch": ph_ms["rows_users"],
+                     "share_of_step": ph_ms["rows_users"] / ms})
+    else:
+        roof.update({"kernel": "fused train step (all kernels)", "achieved": step_roof["achieved"],
+                     "frac": step_roof["frac"]})
+    tr = ncu_traffic().get("upass_rows")
+    if tr:
+        roof["traffic"] = tr["bytes"]
+        roof["traffic_source"] = tr.get("source")
+    roof["step"] = step_roof
     roof["phase_ms"] = ph_ms
 
     # ---- env re-assignment: all nb batches as one slice, as train.py:912-936 does ----
@@ -301,8 +322,13 @@ def run_ours_single(args, w):
     cms = ev0.elapsed_time(ev1) / reps
     cb = cluster_bytes_per_sample(D) * Nc
     cluster = {"value": Nc / (cms * 1e-3), "unit": "samples/s", "samples": Nc, "ms": cms,
-               "roofline": {"bound": "hbm", "achieved": cb / (cms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                            "frac": cb / (cms * 1e-3) / 1e9 / peak}}
+               "roofline": {"bound": "hbm", "kernel": "cluster_kernel (+ stat_envs)", "achieved": cb / (cms * 1e-3) / 1e9,
+                            "peak": peak, "unit": "GB/s", "frac": cb / (cms * 1e-3) / 1e9 / peak,
+                            "bytes_per_launch": cb, "traffic": None}}
+    ctr = ncu_traffic().get("cluster")
+    if ctr:   # captured on ctr["samples"] samples: scale to this launch
+        cluster["roofline"]["traffic"] = ctr["bytes"] * Nc / ctr.get("samples", Nc)
+        cluster["roofline"]["traffic_source"] = ctr.get("source")
 
     # ---- e2e: host (pinned) batch -> H2D -> plan build + step -> D2H of the six losses, every step ----
     hb = [tuple(t.cpu().pin_memory() for t in b) for b in dbatches[:min(nb, 4)]]

@@ -183,8 +183,9 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* params_in
 
 /* ---- EM environment re-assignment ---------------------------------------------------------------
  * train.py:846-879 for a whole slice at once: each sample's loss under all K environments,
- * optional tie-break perturbation eps_table[perm_idx[n]] (train.py:868-873; perm_idx is the
- * host-drawn np.random.randint, NULL = cluster_use_random_sort off), first-min argmin.
+ * optional tie-break perturbation eps_table[perm_idx[n]] (train.py:868-873; eps_table is the fp32
+ * [K!, K] table of train.py:763-769, perm_idx in [0, K!) the host-drawn np.random.randint, NULL =
+ * cluster_use_random_sort off), first-min argmin.
  * new_envs: int64 [B].  hist (int64[K], nullable) and diff (int64, nullable; counts
  * new != old_envs, train.py:933-934) are ACCUMULATED into; zero them first. */
 int invpref_cluster(const invpref_desc* desc, const invpref_params* params, const int64_t* users,

@@ -294,7 +294,7 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
         up.c_inv = (float)hyper->c_inv; up.c_ea = (float)hyper->c_ea; up.c_env = (float)hyper->c_env;
         up.neg_alpha = (float)(-hyper->alpha); up.invB = 1.f / (float)Bg;
         up.gpack_out = w.gpack; up.partials = w.partials; up.P = P;
-        const int ugrid = upass_rows_grid(pu.max_seg);
+        const int ugrid = upass_rows_grid(g, pu.max_seg);
         n_partials = ugrid + UPASS_CHUNK_CTAS;
         pm.mark();   // "forward" phase is empty on this path
         if ((rc = launch_upass_chunks(g, up, ugrid, st)) != INVPREF_OK) return rc;

@@ -5,6 +5,13 @@
 // ONCE, the K env-aware scores are formed in registers against E (staged in shared memory), and the
 // first-min argmin, the env histogram (train.py:949) and the diff count (train.py:933-934) come out of
 // the same pass.
+//
+// ncu on the first version (round 1): 57 % of the warp samples waited on the long scoreboard (ids -> rows ->
+// perm_idx -> eps chains), 64-bit shared atomics were CAS loops.  Now the four rows of a sample are copied
+// global -> shared with cp.async two iterations before they are read (no register held, each lane copies the
+// slice it reads back: wait_group only, no barrier), ids are loaded one iteration before that, the per-sample
+// scalars at the top of the iteration, this lane's slice of E lives in registers, the K! x K tie-break table
+// in shared memory (K <= 6), and histogram / diff counts are per-group registers until the end.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -12,27 +19,76 @@ namespace invpref {
 
 namespace {
 
+// Ring depth of the staged row gathers: a sample's four rows are requested (cp.async, no registers held)
+// CL_STAGES-1 iterations before they are read.
+template <int VEC, int NV> struct ClStages { static constexpr int value = (VEC * NV <= 8) ? 3 : 2; };
+
 template <int VEC, int NV, int KT>
-__global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a) {
-    extern __shared__ float smem[];
-    const int D = a.D, K = a.K;
-    float* sE = smem;   // [K*D]
+__global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_rows_smem) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int RV = VEC * NV, ST = ClStages<VEC, NV>::value;
+    constexpr bool E_REG = KT * RV <= 32;      // this lane's slice of E lives in registers for the whole kernel
+    const int D = a.D, K = a.K, KD = K * D;
+    float* sE = smem;                                        // [K*D]
+    float* sEps = smem + ((KD + 3) & ~3);                    // [eps_rows_smem * K]
+    float* ring = sEps + ((eps_rows_smem * K + 3) & ~3);     // [ST][4 rows][NV][BLOCK][VEC]
     __shared__ unsigned long long sHist[INVPREF_MAX_ENVS + 1];   // [K] histogram, [8] diff
     const int tid = threadIdx.x, lane = tid & (GROUP - 1);
     const unsigned gmask = group_mask();
-    for (int t = tid; t < K * D; t += BLOCK) sE[t] = a.E[t];
+    for (int t = tid; t < KD; t += BLOCK) sE[t] = a.E[t];
+    for (int t = tid; t < eps_rows_smem * K; t += BLOCK) sEps[t] = a.eps_table[t];
     if (tid <= INVPREF_MAX_ENVS) sHist[tid] = 0ull;
     __syncthreads();
+    float eR[E_REG ? KT : 1][RV];
+    if (E_REG) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    const int d = dim_of<VEC>(lane, j) + v;
+                    eR[E_REG ? k : 0][j * VEC + v] = (k < K && d < D) ? sE[k * D + d] : 0.f;
+                }
+    }
 
-    const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
-    for (int64_t n = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (tid >> 4); n < a.B; n += ngroups) {
-        const int64_t u = a.users[n], it = a.items[n];
-        Row<VEC, NV> ra, rc, rue, rie;
-        load_row<VEC, NV, true>(ra, a.Uinv, u, D, lane);
-        load_row<VEC, NV>(rc, a.Iinv, it, D, lane);
-        load_row<VEC, NV, true>(rue, a.Uenv, u, D, lane);
-        load_row<VEC, NV>(rie, a.Ienv, it, D, lane);
+    const int64_t stride = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
+    const int64_t n0 = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (tid >> 4);
+    auto issue = [&](int slot, int64_t u, int64_t it) {
+        stage_row_async<VEC, NV>(ring, slot * 4 + 0, a.Uinv, u, D, lane);
+        stage_row_async<VEC, NV>(ring, slot * 4 + 1, a.Iinv, it, D, lane);
+        stage_row_async<VEC, NV>(ring, slot * 4 + 2, a.Uenv, u, D, lane);
+        stage_row_async<VEC, NV>(ring, slot * 4 + 3, a.Ienv, it, D, lane);
+    };
+    // prologue: rows of the first ST-1 samples in flight, ids of the next one in registers
+#pragma unroll
+    for (int q = 0; q < ST - 1; ++q) {
+        const int64_t n = n0 + q * stride;
+        if (n < a.B) issue(q, a.users[n], a.items[n]);
+        cp_async_commit();
+    }
+    int64_t uq = 0, iq = 0;
+    if (n0 + (ST - 1) * stride < a.B) { uq = a.users[n0 + (ST - 1) * stride]; iq = a.items[n0 + (ST - 1) * stride]; }
+    unsigned cnt[KT], ndiff = 0;   // lane 0: this group's histogram and diff count
+#pragma unroll
+    for (int k = 0; k < KT; ++k) cnt[k] = 0u;
+
+    int slot = 0;
+    for (int64_t n = n0; n < a.B; n += stride) {
+        // request the rows of sample n + (ST-1) stride (ids loaded one iteration ago), then its successor's ids
+        int wslot = slot + ST - 1; if (wslot >= ST) wslot -= ST;
+        if (n + (ST - 1) * stride < a.B) issue(wslot, uq, iq);
+        cp_async_commit();
+        if (n + ST * stride < a.B) { uq = a.users[n + ST * stride]; iq = a.items[n + ST * stride]; }
         const float y = a.scores[n];
+        const int64_t pidx = (a.perm_idx != nullptr) ? a.perm_idx[n] : 0;
+        const int64_t old = (a.diff != nullptr) ? a.old_envs[n] : 0;
+        cp_async_wait<ST - 1>();
+        Row<VEC, NV> ra, rc, rue, rie;
+        read_staged_row<VEC, NV>(ra, ring, slot * 4 + 0, D, lane);
+        read_staged_row<VEC, NV>(rc, ring, slot * 4 + 1, D, lane);
+        read_staged_row<VEC, NV>(rue, ring, slot * 4 + 2, D, lane);
+        read_staged_row<VEC, NV>(rie, ring, slot * 4 + 3, D, lane);
         float z1 = 0.f;
         float z2[KT];
 #pragma unroll
@@ -48,7 +104,7 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a) {
                     const float t = rue.x[x] * rie.x[x];
 #pragma unroll
                     for (int k = 0; k < KT; ++k)
-                        if (k < K) z2[k] += t * sE[k * D + d0 + v];
+                        if (k < K) z2[k] += t * (E_REG ? eR[E_REG ? k : 0][x] : sE[k * D + d0 + v]);
                 }
             }
         }
@@ -56,7 +112,8 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a) {
 #pragma unroll
         for (int k = 0; k < KT; ++k) z2[k] = group_sum(z2[k], gmask);
         if (lane == 0) {
-            const float* eps = (a.perm_idx != nullptr) ? a.eps_table + a.perm_idx[n] * K : nullptr;
+            const float* eps = nullptr;
+            if (a.perm_idx != nullptr) eps = (eps_rows_smem > 0 ? sEps : a.eps_table) + pidx * K;
             const float s_inv = a.implicit ? sigmoidf_(z1) : z1;
             float best = 0.f;
             int arg = 0;
@@ -76,9 +133,18 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a) {
                 }
             }
             a.new_envs[n] = (int64_t)arg;
-            if (a.hist != nullptr) atomicAdd(&sHist[arg], 1ull);
-            if (a.diff != nullptr && a.old_envs[n] != (int64_t)arg) atomicAdd(&sHist[INVPREF_MAX_ENVS], 1ull);
+#pragma unroll
+            for (int k = 0; k < KT; ++k) cnt[k] += (arg == k) ? 1u : 0u;
+            if (a.diff != nullptr && old != (int64_t)arg) ++ndiff;
         }
+        if (++slot == ST) slot = 0;
+    }
+    cp_async_wait<0>();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+            if (k < K && cnt[k] != 0u) atomicAdd(&sHist[k], (unsigned long long)cnt[k]);
+        if (ndiff != 0u) atomicAdd(&sHist[INVPREF_MAX_ENVS], (unsigned long long)ndiff);
     }
     __syncthreads();
     if (tid < K && a.hist != nullptr && sHist[tid] != 0ull) atomicAdd(&a.hist[tid], sHist[tid]);
@@ -127,10 +193,23 @@ __global__ void __launch_bounds__(256) stat_envs_kernel(const int64_t* __restric
 }  // namespace
 
 int launch_cluster(const Geometry& g, const ClusterArgs& a, cudaStream_t stream) {
-    size_t smem = (size_t)g.K * g.D * sizeof(float);
+    // a group handles <= 2^32 samples (its counters are 32-bit): B / (grid * 16) is far below that
+    int eps_rows = 0;
+    if (a.perm_idx != nullptr && a.eps_table != nullptr && g.K <= 6) {
+        eps_rows = 1;
+        for (int j = 2; j <= g.K; ++j) eps_rows *= j;
+    }
+    const int stages = (g.VEC * g.NV <= 8) ? 3 : 2;
+    const size_t smem = ((size_t)((g.K * g.D + 3) & ~3) + (size_t)((eps_rows * g.K + 3) & ~3) +
+                         (size_t)stages * 4 * g.NV * g.VEC * BLOCK) * sizeof(float);
     int64_t need = (a.B + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
     int grid = (int)(need < 1 ? 1 : (need < 148 * 16 ? need : 148 * 16));
-#define CALL(V, N, KT_) cluster_kernel<V, N, KT_><<<grid, BLOCK, smem, stream>>>(a)
+#define CALL(V, N, KT_)                                                                                          \
+    do {                                                                                                         \
+        if (smem > 48 * 1024)                                                                                    \
+            cudaFuncSetAttribute(cluster_kernel<V, N, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cluster_kernel<V, N, KT_><<<grid, BLOCK, smem, stream>>>(a, eps_rows);                                   \
+    } while (0)
     INVPREF_DISPATCH_GEOM(g, CALL);
 #undef CALL
     count_launch();

@@ -107,6 +107,8 @@ struct PlanSide {
     int32_t* seg_off;     // [S+1] offsets into perm
     int32_t* seg_chunk;   // [S+1] exclusive scan of per-segment chunk counts (0 for short segments)
     int32_t* chunk_desc;  // [max_chunks*4] (seg, begin, end, unused)
+    int32_t* seg_desc;    // [S*4] (row, begin, perm[begin], partner[begin]): everything a kernel needs to request
+                          //       a segment's rows and its first interaction with ONE 16-byte load
     uint32_t* touched;    // [ceil(rows/32)] bitmap of rows that have a segment
     int64_t max_seg, max_chunks, rows, B;
 };
@@ -128,6 +130,7 @@ inline size_t plan_side_bytes(int64_t B, int64_t rows) {
     n += align_up((size_t)S * 4);
     n += align_up((size_t)(S + 1) * 4) * 2;
     n += align_up((size_t)plan_max_chunks(B) * 16);
+    n += align_up((size_t)S * 16);
     n += align_up((size_t)((rows + 31) / 32) * 4);
     return n;
 }
@@ -149,6 +152,7 @@ inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
     p.seg_off = (int32_t*)c;    c += align_up((size_t)(S + 1) * 4);
     p.seg_chunk = (int32_t*)c;  c += align_up((size_t)(S + 1) * 4);
     p.chunk_desc = (int32_t*)c; c += align_up((size_t)p.max_chunks * 16);
+    p.seg_desc = (int32_t*)c;   c += align_up((size_t)S * 16);
     p.touched = (uint32_t*)c;
     return p;
 }
@@ -293,6 +297,67 @@ __device__ __forceinline__ void prefetch_row(const float* __restrict__ table, in
     const int bytes = D * 4;
     if (lane * 128 < bytes) prefetch_l2(base + lane * 128);
     if (lane == GROUP - 1 && (bytes & 127)) prefetch_l2(base + bytes - 4);   // trailing partial line
+}
+
+// ---- cp.async staging: global -> shared copies that tie up no register while in flight -----------------
+// Every lane copies ITS OWN slice of a row (the same VEC floats it later reads back), so completion only has to
+// be visible to the issuing thread: cp.async.wait_group is enough, no barrier.  A slot a lane reads is always
+// one it wrote itself.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int BYTES> __device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");   // L2 only
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
+}
+
+// Per-thread slot of a staged row slice: [slot][j][thread][VEC] floats (consecutive threads -> consecutive
+// VEC*4 bytes: conflict-free for the 128-bit shared loads).
+template <int VEC, int NV>
+__device__ __forceinline__ float* stage_slot(float* ring, int slot) {
+    return ring + ((size_t)slot * NV * BLOCK + threadIdx.x) * VEC;
+}
+
+template <int VEC, int NV>
+__device__ __forceinline__ void stage_row_async(float* ring, int slot, const float* __restrict__ table, int64_t row,
+                                                int D, int lane) {
+    const float* p = table + row * (int64_t)D;
+    float* s = stage_slot<VEC, NV>(ring, slot);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int d0 = dim_of<VEC>(lane, j);
+        if (d0 < D) cp_async<VEC * 4>(smem_addr(s + (size_t)j * BLOCK * VEC), p + d0);
+    }
+}
+
+template <int VEC, int NV>
+__device__ __forceinline__ void read_staged_row(Row<VEC, NV>& r, const float* ring, int slot, int D, int lane) {
+    const float* s = stage_slot<VEC, NV>(const_cast<float*>(ring), slot);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int d0 = dim_of<VEC>(lane, j);
+        if (d0 < D) {
+            ldv<VEC>(s + (size_t)j * BLOCK * VEC, &r.x[j * VEC]);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) r.x[j * VEC + v] = 0.f;
+        }
+    }
+}
+
+template <int VEC, int NV>
+__device__ __forceinline__ void write_staged_row(const Row<VEC, NV>& r, float* ring, int slot, int D, int lane) {
+    float* s = stage_slot<VEC, NV>(ring, slot);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int d0 = dim_of<VEC>(lane, j);
+        if (d0 < D) stv<VEC>(s + (size_t)j * BLOCK * VEC, &r.x[j * VEC]);
+    }
 }
 
 // sum over the 16 lanes of a group; every lane gets the result (xor butterfly stays inside the

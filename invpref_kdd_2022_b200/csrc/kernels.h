@@ -83,7 +83,7 @@ struct UserPassArgs {
 };
 
 bool upass_supported(const Geometry& g);
-int upass_rows_grid(int64_t max_seg);
+int upass_rows_grid(const Geometry& g, int64_t max_seg);
 int launch_upass_chunks(const Geometry& g, const UserPassArgs& a, int cta_offset, cudaStream_t stream);
 int launch_upass_rows(const Geometry& g, const UserPassArgs& a, int epi, int grid, cudaStream_t stream);
 

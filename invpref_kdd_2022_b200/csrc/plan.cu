@@ -77,14 +77,15 @@ __global__ void chunk_counts_kernel(PlanSide p, int chunk) {
     p.seg_chunk[s] = c;
 }
 
-__global__ void write_chunks_kernel(PlanSide p, int chunk) {
+__global__ void write_chunks_kernel(PlanSide p, int chunk, int has_partner) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int32_t n_seg = p.counters[0];
     if (s == 0) p.counters[1] = p.seg_chunk[n_seg];
     if (s >= n_seg) return;
     int32_t c0 = p.seg_chunk[s], c1 = p.seg_chunk[s + 1];
-    if (c1 == c0) return;
     int32_t beg = p.seg_off[s], end = p.seg_off[s + 1];
+    reinterpret_cast<int4*>(p.seg_desc)[s] = make_int4(p.seg_row[s], beg, p.perm[beg], has_partner ? p.partner[beg] : 0);
+    if (c1 == c0) return;
     for (int32_t c = c0; c < c1; ++c) {
         int32_t b = beg + (c - c0) * chunk;
         int32_t e = b + chunk < end ? b + chunk : end;
@@ -176,7 +177,8 @@ int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_
     chunk_counts_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B));
     cb = t.cub_bytes;
     cub::DeviceScan::ExclusiveSum(t.cub_tmp, cb, p.seg_chunk, p.seg_chunk, (int)(p.max_seg + 1), stream);
-    write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p, chunk_for(B));
+    write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p, chunk_for(B),
+                                                                                       other_ids != nullptr);
     count_launch(5 + 6);   // 5 of ours + CUB's (radix passes, 2 scans; approximate)
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

@@ -34,13 +34,122 @@ struct Running {
     float sq, ab;         // sum x^2 / |x| over the gathered rows (this lane's dims)
 };
 
+// One interaction, part 1: dot products against the user rows -> logits and scores (unreduced per-lane sums).
+template <int VEC, int NV, int KT>
+struct Inter {
+    float z1, z2, sq, ab;
+    float lg[KT], t[NV * VEC], ee[NV * VEC];
+};
+
+template <int VEC, int NV, int KT>
+__device__ __forceinline__ void inter_dots(const UserPassArgs& a, const float* __restrict__ sE,
+                                           const float* __restrict__ sW, const Row<VEC, NV>& ra,
+                                           const Row<VEC, NV>& rue, const Row<VEC, NV>& rc, const Row<VEC, NV>& rie,
+                                           int e, int lane, Inter<VEC, NV, KT>& q) {
+    const int D = a.side.D, K = a.side.K;
+    q.z1 = 0.f; q.z2 = 0.f; q.sq = 0.f; q.ab = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) q.lg[kk] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int d0 = dim_of<VEC>(lane, j);
+        if (d0 < D) {
+            ldv<VEC>(sE + e * D + d0, &q.ee[j * VEC]);
+            float p[VEC], wk[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int x = j * VEC + v;
+                p[v] = ra.x[x] * rc.x[x];
+                q.t[x] = rue.x[x] * rie.x[x];
+                q.z1 += p[v];
+                q.z2 += q.t[x] * q.ee[x];
+                q.sq += rc.x[x] * rc.x[x] + rie.x[x] * rie.x[x];
+                q.ab += fabsf(rc.x[x]) + fabsf(rie.x[x]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < KT; ++kk) {
+                if (kk < K) {
+                    ldv<VEC>(sW + kk * D + d0, wk);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) q.lg[kk] += wk[v] * p[v];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) { q.t[j * VEC + v] = 0.f; q.ee[j * VEC + v] = 0.f; }
+        }
+    }
+}
+
+// One interaction, part 2: group reductions, losses and their backward scalars, the user-side gradient
+// pieces, dE, the running sums, and the g-pack of interaction n for the item pass.
+template <int VEC, int NV, int KT>
+__device__ __forceinline__ void inter_grads(const UserPassArgs& a, const LossCfg& cfg, float* __restrict__ myDE,
+                                            const float* __restrict__ sB, const Row<VEC, NV>& rc,
+                                            const Row<VEC, NV>& rie, Inter<VEC, NV, KT>& q, int n, int e, float y,
+                                            float w, int lane, unsigned gmask, float (&acc0)[NV * VEC],
+                                            float (&Q)[KT][NV * VEC], float (&acc_env)[NV * VEC], Running& st) {
+    const int D = a.side.D, K = a.side.K;
+    const float z1 = group_sum(q.z1, gmask);
+    const float z2 = group_sum(q.z2, gmask);
+    float lg[KT];
+#pragma unroll
+    for (int kk = 0; kk < KT; ++kk) lg[kk] = (kk < K) ? group_sum(q.lg[kk], gmask) + sB[kk] : -INFINITY;
+
+    float g_z1, g_z2, gl[KT], lw[3];
+    loss_grads<KT>(cfg, z1, z2, lg, y, w, e, g_z1, g_z2, gl, lw);
+    st.sq += q.sq;
+    st.ab += q.ab;
+    {
+        float v1 = (lane == 0) ? lw[0] : ((lane == 1) ? lw[1] : ((lane == 2) ? lw[2] : 0.f));
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) v1 = (lane == 3 + kk) ? gl[kk] : v1;
+        st.stat1 += v1;
+        st.stat2 += (lane == e) ? 1.f : 0.f;
+    }
+    // user-side gradient pieces and dE[e] += g_z2 * ue*ie (this group's shared-memory slice)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int d0 = dim_of<VEC>(lane, j);
+        if (d0 < D) {
+            float de[VEC];
+            ldv<VEC>(myDE + e * D + d0, de);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int x = j * VEC + v;
+                acc0[x] += g_z1 * rc.x[x];
+                acc_env[x] += g_z2 * rie.x[x] * q.ee[x];
+                de[v] += g_z2 * q.t[x];
+#pragma unroll
+                for (int kk = 0; kk < KT; ++kk) Q[kk][x] += gl[kk] * rc.x[x];
+            }
+            stv<VEC>(myDE + e * D + d0, de);
+        }
+    }
+    if (lane == 0) {   // g-pack for the item pass: g_z1, g_z2, env, -alpha * g_logits
+        float* gp = a.gpack_out + (int64_t)n * a.side.GS;
+        float out[12];
+        out[0] = g_z1;
+        out[1] = g_z2;
+        out[2] = __int_as_float(e);
+#pragma unroll
+        for (int kk = 0; kk < 9; ++kk) out[3 + kk] = (kk < KT) ? a.neg_alpha * gl[kk < KT ? kk : 0] : 0.f;
+        *reinterpret_cast<float4*>(gp) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4*>(gp + 4) = make_float4(out[4], out[5], out[6], out[7]);
+        if (KT > 5 && a.side.GS > 8)
+            *reinterpret_cast<float4*>(gp + 8) = make_float4(out[8], out[9], out[10], out[11]);
+    }
+}
+
+// Interactions [beg, end) of one user segment, item rows loaded straight from global memory (chunks kernel and
+// the unstaged rows kernel).
 template <int VEC, int NV, int KT>
 __device__ __forceinline__ void fused_range(const UserPassArgs& a, const LossCfg& cfg, const float* __restrict__ sE,
                                             const float* __restrict__ sW, float* __restrict__ myDE,
                                             const float* __restrict__ sB, const Row<VEC, NV>& ra, const Row<VEC, NV>& rue,
                                             int beg, int end, int lane, unsigned gmask, float (&acc0)[NV * VEC],
                                             float (&Q)[KT][NV * VEC], float (&acc_env)[NV * VEC], Running& st) {
-    const int D = a.side.D, K = a.side.K;
+    const int D = a.side.D;
     const int32_t* __restrict__ perm = a.side.plan.perm;
     const int32_t* __restrict__ partner = a.side.plan.partner;
     for (int k = beg; k < end; ++k) {
@@ -52,87 +161,9 @@ __device__ __forceinline__ void fused_range(const UserPassArgs& a, const LossCfg
         Row<VEC, NV> rc, rie;
         load_row<VEC, NV>(rc, a.side.partner_inv, it, D, lane);
         load_row<VEC, NV>(rie, a.side.partner_env, it, D, lane);
-        float z1 = 0.f, z2 = 0.f, sq = 0.f, ab = 0.f;
-        float lg[KT], t[NV * VEC], ee[NV * VEC];
-#pragma unroll
-        for (int kk = 0; kk < KT; ++kk) lg[kk] = 0.f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int d0 = dim_of<VEC>(lane, j);
-            if (d0 < D) {
-                ldv<VEC>(sE + e * D + d0, &ee[j * VEC]);
-                float p[VEC], wk[VEC];
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const int x = j * VEC + v;
-                    p[v] = ra.x[x] * rc.x[x];
-                    t[x] = rue.x[x] * rie.x[x];
-                    z1 += p[v];
-                    z2 += t[x] * ee[x];
-                    sq += rc.x[x] * rc.x[x] + rie.x[x] * rie.x[x];
-                    ab += fabsf(rc.x[x]) + fabsf(rie.x[x]);
-                }
-#pragma unroll
-                for (int kk = 0; kk < KT; ++kk) {
-                    if (kk < K) {
-                        ldv<VEC>(sW + kk * D + d0, wk);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) lg[kk] += wk[v] * p[v];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) { t[j * VEC + v] = 0.f; ee[j * VEC + v] = 0.f; }
-            }
-        }
-        z1 = group_sum(z1, gmask);
-        z2 = group_sum(z2, gmask);
-#pragma unroll
-        for (int kk = 0; kk < KT; ++kk) lg[kk] = (kk < K) ? group_sum(lg[kk], gmask) + sB[kk] : -INFINITY;
-
-        float g_z1, g_z2, gl[KT], lw[3];
-        loss_grads<KT>(cfg, z1, z2, lg, y, w, e, g_z1, g_z2, gl, lw);
-        st.sq += sq;
-        st.ab += ab;
-        {
-            float v1 = (lane == 0) ? lw[0] : ((lane == 1) ? lw[1] : ((lane == 2) ? lw[2] : 0.f));
-#pragma unroll
-            for (int kk = 0; kk < KT; ++kk) v1 = (lane == 3 + kk) ? gl[kk] : v1;
-            st.stat1 += v1;
-            st.stat2 += (lane == e) ? 1.f : 0.f;
-        }
-        // user-side gradient pieces and dE[e] += g_z2 * ue*ie (this group's shared-memory slice)
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const int d0 = dim_of<VEC>(lane, j);
-            if (d0 < D) {
-                float de[VEC];
-                ldv<VEC>(myDE + e * D + d0, de);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) {
-                    const int x = j * VEC + v;
-                    acc0[x] += g_z1 * rc.x[x];
-                    acc_env[x] += g_z2 * rie.x[x] * ee[x];
-                    de[v] += g_z2 * t[x];
-#pragma unroll
-                    for (int kk = 0; kk < KT; ++kk) Q[kk][x] += gl[kk] * rc.x[x];
-                }
-                stv<VEC>(myDE + e * D + d0, de);
-            }
-        }
-        if (lane == 0) {   // g-pack for the item pass: g_z1, g_z2, env, -alpha * g_logits
-            float* gp = a.gpack_out + (int64_t)n * a.side.GS;
-            float out[12];
-            out[0] = g_z1;
-            out[1] = g_z2;
-            out[2] = __int_as_float(e);
-#pragma unroll
-            for (int kk = 0; kk < 9; ++kk) out[3 + kk] = (kk < KT) ? a.neg_alpha * gl[kk < KT ? kk : 0] : 0.f;
-            *reinterpret_cast<float4*>(gp) = make_float4(out[0], out[1], out[2], out[3]);
-            *reinterpret_cast<float4*>(gp + 4) = make_float4(out[4], out[5], out[6], out[7]);
-            if (KT > 5 && a.side.GS > 8)
-                *reinterpret_cast<float4*>(gp + 8) = make_float4(out[8], out[9], out[10], out[11]);
-        }
+        Inter<VEC, NV, KT> q;
+        inter_dots<VEC, NV, KT>(a, sE, sW, ra, rue, rc, rie, e, lane, q);
+        inter_grads<VEC, NV, KT>(a, cfg, myDE, sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, acc_env, st);
     }
 }
 
@@ -418,6 +449,222 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
     write_partials(a, s, KD, st, blockIdx.x);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Staged rows kernel (row slices of <= 16 bytes per lane, i.e. D <= 64).
+//
+// ncu on the register-only kernel above (round 1): 30 % of the warp samples wait on the long scoreboard -- the
+// (m, v, theta) rows of the segment behind a chain of dependent index loads, and the item rows of each
+// interaction -- with only 16 warps per SM to hide it.  Here the next segment's eight rows (theta, m, v of both
+// user tables + the two item rows of its first interaction) are copied global -> shared with cp.async while
+// the current segment is processed: no register is held while they are in flight, every lane copies exactly
+// the slice it later reads (no barrier, cp.async.wait_group only), and the item rows of interaction k+1 of a
+// multi-interaction segment are requested while interaction k is computed.  Index chain: one 16-byte segment
+// descriptor (row, begin, perm[begin], partner[begin]) loaded two segments ahead; the first interaction's
+// scalars (env, score, weight) and the row's last_step are loaded one segment ahead into ONE register spread
+// over lanes 8..11 and broadcast with shuffles.  The arithmetic is the register-only kernel's, value for value.
+constexpr int UP_SLOTS = 8;   // th_i, th_e, m_i, m_e, v_i, v_e, first item inv, first item env
+
+template <int VEC, int NV, int KT, int EPI, bool LAZY>
+__global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArgs a, int long_len) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = a.side.D, KD = a.side.K * a.side.D;
+    const Smem s = carve_smem(smem, KD);
+    float* ring = smem + (((4 + 2 * GROUPS_PER_BLOCK) * KD + INVPREF_MAX_ENVS + 3) & ~3);   // [2][8][NV][BLOCK][VEC]
+    Running st;
+    stage(a, s, KD, st);
+    const int lane = threadIdx.x & (GROUP - 1);
+    const unsigned gmask = group_mask();
+    const int gbase = threadIdx.x & 16;            // first lane of this group within the warp
+    float* myDE = s.sDE + (threadIdx.x >> 4) * KD;
+    float* myDW = s.sDW + (threadIdx.x >> 4) * KD;
+    const LossCfg cfg = {a.side.K, a.implicit, a.use_class_rw, a.use_rec_rw, a.c_inv, a.c_ea, a.c_env, a.invB};
+    const int n_seg = a.side.plan.counters[0];
+    const int ng = gridDim.x * GROUPS_PER_BLOCK;
+    const int s0 = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4);
+    const int4* __restrict__ seg_desc = reinterpret_cast<const int4*>(a.side.plan.seg_desc);
+    const int32_t* __restrict__ seg_off = a.side.plan.seg_off;
+    const int32_t* __restrict__ perm = a.side.plan.perm;
+    const int32_t* __restrict__ partner = a.side.plan.partner;
+
+    auto issue_segment = [&](int stg, int row, int pid) {
+        stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 0, a.side.own_inv_in, row, D, lane);
+        stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 1, a.side.own_env_in, row, D, lane);
+        if (EPI == EPI_ADAM) {
+            stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 2, a.side.m_inv, row, D, lane);
+            stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 3, a.side.m_env, row, D, lane);
+            stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 4, a.side.v_inv, row, D, lane);
+            stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 5, a.side.v_env, row, D, lane);
+        }
+        stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 6, a.side.partner_inv, pid, D, lane);
+        stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 7, a.side.partner_env, pid, D, lane);
+    };
+    // scalars of interaction n (and last_step of `row` when row >= 0), one per lane 8..11
+    auto load_scalars = [&](int n, int row) -> int {
+        int v = 0;
+        if (lane == 8) v = (int)a.envs[n];
+        else if (lane == 9) v = __float_as_int(a.scores[n]);
+        else if (lane == 10) v = (a.weights != nullptr) ? __float_as_int(a.weights[n]) : __float_as_int(1.f);
+        else if (LAZY && lane == 11 && row >= 0) v = a.side.last_step[row];
+        return v;
+    };
+
+    // cur = (d0, end0, sc0); next = (d1, end1): descriptors are loaded two segments ahead
+    int4 d0 = make_int4(0, 0, 0, 0), d1 = make_int4(0, 0, 0, 0);
+    int end0 = 0, end1 = 0, sc0 = 0;
+    if (s0 < n_seg) {
+        d0 = seg_desc[s0];
+        end0 = seg_off[s0 + 1];
+        issue_segment(0, d0.x, d0.w);
+        sc0 = load_scalars(d0.z, d0.x);
+    }
+    cp_async_commit();
+    if (s0 + ng < n_seg) { d1 = seg_desc[s0 + ng]; end1 = seg_off[s0 + ng + 1]; }
+    int stg = 0;
+    for (int sgm = s0; sgm < n_seg; sgm += ng, stg ^= 1) {
+        int sc1 = 0;
+        if (sgm + ng < n_seg) {
+            issue_segment(stg ^ 1, d1.x, d1.w);
+            sc1 = load_scalars(d1.z, d1.x);
+            if (end1 - d1.y > 1) {   // its second interaction's indices: into L2 now, loaded at the segment's start
+                if (lane == 12) prefetch_l2(perm + d1.y + 1);
+                if (lane == 13) prefetch_l2(partner + d1.y + 1);
+            }
+        }
+        cp_async_commit();
+        int4 d2 = make_int4(0, 0, 0, 0);
+        int end2 = 0;
+        if (sgm + 2 * ng < n_seg) { d2 = seg_desc[sgm + 2 * ng]; end2 = seg_off[sgm + 2 * ng + 1]; }
+
+        const int64_t row = d0.x;
+        const int beg = d0.y, end = end0;
+        int n = d0.z;
+        int e = __shfl_sync(gmask, sc0, gbase + 8);
+        float y = __int_as_float(__shfl_sync(gmask, sc0, gbase + 9));
+        float w = __int_as_float(__shfl_sync(gmask, sc0, gbase + 10));
+        const int last = LAZY ? __shfl_sync(gmask, sc0, gbase + 11) : 0;
+        int n_nx = 0, it_nx = 0;
+        const bool is_long = end - beg > long_len;
+        if (!is_long && beg + 1 < end) { n_nx = perm[beg + 1]; it_nx = partner[beg + 1]; }
+
+        cp_async_wait<1>();   // everything but the group committed above has landed
+        Row<VEC, NV> ra, rue, gi, ge;
+        Row<VEC, NV> m_i, m_e, v_i, v_e;
+        read_staged_row<VEC, NV>(ra, ring, stg * UP_SLOTS + 0, D, lane);
+        read_staged_row<VEC, NV>(rue, ring, stg * UP_SLOTS + 1, D, lane);
+        if (LAZY) {
+            // the row may be several steps behind: replay the skipped zero-gradient Adam steps in registers,
+            // then stash the caught-up row (what every reader of this step must see) for the item pass
+            read_staged_row<VEC, NV>(m_i, ring, stg * UP_SLOTS + 2, D, lane);
+            read_staged_row<VEC, NV>(m_e, ring, stg * UP_SLOTS + 3, D, lane);
+            read_staged_row<VEC, NV>(v_i, ring, stg * UP_SLOTS + 4, D, lane);
+            read_staged_row<VEC, NV>(v_e, ring, stg * UP_SLOTS + 5, D, lane);
+            replay_steps<VEC, NV>(a.side, last, a.side.step - 1, ra, rue, m_i, m_e, v_i, v_e);
+            store_row<VEC, NV>(ra, a.side.stash, (int64_t)sgm * 2, D, lane);
+            store_row<VEC, NV>(rue, a.side.stash, (int64_t)sgm * 2 + 1, D, lane);
+            // the caught-up moments go back to their (own) slots: no registers held over the interactions
+            write_staged_row<VEC, NV>(m_i, ring, stg * UP_SLOTS + 2, D, lane);
+            write_staged_row<VEC, NV>(m_e, ring, stg * UP_SLOTS + 3, D, lane);
+            write_staged_row<VEC, NV>(v_i, ring, stg * UP_SLOTS + 4, D, lane);
+            write_staged_row<VEC, NV>(v_e, ring, stg * UP_SLOTS + 5, D, lane);
+        }
+        if (is_long) {   // long segment: its forward + reduction ran in upass_chunks_kernel
+            const int c0 = a.side.plan.seg_chunk[sgm], c1 = a.side.plan.seg_chunk[sgm + 1];
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
+            for (int c = c0; c < c1; ++c) {
+                Row<VEC, NV> pi, pe;
+                load_row<VEC, NV>(pi, a.side.chunk_part, (int64_t)c * 2, D, lane);
+                load_row<VEC, NV>(pe, a.side.chunk_part, (int64_t)c * 2 + 1, D, lane);
+#pragma unroll
+                for (int x = 0; x < NV * VEC; ++x) { gi.x[x] += pi.x[x]; ge.x[x] += pe.x[x]; }
+            }
+        } else {
+            float acc0[NV * VEC], Q[KT][NV * VEC];
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) {
+                acc0[x] = 0.f; ge.x[x] = 0.f;
+#pragma unroll
+                for (int k = 0; k < KT; ++k) Q[k][x] = 0.f;
+            }
+            for (int k = beg; k < end; ++k) {
+                if (k > beg) cp_async_wait<0>();
+                Row<VEC, NV> rc, rie;
+                read_staged_row<VEC, NV>(rc, ring, stg * UP_SLOTS + 6, D, lane);
+                read_staged_row<VEC, NV>(rie, ring, stg * UP_SLOTS + 7, D, lane);
+                Inter<VEC, NV, KT> q;
+                inter_dots<VEC, NV, KT>(a, s.sE, s.sW, ra, rue, rc, rie, e, lane, q);
+                int sck = 0, n_k1 = 0;
+                if (k + 1 < end) {
+                    // the item slots were read into registers (the sums below depend on every element): request
+                    // interaction k+1's rows into them, its scalars into a register, and k+2's indices
+                    asm volatile("" ::"f"(q.z1), "f"(q.z2) : "memory");
+                    stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 6, a.side.partner_inv, it_nx, D, lane);
+                    stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 7, a.side.partner_env, it_nx, D, lane);
+                    cp_async_commit();
+                    sck = load_scalars(n_nx, -1);
+                    n_k1 = n_nx;
+                    if (k + 2 < end) { n_nx = perm[k + 2]; it_nx = partner[k + 2]; }
+                }
+                inter_grads<VEC, NV, KT>(a, cfg, myDE, s.sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, ge.x, st);
+                if (k + 1 < end) {
+                    n = n_k1;
+                    e = __shfl_sync(gmask, sck, gbase + 8);
+                    y = __int_as_float(__shfl_sync(gmask, sck, gbase + 9));
+                    w = __int_as_float(__shfl_sync(gmask, sck, gbase + 10));
+                }
+            }
+            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi);
+        }
+        // the user rows' own L1/L2 terms (models.py:469-482): every occurrence in the batch counts
+        const float cnt = (float)(end - beg);
+        float sq = 0.f, ab = 0.f;
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) {
+            sq += ra.x[x] * ra.x[x] + rue.x[x] * rue.x[x];
+            ab += fabsf(ra.x[x]) + fabsf(rue.x[x]);
+            gi.x[x] += cnt * (a.side.reg2 * ra.x[x] + mul_sign(a.side.reg1, ra.x[x]));
+            ge.x[x] += cnt * (a.side.reg2 * rue.x[x] + mul_sign(a.side.reg1, rue.x[x]));
+        }
+        st.sq += cnt * sq;
+        st.ab += cnt * ab;
+        if (a.side.grad_inv != nullptr) {
+            store_row<VEC, NV>(gi, a.side.grad_inv, row, D, lane);
+            store_row<VEC, NV>(ge, a.side.grad_env, row, D, lane);
+        }
+        if (EPI == EPI_ADAM) {
+            read_staged_row<VEC, NV>(m_i, ring, stg * UP_SLOTS + 2, D, lane);
+            read_staged_row<VEC, NV>(m_e, ring, stg * UP_SLOTS + 3, D, lane);
+            read_staged_row<VEC, NV>(v_i, ring, stg * UP_SLOTS + 4, D, lane);
+            read_staged_row<VEC, NV>(v_e, ring, stg * UP_SLOTS + 5, D, lane);
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) {
+                adam_update(ra.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.side.adam);
+                adam_update(rue.x[x], m_e.x[x], v_e.x[x], ge.x[x], a.side.adam);
+            }
+            store_row<VEC, NV>(ra, a.side.own_inv_out, row, D, lane);
+            store_row<VEC, NV>(rue, a.side.own_env_out, row, D, lane);
+            store_row<VEC, NV, true>(m_i, a.side.m_inv, row, D, lane);
+            store_row<VEC, NV, true>(m_e, a.side.m_env, row, D, lane);
+            store_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
+            store_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
+            if (LAZY && lane == 0) a.side.last_step[row] = a.side.step;
+        }
+        d0 = d1; end0 = end1; sc0 = sc1;
+        d1 = d2; end1 = end2;
+    }
+    cp_async_wait<0>();
+    write_partials(a, s, KD, st, blockIdx.x);
+}
+
+inline size_t upass_ring_bytes(const Geometry& g) { return (size_t)2 * UP_SLOTS * g.NV * g.VEC * BLOCK * sizeof(float); }
+inline bool upass_staged(const Geometry& g) {
+    static const bool enabled = [] {
+        const char* e = getenv("INVPREF_STAGED");   // INVPREF_STAGED=0: register-only rows kernel (A/B runs)
+        return !(e && e[0] == '0');
+    }();
+    return enabled && g.NV * g.VEC <= 4;
+}
+
 inline size_t upass_smem(const Geometry& g) {
     return ((size_t)(4 + 2 * GROUPS_PER_BLOCK) * g.K * g.D + INVPREF_MAX_ENVS) * sizeof(float);
 }
@@ -426,10 +673,16 @@ inline size_t upass_smem(const Geometry& g) {
 
 bool upass_supported(const Geometry& g) { return upass_smem(g) <= 96 * 1024; }
 
-int upass_rows_grid(int64_t max_seg) {
+static bool use_staged(const Geometry& g) {
+    return upass_staged(g) && ((upass_smem(g) + 15) & ~(size_t)15) + upass_ring_bytes(g) <= 227 * 1024;
+}
+
+int upass_rows_grid(const Geometry& g, int64_t max_seg) {
     int64_t need = (max_seg + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
     if (need < 1) need = 1;
-    return (int)(need < 148 * 4 ? need : 148 * 4);
+    // staged kernel: two CTAs are resident per SM (registers, shared memory) -> one wave
+    const int64_t cap = use_staged(g) ? 148 * 2 : 148 * 4;
+    return (int)(need < cap ? need : cap);
 }
 
 int launch_upass_chunks(const Geometry& g, const UserPassArgs& a, int cta_offset, cudaStream_t stream) {
@@ -453,9 +706,33 @@ int launch_upass_chunks(const Geometry& g, const UserPassArgs& a, int cta_offset
 }
 
 int launch_upass_rows(const Geometry& g, const UserPassArgs& a, int epi, int grid, cudaStream_t stream) {
-    const size_t smem = upass_smem(g);
     const bool lazy = a.side.last_step != nullptr;
     if (lazy && epi != EPI_ADAM) return INVPREF_ERR_BAD_ARG;
+    if (use_staged(g)) {
+        const size_t smem = ((upass_smem(g) + 15) & ~(size_t)15) + upass_ring_bytes(g);
+        const int long_len = 2 * chunk_for(a.side.plan.B);   // plan.cu: segments longer than this are chunked
+#define LAUNCH(KERNEL)                                                                                           \
+    do {                                                                                                         \
+        cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
+        KERNEL<<<grid, BLOCK, smem, stream>>>(a, long_len);                                                      \
+    } while (0)
+#define CALL(V, N, KT_)                                                                                          \
+    do {                                                                                                         \
+        if (lazy) LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_ADAM, true>));                                 \
+        else if (epi == EPI_ADAM) LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_ADAM, false>));                \
+        else LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_EXPORT, false>));                                   \
+    } while (0)
+        const int _k = g.KT;
+        if (g.VEC == 4) { INVPREF_DISPATCH_K(4, 1, _k, CALL); }
+        else if (g.VEC == 2 && g.NV == 1) { INVPREF_DISPATCH_K(2, 1, _k, CALL); }
+        else if (g.VEC == 2) { INVPREF_DISPATCH_K(2, 2, _k, CALL); }
+        else { INVPREF_DISPATCH_K(1, 4, _k, CALL); }
+#undef CALL
+#undef LAUNCH
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+    }
+    const size_t smem = upass_smem(g);
 #define LAUNCH(KERNEL)                                                                                           \
     do {                                                                                                         \
         if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
