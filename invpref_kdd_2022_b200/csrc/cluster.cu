@@ -60,15 +60,20 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_r
         stage_row_async<VEC, NV>(ring, slot * 4 + 2, a.Uenv, u, D, lane);
         stage_row_async<VEC, NV>(ring, slot * 4 + 3, a.Ienv, it, D, lane);
     };
-    // prologue: rows of the first ST-1 samples in flight, ids of the next one in registers
+    // ids are below 2^31 (make_geometry): only the low word of each int64 is loaded.  They run TWO iterations
+    // ahead of the row requests (one was not enough: the request stalled on its own ids, ncu round 1).
+    const int32_t* __restrict__ users_lo = reinterpret_cast<const int32_t*>(a.users);
+    const int32_t* __restrict__ items_lo = reinterpret_cast<const int32_t*>(a.items);
+    // prologue: rows of the first ST-1 samples in flight, ids of the next two in registers
 #pragma unroll
     for (int q = 0; q < ST - 1; ++q) {
         const int64_t n = n0 + q * stride;
-        if (n < a.B) issue(q, a.users[n], a.items[n]);
+        if (n < a.B) issue(q, users_lo[2 * n], items_lo[2 * n]);
         cp_async_commit();
     }
-    int64_t uq = 0, iq = 0;
-    if (n0 + (ST - 1) * stride < a.B) { uq = a.users[n0 + (ST - 1) * stride]; iq = a.items[n0 + (ST - 1) * stride]; }
+    int uq = 0, iq = 0, uq2 = 0, iq2 = 0;
+    if (n0 + (ST - 1) * stride < a.B) { uq = users_lo[2 * (n0 + (ST - 1) * stride)]; iq = items_lo[2 * (n0 + (ST - 1) * stride)]; }
+    if (n0 + ST * stride < a.B) { uq2 = users_lo[2 * (n0 + ST * stride)]; iq2 = items_lo[2 * (n0 + ST * stride)]; }
     unsigned cnt[KT], ndiff = 0;   // lane 0: this group's histogram and diff count
 #pragma unroll
     for (int k = 0; k < KT; ++k) cnt[k] = 0u;
@@ -79,7 +84,8 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_r
         int wslot = slot + ST - 1; if (wslot >= ST) wslot -= ST;
         if (n + (ST - 1) * stride < a.B) issue(wslot, uq, iq);
         cp_async_commit();
-        if (n + ST * stride < a.B) { uq = a.users[n + ST * stride]; iq = a.items[n + ST * stride]; }
+        uq = uq2; iq = iq2;
+        if (n + (ST + 1) * stride < a.B) { uq2 = users_lo[2 * (n + (ST + 1) * stride)]; iq2 = items_lo[2 * (n + (ST + 1) * stride)]; }
         const float y = a.scores[n];
         const int64_t pidx = (a.perm_idx != nullptr) ? a.perm_idx[n] : 0;
         const int64_t old = (a.diff != nullptr) ? a.old_envs[n] : 0;
@@ -108,30 +114,36 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_r
                 }
             }
         }
+        // K sums with one scattered reduction: lanes [k * 16/NS, (k+1) * 16/NS) end up with z2[k]; each computes
+        // the distance under ITS environment, then a (distance, k) butterfly picks the first minimum
+        // (torch.argmin: ties go to the lowest k) -- same values as the serial loop of train.py:853-876.
         z1 = group_sum(z1, gmask);
+        constexpr int NS = (KT <= 2) ? 2 : ((KT <= 4) ? 4 : 8);
+        float zs[NS];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) z2[k] = group_sum(z2[k], gmask);
+        for (int k = 0; k < NS; ++k) zs[k] = (k < KT) ? z2[k < KT ? k : 0] : 0.f;
+        const float zk = group_sum_scatter<NS>(zs, lane, gmask);
+        int arg = lane / (GROUP / NS);
+        float d;
+        if (a.implicit) {
+            const float s = sigmoidf_(z1) * sigmoidf_(zk);
+            d = -(y * fmaxf(logf(s), -100.f) + (1.f - y) * fmaxf(logf(1.f - s), -100.f));
+        } else {
+            const float r = (z1 + zk) - y;
+            d = r * r;
+        }
+        if (arg < K) {
+            if (a.perm_idx != nullptr) d = d + ((eps_rows_smem > 0 ? sEps : a.eps_table) + pidx * K)[arg];
+        } else {
+            d = INFINITY;   // padding lanes never win (an all-inf row still resolves to the lowest k)
+        }
+#pragma unroll
+        for (int o = GROUP / NS; o < GROUP; o <<= 1) {
+            const float d2 = __shfl_xor_sync(gmask, d, o);
+            const int k2 = __shfl_xor_sync(gmask, arg, o);
+            if (d2 < d || (d2 == d && k2 < arg)) { d = d2; arg = k2; }
+        }
         if (lane == 0) {
-            const float* eps = nullptr;
-            if (a.perm_idx != nullptr) eps = (eps_rows_smem > 0 ? sEps : a.eps_table) + pidx * K;
-            const float s_inv = a.implicit ? sigmoidf_(z1) : z1;
-            float best = 0.f;
-            int arg = 0;
-#pragma unroll
-            for (int k = 0; k < KT; ++k) {
-                if (k < K) {
-                    float d;
-                    if (a.implicit) {
-                        const float s = s_inv * sigmoidf_(z2[k]);
-                        d = -(y * fmaxf(logf(s), -100.f) + (1.f - y) * fmaxf(logf(1.f - s), -100.f));
-                    } else {
-                        const float r = (z1 + z2[k]) - y;
-                        d = r * r;
-                    }
-                    if (eps != nullptr) d = d + eps[k];
-                    if (k == 0 || d < best) { best = d; arg = k; }   // torch.argmin: first minimum wins
-                }
-            }
             a.new_envs[n] = (int64_t)arg;
 #pragma unroll
             for (int k = 0; k < KT; ++k) cnt[k] += (arg == k) ? 1u : 0u;

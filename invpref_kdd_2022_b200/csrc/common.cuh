@@ -370,6 +370,30 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
     return v;
 }
 
+// N sums at once (N = 2, 4, 8 or 16): every lane passes v[0..N-1] and gets back the 16-lane sum of v[k],
+// k = lane / (16 / N).  At each level a lane keeps one half of its values and sends the other half to its
+// partner (keep + received, the butterfly's own + partner), so the result is bitwise group_sum(v[k]) with
+// N - 1 + log2(16 / N) shuffles instead of 4 N.
+template <int N>
+__device__ __forceinline__ float group_sum_scatter(float (&v)[N], int lane, unsigned mask) {
+    static_assert(N == 2 || N == 4 || N == 8 || N == 16, "N must divide the group");
+    int off = GROUP / 2;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1, off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < n / 2; ++j) {
+            const float keep = hi ? v[n / 2 + j] : v[j];
+            const float send = hi ? v[j] : v[n / 2 + j];
+            v[j] = keep + __shfl_xor_sync(mask, send, off);
+        }
+    }
+    float x = v[0];
+#pragma unroll
+    for (int o = GROUP / (2 * N); o >= 1; o >>= 1) x += __shfl_xor_sync(mask, x, o);
+    return x;
+}
+
 // all 32 lanes must be converged (used after the loops only)
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);

@@ -498,13 +498,21 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
         stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 6, a.side.partner_inv, pid, D, lane);
         stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 7, a.side.partner_env, pid, D, lane);
     };
-    // scalars of interaction n (and last_step of `row` when row >= 0), one per lane 8..11
-    auto load_scalars = [&](int n, int row) -> int {
-        int v = 0;
-        if (lane == 8) v = (int)a.envs[n];
-        else if (lane == 9) v = __float_as_int(a.scores[n]);
-        else if (lane == 10) v = (a.weights != nullptr) ? __float_as_int(a.weights[n]) : __float_as_int(1.f);
-        else if (LAZY && lane == 11 && row >= 0) v = a.side.last_step[row];
+    // Scalars needed one step ahead, ONE 32-bit register spread over the lanes of the group and broadcast with
+    // shuffles when used: lane 8 env[n], 9 score[n], 10 weight[n], 11 last_step[row] (row >= 0), 12 perm[k2],
+    // 13 partner[k2] (k2 >= 0: sorted position of the interaction after n).  The address is picked with
+    // selects and loaded with one predicated instruction (per-lane branches here cost 15 % of the kernel: ncu).
+    const bool has_w = a.weights != nullptr;
+    auto load_scalars = [&](int n, int row, int k2) -> int {
+        const int32_t* p = reinterpret_cast<const int32_t*>(a.envs + n);   // low word of the int64 (0 <= env < K)
+        bool on = lane == 8;
+        if (lane == 9) { p = reinterpret_cast<const int32_t*>(a.scores + n); on = true; }
+        if (lane == 10 && has_w) { p = reinterpret_cast<const int32_t*>(a.weights + n); on = true; }
+        if (LAZY && lane == 11 && row >= 0) { p = a.side.last_step + row; on = true; }
+        if (lane == 12 && k2 >= 0) { p = perm + k2; on = true; }
+        if (lane == 13 && k2 >= 0) { p = partner + k2; on = true; }
+        int v = (lane == 10) ? __float_as_int(1.f) : 0;
+        if (on) v = *p;
         return v;
     };
 
@@ -515,7 +523,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
         d0 = seg_desc[s0];
         end0 = seg_off[s0 + 1];
         issue_segment(0, d0.x, d0.w);
-        sc0 = load_scalars(d0.z, d0.x);
+        sc0 = load_scalars(d0.z, d0.x, d0.y + 1 < end0 ? d0.y + 1 : -1);
     }
     cp_async_commit();
     if (s0 + ng < n_seg) { d1 = seg_desc[s0 + ng]; end1 = seg_off[s0 + ng + 1]; }
@@ -524,11 +532,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
         int sc1 = 0;
         if (sgm + ng < n_seg) {
             issue_segment(stg ^ 1, d1.x, d1.w);
-            sc1 = load_scalars(d1.z, d1.x);
-            if (end1 - d1.y > 1) {   // its second interaction's indices: into L2 now, loaded at the segment's start
-                if (lane == 12) prefetch_l2(perm + d1.y + 1);
-                if (lane == 13) prefetch_l2(partner + d1.y + 1);
-            }
+            sc1 = load_scalars(d1.z, d1.x, d1.y + 1 < end1 ? d1.y + 1 : -1);
         }
         cp_async_commit();
         int4 d2 = make_int4(0, 0, 0, 0);
@@ -542,9 +546,8 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
         float y = __int_as_float(__shfl_sync(gmask, sc0, gbase + 9));
         float w = __int_as_float(__shfl_sync(gmask, sc0, gbase + 10));
         const int last = LAZY ? __shfl_sync(gmask, sc0, gbase + 11) : 0;
-        int n_nx = 0, it_nx = 0;
+        int n_nx = __shfl_sync(gmask, sc0, gbase + 12), it_nx = __shfl_sync(gmask, sc0, gbase + 13);
         const bool is_long = end - beg > long_len;
-        if (!is_long && beg + 1 < end) { n_nx = perm[beg + 1]; it_nx = partner[beg + 1]; }
 
         cp_async_wait<1>();   // everything but the group committed above has landed
         Row<VEC, NV> ra, rue, gi, ge;
@@ -601,9 +604,8 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
                     stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 6, a.side.partner_inv, it_nx, D, lane);
                     stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 7, a.side.partner_env, it_nx, D, lane);
                     cp_async_commit();
-                    sck = load_scalars(n_nx, -1);
+                    sck = load_scalars(n_nx, -1, k + 2 < end ? k + 2 : -1);
                     n_k1 = n_nx;
-                    if (k + 2 < end) { n_nx = perm[k + 2]; it_nx = partner[k + 2]; }
                 }
                 inter_grads<VEC, NV, KT>(a, cfg, myDE, s.sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, ge.x, st);
                 if (k + 1 < end) {
@@ -611,6 +613,8 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
                     e = __shfl_sync(gmask, sck, gbase + 8);
                     y = __int_as_float(__shfl_sync(gmask, sck, gbase + 9));
                     w = __int_as_float(__shfl_sync(gmask, sck, gbase + 10));
+                    n_nx = __shfl_sync(gmask, sck, gbase + 12);
+                    it_nx = __shfl_sync(gmask, sck, gbase + 13);
                 }
             }
             finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi);

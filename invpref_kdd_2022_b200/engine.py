@@ -137,16 +137,28 @@ class HotPath:
             self._ws_batch = batch
         return self._ws
 
-    def new_plan(self, users: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
-        """Sort-segment plan of one batch (``invpref_build_plan``); reusable while (users, items) are fixed."""
+    def new_plan(self, users: torch.Tensor, items: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Sort-segment plan of one batch (``invpref_build_plan``); reusable while (users, items) are fixed.
+
+        Runs on the current stream and touches only the sort scratch of the workspace, which a ``train_step``
+        that is GIVEN a plan never uses: the plan of the next batch can be built on a side stream while the
+        current step runs (``out``: caller-owned buffer of at least ``plan_bytes`` bytes to build into)."""
         B = users.numel()
         n = _lib.plan_bytes(self.desc, B)
-        plan = torch.empty(n, dtype=torch.uint8, device=self.device)
+        if out is None:
+            plan = torch.empty(n, dtype=torch.uint8, device=self.device)
+        else:
+            if not (out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= n):
+                raise RuntimeError("new_plan(out=...): need a contiguous uint8 CUDA buffer of plan_bytes() bytes")
+            plan = out
         ws = self.workspace(B)
         _lib.check(self.lib.invpref_build_plan(C.byref(self.desc), _lib.ptr(users, torch.int64),
-                                               _lib.ptr(items, torch.int64), B, _lib.ptr(plan), n, _lib.ptr(ws),
-                                               ws.numel(), _lib.stream_ptr()), "build_plan")
+                                               _lib.ptr(items, torch.int64), B, _lib.ptr(plan), plan.numel(),
+                                               _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "build_plan")
         return plan
+
+    def plan_bytes(self, batch: int) -> int:
+        return _lib.plan_bytes(self.desc, batch)
 
     # ---- fused train step ---------------------------------------------------------------------
     def train_step(self, users, items, scores, envs, weights, *, c_inv, c_ea, c_env, c_L2, c_L1, alpha,
