@@ -91,6 +91,48 @@ __device__ __forceinline__ void stage_EW(const BwdSideArgs& a, float* sE, float*
     __syncthreads();
 }
 
+// Epilogue of one row: its own L1/L2 term (models.py:469-497, every occurrence counts), then Adam in
+// registers / gradient export / accumulation into a dense gradient.
+template <int VEC, int NV, int EPI>
+__device__ __forceinline__ void finish_row(const BwdSideArgs& a, int64_t row, float cnt, Row<VEC, NV>& th_i,
+                                           Row<VEC, NV>& th_e, Row<VEC, NV>& m_i, Row<VEC, NV>& m_e,
+                                           Row<VEC, NV>& v_i, Row<VEC, NV>& v_e, Row<VEC, NV>& gi, Row<VEC, NV>& ge,
+                                           int lane) {
+    const int D = a.D;
+    if (EPI == EPI_ADAM || EPI == EPI_EXPORT) {
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) {
+            gi.x[x] += cnt * (a.reg2 * th_i.x[x] + mul_sign(a.reg1, th_i.x[x]));
+            ge.x[x] += cnt * (a.reg2 * th_e.x[x] + mul_sign(a.reg1, th_e.x[x]));
+        }
+        if (a.grad_inv != nullptr) {
+            store_row<VEC, NV>(gi, a.grad_inv, row, D, lane);
+            store_row<VEC, NV>(ge, a.grad_env, row, D, lane);
+        }
+    }
+    if (EPI == EPI_ADAM) {
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) {
+            adam_update(th_i.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.adam);
+            adam_update(th_e.x[x], m_e.x[x], v_e.x[x], ge.x[x], a.adam);
+        }
+        store_row<VEC, NV>(th_i, a.own_inv_out, row, D, lane);
+        store_row<VEC, NV>(th_e, a.own_env_out, row, D, lane);
+        store_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+        store_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+        store_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+        store_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
+    } else if (EPI == EPI_ACCUM) {
+        Row<VEC, NV> oi, oe;
+        load_row<VEC, NV>(oi, a.grad_inv, row, D, lane);
+        load_row<VEC, NV>(oe, a.grad_env, row, D, lane);
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) { oi.x[x] += gi.x[x]; oe.x[x] += ge.x[x]; }
+        store_row<VEC, NV>(oi, a.grad_inv, row, D, lane);
+        store_row<VEC, NV>(oe, a.grad_env, row, D, lane);
+    }
+}
+
 template <int VEC, int NV, bool STASH>
 __global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_kernel(BwdSideArgs a) {
     extern __shared__ float smem[];
@@ -150,41 +192,177 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
         } else {
             accumulate_range<VEC, NV, STASH>(a, sE, sW, beg, end, lane, gi.x, ge.x);
         }
-        if (EPI == EPI_ADAM || EPI == EPI_EXPORT) {
-            // L1/L2 term of the gathered rows (models.py:469-497): every occurrence counts
-            const float cnt = (float)(end - beg);
-#pragma unroll
-            for (int x = 0; x < NV * VEC; ++x) {
-                gi.x[x] += cnt * (a.reg2 * th_i.x[x] + mul_sign(a.reg1, th_i.x[x]));
-                ge.x[x] += cnt * (a.reg2 * th_e.x[x] + mul_sign(a.reg1, th_e.x[x]));
-            }
-            if (a.grad_inv != nullptr) {
-                store_row<VEC, NV>(gi, a.grad_inv, row, D, lane);
-                store_row<VEC, NV>(ge, a.grad_env, row, D, lane);
-            }
+        finish_row<VEC, NV, EPI>(a, row, (float)(end - beg), th_i, th_e, m_i, m_e, v_i, v_e, gi, ge, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Ring rows kernel (row slices of <= 16 bytes per lane, i.e. D <= 64; Adam / export epilogues).
+//
+// ncu on bwd_rows_kernel (round 1): 47 % of the warp samples wait on the long scoreboard -- perm/partner ->
+// g-pack + two partner rows per interaction, L2 prefetch or not.  Here
+//  * the plan cuts the segments into cost-balanced CONTIGUOUS ranges (plan.cu: write_ranges_kernel); a group
+//    takes ranges g, g + G, ...: inside a range the sorted positions it walks are contiguous across segment
+//    boundaries, and the strided assignment averages out what the cost model misses (a first version with ONE
+//    range per group ran 1.5x longer on its slowest SM than on average);
+//  * a producer cursor runs RING-1 interactions ahead of the consumer -- across segment and range boundaries
+//    -- and copies the partner rows (each lane its own slice) and the g-pack of every interaction global ->
+//    shared with cp.async: no register is held while the data is in flight;
+//  * per segment the arithmetic is accumulate_range's / finish_row's, value for value and in the same order.
+constexpr int RING = 4;
+
+template <int VEC, int NV, int EPI, bool STASH>
+__global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, int long_len) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = a.D, K = a.K, GS = a.GS, KD = a.K * a.D;
+    float* sE = smem;
+    float* sW = smem + KD;
+    float* sG = smem + ((2 * KD + 3) & ~3);                    // [groups][RING + 1][12] g-packs
+    float* ring = sG + GROUPS_PER_BLOCK * (RING + 1) * 12;     // [RING][2 rows][NV][BLOCK][VEC]
+    stage_EW(a, sE, sW);
+    const int lane = threadIdx.x & (GROUP - 1);
+    const unsigned gmask = group_mask();
+    float* myG = sG + (threadIdx.x >> 4) * (RING + 1) * 12;
+    const int n_seg = a.plan.counters[0];
+    const int NR = a.plan.counters[3];
+    const int32_t* __restrict__ range_start = a.plan.range_start;
+    const int32_t* __restrict__ seg_off = a.plan.seg_off;
+    const int32_t* __restrict__ seg_row = a.plan.seg_row;
+    const int32_t* __restrict__ perm = a.plan.perm;
+    const int32_t* __restrict__ partner = STASH ? a.plan.pseg : a.plan.partner;
+    const float* __restrict__ pinv = STASH ? a.stash : a.partner_inv;
+    const float* __restrict__ penv = STASH ? a.stash + D : a.partner_env;
+    constexpr int pmul = STASH ? 2 : 1;
+    const int G = gridDim.x * GROUPS_PER_BLOCK;
+    const int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4);
+
+    // ---- producer cursor: the next interaction to request.  (pr, ps, pk): range, segment, sorted position;
+    //      pr >= NR: exhausted.  Long segments (pre-reduced by the chunks kernel) are skipped.
+    int pr = g, ps = 0, psb = 0, pk = 0, pend = 0, pend_nx = 0, nsa = 0, nsb = 0, n_q = 0, pid_q = 0;
+    auto p_enter_range = [&]() {   // bounds of range pr were loaded one range ago (nsa, nsb)
+        ps = nsa; psb = nsb;
+        if (pr + G < NR) { nsa = range_start[pr + G]; nsb = range_start[pr + G + 1]; }
+        if (ps < psb) {
+            pk = seg_off[ps]; pend = seg_off[ps + 1];
+            pend_nx = (ps + 2 <= n_seg) ? seg_off[ps + 2] : 0;
         }
-        if (EPI == EPI_ADAM) {
+    };
+    auto p_next_seg = [&]() {
+        ++ps; pk = pend; pend = pend_nx;
+        pend_nx = (ps + 2 <= n_seg) ? seg_off[ps + 2] : 0;
+    };
+    auto p_seek = [&]() {          // settle on a short segment, or run out of ranges
+        while (pr < NR) {
+            if (ps >= psb) { pr += G; if (pr < NR) p_enter_range(); continue; }
+            if (pend - pk > long_len) { p_next_seg(); continue; }
+            break;
+        }
+    };
+    if (pr < NR) {
+        nsa = range_start[pr]; nsb = range_start[pr + 1];
+        p_enter_range();
+        p_seek();
+        if (pr < NR) { n_q = perm[pk]; pid_q = partner[pk]; }
+    }
+    int wslot = 0, wgs = 0;        // ring slot / g-pack slot the producer fills next
+    auto produce = [&]() {
+        if (pr < NR) {
+            stage_row_async<VEC, NV>(ring, wslot * 2 + 0, pinv, (int64_t)pid_q * pmul, D, lane);
+            stage_row_async<VEC, NV>(ring, wslot * 2 + 1, penv, (int64_t)pid_q * pmul, D, lane);
+            if (lane * 4 < GS) cp_async<16>(smem_addr(myG + wgs * 12 + lane * 4), a.gpack + (int64_t)n_q * GS + lane * 4);
+            if (++pk == pend) { p_next_seg(); p_seek(); }
+            if (pr < NR) { n_q = perm[pk]; pid_q = partner[pk]; }
+        }
+        cp_async_commit();
+        if (++wslot == RING) wslot = 0;
+        if (++wgs == RING + 1) wgs = 0;
+    };
 #pragma unroll
-            for (int x = 0; x < NV * VEC; ++x) {
-                adam_update(th_i.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.adam);
-                adam_update(th_e.x[x], m_e.x[x], v_e.x[x], ge.x[x], a.adam);
+    for (int q = 0; q < RING - 1; ++q) produce();
+
+    // ---- consumer: the same ranges, segment by segment ----
+    int rslot = 0, rgs = 0;
+    int csa_n = 0, csb_n = 0;      // bounds of the consumer's next range
+    if (g < NR) { csa_n = range_start[g]; csb_n = range_start[g + 1]; }
+    for (int r = g; r < NR; r += G) {
+        const int sa = csa_n, sb = csb_n;
+        if (r + G < NR) { csa_n = range_start[r + G]; csb_n = range_start[r + G + 1]; }
+        if (sa >= sb) continue;
+        int cend = seg_off[sa], cend_nx = seg_off[sa + 1], row_nx = seg_row[sa];
+        for (int cs = sa; cs < sb; ++cs) {
+            const int beg = cend, end = cend_nx;
+            const int64_t row = row_nx;
+            cend = cend_nx;
+            cend_nx = (cs + 2 <= n_seg) ? seg_off[cs + 2] : 0;
+            if (cs + 1 < n_seg) row_nx = seg_row[cs + 1];
+            Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
+            load_row<VEC, NV>(th_i, a.own_inv_in, row, D, lane);
+            load_row<VEC, NV>(th_e, a.own_env_in, row, D, lane);
+            if (EPI == EPI_ADAM) {
+                load_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+                load_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+                load_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+                load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
             }
-            store_row<VEC, NV>(th_i, a.own_inv_out, row, D, lane);
-            store_row<VEC, NV>(th_e, a.own_env_out, row, D, lane);
-            store_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
-            store_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
-            store_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
-            store_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
-        } else if (EPI == EPI_ACCUM) {
-            Row<VEC, NV> oi, oe;
-            load_row<VEC, NV>(oi, a.grad_inv, row, D, lane);
-            load_row<VEC, NV>(oe, a.grad_env, row, D, lane);
+            Row<VEC, NV> gi, ge;
 #pragma unroll
-            for (int x = 0; x < NV * VEC; ++x) { oi.x[x] += gi.x[x]; oe.x[x] += ge.x[x]; }
-            store_row<VEC, NV>(oi, a.grad_inv, row, D, lane);
-            store_row<VEC, NV>(oe, a.grad_env, row, D, lane);
+            for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
+            if (end - beg > long_len) {
+                const int c0 = a.plan.seg_chunk[cs], c1 = a.plan.seg_chunk[cs + 1];
+                for (int c = c0; c < c1; ++c) {
+                    Row<VEC, NV> pi, pe;
+                    load_row<VEC, NV>(pi, a.chunk_part, (int64_t)c * 2, D, lane);
+                    load_row<VEC, NV>(pe, a.chunk_part, (int64_t)c * 2 + 1, D, lane);
+#pragma unroll
+                    for (int x = 0; x < NV * VEC; ++x) { gi.x[x] += pi.x[x]; ge.x[x] += pe.x[x]; }
+                }
+            } else {
+                for (int k = beg; k < end; ++k) {
+                    produce();
+                    cp_async_wait<RING - 1>();
+                    __syncwarp(gmask);   // the g-pack was copied by lanes 0..2 of this group
+                    float gq[12];
+                    {
+                        const float4* gp = reinterpret_cast<const float4*>(myG + rgs * 12);
+                        const float4 q0 = gp[0], q1 = gp[1];
+                        gq[0] = q0.x; gq[1] = q0.y; gq[2] = q0.z; gq[3] = q0.w;
+                        gq[4] = q1.x; gq[5] = q1.y; gq[6] = q1.z; gq[7] = q1.w;
+                        if (GS > 8) {
+                            const float4 q2 = gp[2];
+                            gq[8] = q2.x; gq[9] = q2.y; gq[10] = q2.z; gq[11] = q2.w;
+                        } else {
+                            gq[8] = gq[9] = gq[10] = gq[11] = 0.f;
+                        }
+                    }
+                    Row<VEC, NV> pc, pe;
+                    read_staged_row<VEC, NV>(pc, ring, rslot * 2 + 0, D, lane);
+                    read_staged_row<VEC, NV>(pe, ring, rslot * 2 + 1, D, lane);
+                    const float g_z1 = gq[0], g_z2 = gq[1];
+                    const int e = __float_as_int(gq[2]);
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        const int d0 = dim_of<VEC>(lane, j);
+                        if (d0 < D) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                const int x = j * VEC + v;
+                                float gpd = g_z1;
+#pragma unroll
+                                for (int kk = 0; kk < INVPREF_MAX_ENVS; ++kk)
+                                    if (kk < K) gpd += gq[3 + kk] * sW[kk * D + d0 + v];
+                                gi.x[x] += gpd * pc.x[x];
+                                ge.x[x] += g_z2 * pe.x[x] * sE[e * D + d0 + v];
+                            }
+                        }
+                    }
+                    if (++rslot == RING) rslot = 0;
+                    if (++rgs == RING + 1) rgs = 0;
+                }
+            }
+            finish_row<VEC, NV, EPI>(a, row, (float)(end - beg), th_i, th_e, m_i, m_e, v_i, v_e, gi, ge, lane);
         }
     }
+    cp_async_wait<0>();
 }
 
 // Dense Adam over the rows that received no gradient this step.
@@ -410,10 +588,44 @@ int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stre
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 
+static bool use_ring(const Geometry& g, int epi) {
+    static const bool enabled = [] {
+        const char* e = getenv("INVPREF_RING");   // INVPREF_RING=0: register-only rows kernel (A/B runs)
+        return !(e && e[0] == '0');
+    }();
+    return enabled && g.NV * g.VEC <= 4 && (epi == EPI_ADAM || epi == EPI_EXPORT);
+}
+
 int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream_t stream) {
+    const bool stash = a.stash != nullptr;
+    if (use_ring(g, epi)) {
+        const size_t smem = ((size_t)((2 * g.K * g.D + 3) & ~3) + (size_t)GROUPS_PER_BLOCK * (RING + 1) * 12 +
+                             (size_t)RING * 2 * g.NV * g.VEC * BLOCK) * sizeof(float);
+        const int grid = grid_groups(a.plan.max_seg, 148 * 3);   // three CTAs per SM are resident: one wave
+        const int long_len = 2 * chunk_for(a.plan.B);
+#define LAUNCH(KERNEL)                                                                                           \
+    do {                                                                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        KERNEL<<<grid, BLOCK, smem, stream>>>(a, long_len);                                                      \
+    } while (0)
+#define CALL(V, N)                                                                                               \
+    do {                                                                                                         \
+        if (epi == EPI_ADAM && stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, true>));                      \
+        else if (epi == EPI_ADAM) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, false>));                         \
+        else if (stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, true>));                                  \
+        else LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, false>));                                            \
+    } while (0)
+        if (g.VEC == 4) { CALL(4, 1); }
+        else if (g.VEC == 2 && g.NV == 1) { CALL(2, 1); }
+        else if (g.VEC == 2) { CALL(2, 2); }
+        else { CALL(1, 4); }
+#undef CALL
+#undef LAUNCH
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+    }
     size_t smem = (size_t)2 * g.K * g.D * sizeof(float);
     int grid = grid_groups(a.plan.max_seg, 148 * 8);
-    const bool stash = a.stash != nullptr;
     if (epi == EPI_ADAM && stash) {
 #define CALL(V, N) bwd_rows_kernel<V, N, EPI_ADAM, true><<<grid, BLOCK, smem, stream>>>(a)
         INVPREF_DISPATCH_VN(g, CALL);

@@ -109,11 +109,18 @@ struct PlanSide {
     int32_t* chunk_desc;  // [max_chunks*4] (seg, begin, end, unused)
     int32_t* seg_desc;    // [S*4] (row, begin, perm[begin], partner[begin]): everything a kernel needs to request
                           //       a segment's rows and its first interaction with ONE 16-byte load
+    int32_t* range_start; // [R+1] cost-balanced contiguous segment ranges: range r = segments
+                          //       [range_start[r], range_start[r+1]); R = counters[3] = plan_ranges(B)
     uint32_t* touched;    // [ceil(rows/32)] bitmap of rows that have a segment
     int64_t max_seg, max_chunks, rows, B;
 };
 
 inline int64_t plan_max_seg(int64_t B, int64_t rows) { return B < rows ? B : rows; }
+// Work ranges of the ring rows kernel: contiguous runs of segments of about equal cost (PLAN_CSEG per segment
+// + 1 per interaction), a few dozen interactions each; a group takes ranges g, g + G, ... so that whatever the
+// cost model misses averages out.  The count depends on the batch size only.
+constexpr int PLAN_CSEG = 2;
+inline int64_t plan_ranges(int64_t B) { int64_t r = B / 64; return r < 1 ? 1 : (r > 65536 ? 65536 : r); }
 // Upper bound on the chunk count of a batch of AT MOST B interactions (monotonic in B, so a workspace sized
 // for the largest batch also fits every shorter one): chunks <= 1.5 * B' / chunk_for(B') for any B' <= B.
 inline int64_t plan_max_chunks(int64_t B) {
@@ -131,6 +138,7 @@ inline size_t plan_side_bytes(int64_t B, int64_t rows) {
     n += align_up((size_t)(S + 1) * 4) * 2;
     n += align_up((size_t)plan_max_chunks(B) * 16);
     n += align_up((size_t)S * 16);
+    n += align_up((size_t)(plan_ranges(B) + 1) * 4);
     n += align_up((size_t)((rows + 31) / 32) * 4);
     return n;
 }
@@ -153,6 +161,7 @@ inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
     p.seg_chunk = (int32_t*)c;  c += align_up((size_t)(S + 1) * 4);
     p.chunk_desc = (int32_t*)c; c += align_up((size_t)p.max_chunks * 16);
     p.seg_desc = (int32_t*)c;   c += align_up((size_t)S * 16);
+    p.range_start = (int32_t*)c; c += align_up((size_t)(plan_ranges(B) + 1) * 4);
     p.touched = (uint32_t*)c;
     return p;
 }

@@ -93,10 +93,29 @@ __global__ void write_chunks_kernel(PlanSide p, int chunk, int has_partner) {
     }
 }
 
+// Cost prefix of the segments before s: strictly increasing in s (a long segment, pre-reduced by the chunks
+// kernels, counts len - ceil(len / chunk) * chunk / 2 > 0 of its interactions).
+__device__ __forceinline__ int64_t seg_cost(const PlanSide& p, int64_t s, int half_chunk) {
+    return (int64_t)PLAN_CSEG * s + p.seg_off[s] - (int64_t)half_chunk * p.seg_chunk[s];
+}
+
+// range_start[r] = smallest s in [0, n_seg] with seg_cost(s) * R >= r * seg_cost(n_seg), r = 0..R.
+// Thread s writes the r's that map to it: every r is written exactly once.
+__global__ void write_ranges_kernel(PlanSide p, int half_chunk, int n_ranges) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int32_t n_seg = p.counters[0];
+    if (s == 0) { p.counters[3] = n_ranges; p.range_start[0] = 0; }
+    if (s < 1 || s > n_seg) return;
+    const int64_t total = seg_cost(p, n_seg, half_chunk);
+    const int64_t lo = seg_cost(p, s - 1, half_chunk) * n_ranges / total + 1;
+    const int64_t hi = seg_cost(p, s, half_chunk) * n_ranges / total;
+    for (int64_t r = lo; r <= hi; ++r) p.range_start[r] = (int32_t)s;
+}
+
 __global__ void empty_plan_kernel(PlanSide p) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        p.counters[0] = 0; p.counters[1] = 0;
-        p.seg_off[0] = 0; p.seg_chunk[0] = 0;
+        p.counters[0] = 0; p.counters[1] = 0; p.counters[3] = 0;
+        p.seg_off[0] = 0; p.seg_chunk[0] = 0; p.range_start[0] = 0;
     }
 }
 
@@ -179,7 +198,8 @@ int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_
     cub::DeviceScan::ExclusiveSum(t.cub_tmp, cb, p.seg_chunk, p.seg_chunk, (int)(p.max_seg + 1), stream);
     write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p, chunk_for(B),
                                                                                        other_ids != nullptr);
-    count_launch(5 + 6);   // 5 of ours + CUB's (radix passes, 2 scans; approximate)
+    write_ranges_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B) / 2, (int)plan_ranges(B));
+    count_launch(6 + 6);   // 6 of ours + CUB's (radix passes, 2 scans; approximate)
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 
