@@ -97,8 +97,7 @@ template <int VEC, int NV, int EPI>
 __device__ __forceinline__ void finish_row(const BwdSideArgs& a, int64_t row, float cnt, Row<VEC, NV>& th_i,
                                            Row<VEC, NV>& th_e, Row<VEC, NV>& m_i, Row<VEC, NV>& m_e,
                                            Row<VEC, NV>& v_i, Row<VEC, NV>& v_e, Row<VEC, NV>& gi, Row<VEC, NV>& ge,
-                                           int lane) {
-    const int D = a.D;
+                                           int lane, int D) {
     if (EPI == EPI_ADAM || EPI == EPI_EXPORT) {
 #pragma unroll
         for (int x = 0; x < NV * VEC; ++x) {
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
         } else {
             accumulate_range<VEC, NV, STASH>(a, sE, sW, beg, end, lane, gi.x, ge.x);
         }
-        finish_row<VEC, NV, EPI>(a, row, (float)(end - beg), th_i, th_e, m_i, m_e, v_i, v_e, gi, ge, lane);
+        finish_row<VEC, NV, EPI>(a, row, (float)(end - beg), th_i, th_e, m_i, m_e, v_i, v_e, gi, ge, lane, D);
     }
 }
 
@@ -211,10 +210,12 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
 //  * per segment the arithmetic is accumulate_range's / finish_row's, value for value and in the same order.
 constexpr int RING = 4;
 
-template <int VEC, int NV, int EPI, bool STASH>
+// KX > 0: D = 16 * VEC * NV and K = KX are compile-time constants (every bounds guard folds away, row offsets are
+// shifts); KX = 0: any D, K.
+template <int VEC, int NV, int EPI, bool STASH, int KX>
 __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, int long_len) {
     extern __shared__ __align__(16) float smem[];
-    const int D = a.D, K = a.K, GS = a.GS, KD = a.K * a.D;
+    const int D = KX ? GROUP * VEC * NV : a.D, K = KX ? KX : a.K, GS = KX ? (KX <= 5 ? 8 : 12) : a.GS, KD = K * D;
     float* sE = smem;
     float* sW = smem + KD;
     float* sG = smem + ((2 * KD + 3) & ~3);                    // [groups][RING + 1][12] g-packs
@@ -343,15 +344,24 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
                     for (int j = 0; j < NV; ++j) {
                         const int d0 = dim_of<VEC>(lane, j);
                         if (d0 < D) {
+                            float ee[VEC], gpd[VEC];
+                            ldv<VEC>(sE + e * D + d0, ee);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) gpd[v] = g_z1;
+#pragma unroll
+                            for (int kk = 0; kk < (KX ? KX : INVPREF_MAX_ENVS); ++kk) {
+                                if (kk < K) {
+                                    float wk[VEC];
+                                    ldv<VEC>(sW + kk * D + d0, wk);
+#pragma unroll
+                                    for (int v = 0; v < VEC; ++v) gpd[v] += gq[3 + kk] * wk[v];
+                                }
+                            }
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) {
                                 const int x = j * VEC + v;
-                                float gpd = g_z1;
-#pragma unroll
-                                for (int kk = 0; kk < INVPREF_MAX_ENVS; ++kk)
-                                    if (kk < K) gpd += gq[3 + kk] * sW[kk * D + d0 + v];
-                                gi.x[x] += gpd * pc.x[x];
-                                ge.x[x] += g_z2 * pe.x[x] * sE[e * D + d0 + v];
+                                gi.x[x] += gpd[v] * pc.x[x];
+                                ge.x[x] += g_z2 * pe.x[x] * ee[v];
                             }
                         }
                     }
@@ -359,7 +369,7 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
                     if (++rgs == RING + 1) rgs = 0;
                 }
             }
-            finish_row<VEC, NV, EPI>(a, row, (float)(end - beg), th_i, th_e, m_i, m_e, v_i, v_e, gi, ge, lane);
+            finish_row<VEC, NV, EPI>(a, row, (float)(end - beg), th_i, th_e, m_i, m_e, v_i, v_e, gi, ge, lane, D);
         }
     }
     cp_async_wait<0>();
@@ -608,17 +618,20 @@ int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream
         if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         KERNEL<<<grid, BLOCK, smem, stream>>>(a, long_len);                                                      \
     } while (0)
-#define CALL(V, N)                                                                                               \
+#define CALL(V, N, KX_)                                                                                          \
     do {                                                                                                         \
-        if (epi == EPI_ADAM && stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, true>));                      \
-        else if (epi == EPI_ADAM) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, false>));                         \
-        else if (stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, true>));                                  \
-        else LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, false>));                                            \
+        if (epi == EPI_ADAM && stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, true, KX_>));                 \
+        else if (epi == EPI_ADAM) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, false, KX_>));                    \
+        else if (stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, true, KX_>));                             \
+        else LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, false, KX_>));                                       \
     } while (0)
-        if (g.VEC == 4) { CALL(4, 1); }
-        else if (g.VEC == 2 && g.NV == 1) { CALL(2, 1); }
-        else if (g.VEC == 2) { CALL(2, 2); }
-        else { CALL(1, 4); }
+        if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 2) { CALL(4, 1, 2); }         // exact: D = 64, K = KT
+        else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 4) { CALL(4, 1, 4); }
+        else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 6) { CALL(4, 1, 6); }
+        else if (g.VEC == 4) { CALL(4, 1, 0); }
+        else if (g.VEC == 2 && g.NV == 1) { CALL(2, 1, 0); }
+        else if (g.VEC == 2) { CALL(2, 2, 0); }
+        else { CALL(1, 4, 0); }
 #undef CALL
 #undef LAUNCH
         count_launch();

@@ -23,12 +23,14 @@ namespace {
 // CL_STAGES-1 iterations before they are read.
 template <int VEC, int NV> struct ClStages { static constexpr int value = (VEC * NV <= 8) ? 3 : 2; };
 
-template <int VEC, int NV, int KT>
-__global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_rows_smem) {
+// EXACT: D = 16 * VEC * NV and K = KT are compile-time constants (bounds guards fold away, row offsets are shifts).
+template <int VEC, int NV, int KT, bool EXACT>
+__global__ void __launch_bounds__(BLOCK, (VEC * NV <= 4 && KT <= 4) ? 4 : 1) cluster_kernel(ClusterArgs a,
+                                                                                            int eps_rows_smem) {
     extern __shared__ __align__(16) float smem[];
     constexpr int RV = VEC * NV, ST = ClStages<VEC, NV>::value;
     constexpr bool E_REG = KT * RV <= 32;      // this lane's slice of E lives in registers for the whole kernel
-    const int D = a.D, K = a.K, KD = K * D;
+    const int D = EXACT ? GROUP * VEC * NV : a.D, K = EXACT ? KT : a.K, KD = K * D;
     float* sE = smem;                                        // [K*D]
     float* sEps = smem + ((KD + 3) & ~3);                    // [eps_rows_smem * K]
     float* ring = sEps + ((eps_rows_smem * K + 3) & ~3);     // [ST][4 rows][NV][BLOCK][VEC]
@@ -74,6 +76,20 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_r
     int uq = 0, iq = 0, uq2 = 0, iq2 = 0;
     if (n0 + (ST - 1) * stride < a.B) { uq = users_lo[2 * (n0 + (ST - 1) * stride)]; iq = items_lo[2 * (n0 + (ST - 1) * stride)]; }
     if (n0 + ST * stride < a.B) { uq2 = users_lo[2 * (n0 + ST * stride)]; iq2 = items_lo[2 * (n0 + ST * stride)]; }
+    // per-sample scalars one iteration ahead, in ONE register spread over lanes 0..2 (score, low words of
+    // perm_idx and of the old env), broadcast with shuffles when used
+    const int gbase = tid & 16;
+    const bool has_p = a.perm_idx != nullptr, has_d = a.diff != nullptr;
+    auto load_scalars = [&](int64_t n) -> int {
+        const int32_t* p = reinterpret_cast<const int32_t*>(a.scores + n);
+        bool on = lane == 0;
+        if (lane == 1 && has_p) { p = reinterpret_cast<const int32_t*>(a.perm_idx + n); on = true; }
+        if (lane == 2 && has_d) { p = reinterpret_cast<const int32_t*>(a.old_envs + n); on = true; }
+        int v = 0;
+        if (on) v = *p;
+        return v;
+    };
+    int sc = (n0 < a.B) ? load_scalars(n0) : 0;
     unsigned cnt[KT], ndiff = 0;   // lane 0: this group's histogram and diff count
 #pragma unroll
     for (int k = 0; k < KT; ++k) cnt[k] = 0u;
@@ -86,9 +102,10 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_r
         cp_async_commit();
         uq = uq2; iq = iq2;
         if (n + (ST + 1) * stride < a.B) { uq2 = users_lo[2 * (n + (ST + 1) * stride)]; iq2 = items_lo[2 * (n + (ST + 1) * stride)]; }
-        const float y = a.scores[n];
-        const int64_t pidx = (a.perm_idx != nullptr) ? a.perm_idx[n] : 0;
-        const int64_t old = (a.diff != nullptr) ? a.old_envs[n] : 0;
+        const float y = __int_as_float(__shfl_sync(gmask, sc, gbase));
+        const int pidx = __shfl_sync(gmask, sc, gbase + 1);
+        const int old = __shfl_sync(gmask, sc, gbase + 2);
+        if (n + stride < a.B) sc = load_scalars(n + stride);
         cp_async_wait<ST - 1>();
         Row<VEC, NV> ra, rc, rue, rie;
         read_staged_row<VEC, NV>(ra, ring, slot * 4 + 0, D, lane);
@@ -133,7 +150,7 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_r
             d = r * r;
         }
         if (arg < K) {
-            if (a.perm_idx != nullptr) d = d + ((eps_rows_smem > 0 ? sEps : a.eps_table) + pidx * K)[arg];
+            if (has_p) d = d + ((eps_rows_smem > 0 ? sEps : a.eps_table) + (int64_t)pidx * K)[arg];
         } else {
             d = INFINITY;   // padding lanes never win (an all-inf row still resolves to the lowest k)
         }
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(BLOCK) cluster_kernel(ClusterArgs a, int eps_r
             a.new_envs[n] = (int64_t)arg;
 #pragma unroll
             for (int k = 0; k < KT; ++k) cnt[k] += (arg == k) ? 1u : 0u;
-            if (a.diff != nullptr && old != (int64_t)arg) ++ndiff;
+            if (has_d && old != arg) ++ndiff;
         }
         if (++slot == ST) slot = 0;
     }
@@ -216,14 +233,23 @@ int launch_cluster(const Geometry& g, const ClusterArgs& a, cudaStream_t stream)
                          (size_t)stages * 4 * g.NV * g.VEC * BLOCK) * sizeof(float);
     int64_t need = (a.B + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
     int grid = (int)(need < 1 ? 1 : (need < 148 * 16 ? need : 148 * 16));
-#define CALL(V, N, KT_)                                                                                          \
+#define CALL_X(V, N, KT_, X)                                                                                     \
     do {                                                                                                         \
         if (smem > 48 * 1024)                                                                                    \
-            cudaFuncSetAttribute(cluster_kernel<V, N, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        cluster_kernel<V, N, KT_><<<grid, BLOCK, smem, stream>>>(a, eps_rows);                                   \
+            cudaFuncSetAttribute(cluster_kernel<V, N, KT_, X>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                 (int)smem);                                                                     \
+        cluster_kernel<V, N, KT_, X><<<grid, BLOCK, smem, stream>>>(a, eps_rows);                                \
     } while (0)
-    INVPREF_DISPATCH_GEOM(g, CALL);
+#define CALL(V, N, KT_) CALL_X(V, N, KT_, false)
+#define CALL_EXACT(V, N, KT_) CALL_X(V, N, KT_, true)
+    if (g.VEC == 4 && g.D == GROUP * 4 && g.K == g.KT) {
+        INVPREF_DISPATCH_K(4, 1, g.KT, CALL_EXACT);
+    } else {
+        INVPREF_DISPATCH_GEOM(g, CALL);
+    }
 #undef CALL
+#undef CALL_EXACT
+#undef CALL_X
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

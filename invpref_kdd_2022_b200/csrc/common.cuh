@@ -107,8 +107,9 @@ struct PlanSide {
     int32_t* seg_off;     // [S+1] offsets into perm
     int32_t* seg_chunk;   // [S+1] exclusive scan of per-segment chunk counts (0 for short segments)
     int32_t* chunk_desc;  // [max_chunks*4] (seg, begin, end, unused)
-    int32_t* seg_desc;    // [S*4] (row, begin, perm[begin], partner[begin]): everything a kernel needs to request
-                          //       a segment's rows and its first interaction with ONE 16-byte load
+    int32_t* seg_desc;    // [S*8] (row, begin, end, perm[begin]; partner[begin], perm[begin+1], partner[begin+1], -):
+                          //       everything a kernel needs to request a segment's rows and its first two
+                          //       interactions, in one 32-byte record
     int32_t* range_start; // [R+1] cost-balanced contiguous segment ranges: range r = segments
                           //       [range_start[r], range_start[r+1]); R = counters[3] = plan_ranges(B)
     uint32_t* touched;    // [ceil(rows/32)] bitmap of rows that have a segment
@@ -137,7 +138,7 @@ inline size_t plan_side_bytes(int64_t B, int64_t rows) {
     n += align_up((size_t)S * 4);
     n += align_up((size_t)(S + 1) * 4) * 2;
     n += align_up((size_t)plan_max_chunks(B) * 16);
-    n += align_up((size_t)S * 16);
+    n += align_up((size_t)S * 32);
     n += align_up((size_t)(plan_ranges(B) + 1) * 4);
     n += align_up((size_t)((rows + 31) / 32) * 4);
     return n;
@@ -160,7 +161,7 @@ inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
     p.seg_off = (int32_t*)c;    c += align_up((size_t)(S + 1) * 4);
     p.seg_chunk = (int32_t*)c;  c += align_up((size_t)(S + 1) * 4);
     p.chunk_desc = (int32_t*)c; c += align_up((size_t)p.max_chunks * 16);
-    p.seg_desc = (int32_t*)c;   c += align_up((size_t)S * 16);
+    p.seg_desc = (int32_t*)c;   c += align_up((size_t)S * 32);
     p.range_start = (int32_t*)c; c += align_up((size_t)(plan_ranges(B) + 1) * 4);
     p.touched = (uint32_t*)c;
     return p;

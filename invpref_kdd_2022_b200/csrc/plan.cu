@@ -84,7 +84,13 @@ __global__ void write_chunks_kernel(PlanSide p, int chunk, int has_partner) {
     if (s >= n_seg) return;
     int32_t c0 = p.seg_chunk[s], c1 = p.seg_chunk[s + 1];
     int32_t beg = p.seg_off[s], end = p.seg_off[s + 1];
-    reinterpret_cast<int4*>(p.seg_desc)[s] = make_int4(p.seg_row[s], beg, p.perm[beg], has_partner ? p.partner[beg] : 0);
+    {   // {row, begin, end, perm[begin]}, {partner[begin], perm[begin+1], partner[begin+1], -}
+        const bool two = beg + 1 < end;
+        int4* d = reinterpret_cast<int4*>(p.seg_desc) + 2 * s;
+        d[0] = make_int4(p.seg_row[s], beg, end, p.perm[beg]);
+        d[1] = make_int4(has_partner ? p.partner[beg] : 0, two ? p.perm[beg + 1] : 0,
+                         (two && has_partner) ? p.partner[beg + 1] : 0, 0);
+    }
     if (c1 == c0) return;
     for (int32_t c = c0; c < c1; ++c) {
         int32_t b = beg + (c - c0) * chunk;

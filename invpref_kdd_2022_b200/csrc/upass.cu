@@ -45,8 +45,7 @@ template <int VEC, int NV, int KT>
 __device__ __forceinline__ void inter_dots(const UserPassArgs& a, const float* __restrict__ sE,
                                            const float* __restrict__ sW, const Row<VEC, NV>& ra,
                                            const Row<VEC, NV>& rue, const Row<VEC, NV>& rc, const Row<VEC, NV>& rie,
-                                           int e, int lane, Inter<VEC, NV, KT>& q) {
-    const int D = a.side.D, K = a.side.K;
+                                           int e, int lane, Inter<VEC, NV, KT>& q, int D, int K) {
     q.z1 = 0.f; q.z2 = 0.f; q.sq = 0.f; q.ab = 0.f;
 #pragma unroll
     for (int kk = 0; kk < KT; ++kk) q.lg[kk] = 0.f;
@@ -88,8 +87,8 @@ __device__ __forceinline__ void inter_grads(const UserPassArgs& a, const LossCfg
                                             const float* __restrict__ sB, const Row<VEC, NV>& rc,
                                             const Row<VEC, NV>& rie, Inter<VEC, NV, KT>& q, int n, int e, float y,
                                             float w, int lane, unsigned gmask, float (&acc0)[NV * VEC],
-                                            float (&Q)[KT][NV * VEC], float (&acc_env)[NV * VEC], Running& st) {
-    const int D = a.side.D, K = a.side.K;
+                                            float (&Q)[KT][NV * VEC], float (&acc_env)[NV * VEC], Running& st,
+                                            int D, int K) {
     const float z1 = group_sum(q.z1, gmask);
     const float z2 = group_sum(q.z2, gmask);
     float lg[KT];
@@ -127,7 +126,8 @@ __device__ __forceinline__ void inter_grads(const UserPassArgs& a, const LossCfg
         }
     }
     if (lane == 0) {   // g-pack for the item pass: g_z1, g_z2, env, -alpha * g_logits
-        float* gp = a.gpack_out + (int64_t)n * a.side.GS;
+        const int GS = (K <= 5) ? 8 : 12;   // make_geometry
+        float* gp = a.gpack_out + (int64_t)n * GS;
         float out[12];
         out[0] = g_z1;
         out[1] = g_z2;
@@ -136,7 +136,7 @@ __device__ __forceinline__ void inter_grads(const UserPassArgs& a, const LossCfg
         for (int kk = 0; kk < 9; ++kk) out[3 + kk] = (kk < KT) ? a.neg_alpha * gl[kk < KT ? kk : 0] : 0.f;
         *reinterpret_cast<float4*>(gp) = make_float4(out[0], out[1], out[2], out[3]);
         *reinterpret_cast<float4*>(gp + 4) = make_float4(out[4], out[5], out[6], out[7]);
-        if (KT > 5 && a.side.GS > 8)
+        if (KT > 5 && GS > 8)
             *reinterpret_cast<float4*>(gp + 8) = make_float4(out[8], out[9], out[10], out[11]);
     }
 }
@@ -162,8 +162,8 @@ __device__ __forceinline__ void fused_range(const UserPassArgs& a, const LossCfg
         load_row<VEC, NV>(rc, a.side.partner_inv, it, D, lane);
         load_row<VEC, NV>(rie, a.side.partner_env, it, D, lane);
         Inter<VEC, NV, KT> q;
-        inter_dots<VEC, NV, KT>(a, sE, sW, ra, rue, rc, rie, e, lane, q);
-        inter_grads<VEC, NV, KT>(a, cfg, myDE, sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, acc_env, st);
+        inter_dots<VEC, NV, KT>(a, sE, sW, ra, rue, rc, rie, e, lane, q, D, a.side.K);
+        inter_grads<VEC, NV, KT>(a, cfg, myDE, sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, acc_env, st, D, a.side.K);
     }
 }
 
@@ -172,8 +172,7 @@ template <int VEC, int NV, int KT>
 __device__ __forceinline__ void finish_range(const UserPassArgs& a, const float* __restrict__ sW,
                                              float* __restrict__ myDW, const Row<VEC, NV>& ra, int lane,
                                              const float (&acc0)[NV * VEC], const float (&Q)[KT][NV * VEC],
-                                             Row<VEC, NV>& gi) {
-    const int D = a.side.D, K = a.side.K;
+                                             Row<VEC, NV>& gi, int D, int K) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int d0 = dim_of<VEC>(lane, j);
@@ -315,7 +314,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_chunks_kernel(UserPassArgs a, 
             for (int k = 0; k < KT; ++k) Q[k][x] = 0.f;
         }
         fused_range<VEC, NV, KT>(a, cfg, s.sE, s.sW, myDE, s.sB, ra, rue, desc.y, desc.z, lane, gmask, acc0, Q, ge.x, st);
-        finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi);
+        finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, a.side.K);
         store_row<VEC, NV>(gi, a.side.chunk_part, (int64_t)c * 2, D, lane);
         store_row<VEC, NV>(ge, a.side.chunk_part, (int64_t)c * 2 + 1, D, lane);
     }
@@ -405,7 +404,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
                 for (int k = 0; k < KT; ++k) Q[k][x] = 0.f;
             }
             fused_range<VEC, NV, KT>(a, cfg, s.sE, s.sW, myDE, s.sB, ra, rue, beg, end, lane, gmask, acc0, Q, ge.x, st);
-            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi);
+            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, a.side.K);
         }
         // the user rows' own L1/L2 terms (models.py:469-482): every occurrence in the batch counts
         const float cnt = (float)(end - beg);
@@ -454,39 +453,69 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
 //
 // ncu on the register-only kernel above (round 1): 30 % of the warp samples wait on the long scoreboard -- the
 // (m, v, theta) rows of the segment behind a chain of dependent index loads, and the item rows of each
-// interaction -- with only 16 warps per SM to hide it.  Here the next segment's eight rows (theta, m, v of both
-// user tables + the two item rows of its first interaction) are copied global -> shared with cp.async while
-// the current segment is processed: no register is held while they are in flight, every lane copies exactly
-// the slice it later reads (no barrier, cp.async.wait_group only), and the item rows of interaction k+1 of a
-// multi-interaction segment are requested while interaction k is computed.  Index chain: one 16-byte segment
-// descriptor (row, begin, perm[begin], partner[begin]) loaded two segments ahead; the first interaction's
-// scalars (env, score, weight) and the row's last_step are loaded one segment ahead into ONE register spread
-// over lanes 8..11 and broadcast with shuffles.  The arithmetic is the register-only kernel's, value for value.
-constexpr int UP_SLOTS = 8;   // th_i, th_e, m_i, m_e, v_i, v_e, first item inv, first item env
+// interaction -- with only 16 warps per SM to hide it.  Here EVERYTHING a group will need is copied global ->
+// shared with cp.async one step before it is used, so that no register (and no register scoreboard: ptxas made
+// the inner loop's first branch wait for every load issued at the top of the segment, 35 % of the samples in
+// an intermediate version that kept index loads in registers) is tied up while data is in flight:
+//   * group A_{m+1}, requested at the top of segment m: the eight rows of the next segment (theta, m, v of both
+//     user tables + the two item rows of its first interaction; every lane copies exactly the slice it later
+//     reads), the scalars of its first interaction (env, score, weight) and the row's last_step, and the
+//     32-byte descriptor {row, begin, end, perm/partner[begin], perm/partner[begin+1]} of the segment after it;
+//   * group G_i, requested while interaction i is computed: the item rows and scalars of interaction i+1 and
+//     the indices of interaction i+2.
+// Row slices are read back by the lane that copied them; the few words shared by the group (descriptors,
+// scalars, indices) after cp.async.wait_group + __syncwarp.  The arithmetic is the register-only kernel's,
+// value for value.
+constexpr int UP_SLOTS = 8;    // per stage: th_i, th_e, m_i, m_e, v_i, v_e, first item inv, first item env
+// per-group metadata (32-bit words)
+constexpr int UM_DESC = 0;     // [4][8]  descriptor ring, segment ordinal & 3 (ordinal o is read at the top of
+                               //         segments o-1 and o; o+3 is requested during segment o: four slots)
+constexpr int UM_SEGS = 32;    // [2][4]  {env, score, weight, last_step} of a segment's first interaction, by stage
+constexpr int UM_ITS = 40;     // [2][4]  {env, score, weight, -} of interaction i, slot i & 1
+constexpr int UM_ITI = 48;     // [2][2]  {perm, partner} of interaction i, slot i & 1
+constexpr int UM_WORDS = 56;
 
-template <int VEC, int NV, int KT, int EPI, bool LAZY>
+// EXACT: D = 16 * VEC * NV and K = KT are compile-time constants (bounds guards fold away, row offsets are shifts).
+template <int VEC, int NV, int KT, int EPI, bool LAZY, bool EXACT>
 __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArgs a, int long_len) {
     extern __shared__ __align__(16) float smem[];
-    const int D = a.side.D, KD = a.side.K * a.side.D;
+    const int D = EXACT ? GROUP * VEC * NV : a.side.D, K = EXACT ? KT : a.side.K, KD = K * D;
     const Smem s = carve_smem(smem, KD);
     float* ring = smem + (((4 + 2 * GROUPS_PER_BLOCK) * KD + INVPREF_MAX_ENVS + 3) & ~3);   // [2][8][NV][BLOCK][VEC]
+    int32_t* meta = reinterpret_cast<int32_t*>(ring + (size_t)2 * UP_SLOTS * NV * VEC * BLOCK) +
+                    (threadIdx.x >> 4) * UM_WORDS;                                          // this group's words
     Running st;
     stage(a, s, KD, st);
     const int lane = threadIdx.x & (GROUP - 1);
     const unsigned gmask = group_mask();
-    const int gbase = threadIdx.x & 16;            // first lane of this group within the warp
     float* myDE = s.sDE + (threadIdx.x >> 4) * KD;
     float* myDW = s.sDW + (threadIdx.x >> 4) * KD;
-    const LossCfg cfg = {a.side.K, a.implicit, a.use_class_rw, a.use_rec_rw, a.c_inv, a.c_ea, a.c_env, a.invB};
+    const LossCfg cfg = {K, a.implicit, a.use_class_rw, a.use_rec_rw, a.c_inv, a.c_ea, a.c_env, a.invB};
     const int n_seg = a.side.plan.counters[0];
     const int ng = gridDim.x * GROUPS_PER_BLOCK;
     const int s0 = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4);
-    const int4* __restrict__ seg_desc = reinterpret_cast<const int4*>(a.side.plan.seg_desc);
-    const int32_t* __restrict__ seg_off = a.side.plan.seg_off;
+    const int32_t* __restrict__ seg_desc = a.side.plan.seg_desc;
     const int32_t* __restrict__ perm = a.side.plan.perm;
     const int32_t* __restrict__ partner = a.side.plan.partner;
+    const bool has_w = a.weights != nullptr;
 
-    auto issue_segment = [&](int stg, int row, int pid) {
+    // descriptor of segment `seg` (ordinal `ord` of this group) -> ring slot ord & 3; lanes 0 and 1, 16 bytes each
+    auto request_desc = [&](int ord, int seg) {
+        if (seg < n_seg && lane < 2)
+            cp_async<16>(smem_addr(meta + UM_DESC + (ord & 3) * 8 + lane * 4), seg_desc + (int64_t)seg * 8 + lane * 4);
+    };
+    // env / score / weight of interaction n -> dst[0..2] (lanes 8, 9, 10)
+    auto request_scalars = [&](int32_t* dst, int n) {
+        if (lane == 8) cp_async<4>(smem_addr(dst + 0), reinterpret_cast<const int32_t*>(a.envs + n));   // low word
+        if (lane == 9) cp_async<4>(smem_addr(dst + 1), a.scores + n);
+        if (lane == 10) {
+            if (has_w) cp_async<4>(smem_addr(dst + 2), a.weights + n);
+            else dst[2] = __float_as_int(1.f);
+        }
+    };
+    // rows + first-interaction scalars + last_step of the segment described by dsc[] (shared memory) -> stage stg
+    auto request_segment = [&](int stg, const int32_t* dsc) {
+        const int row = dsc[0], n0 = dsc[3], p0 = dsc[4];
         stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 0, a.side.own_inv_in, row, D, lane);
         stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 1, a.side.own_env_in, row, D, lane);
         if (EPI == EPI_ADAM) {
@@ -495,61 +524,42 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
             stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 4, a.side.v_inv, row, D, lane);
             stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 5, a.side.v_env, row, D, lane);
         }
-        stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 6, a.side.partner_inv, pid, D, lane);
-        stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 7, a.side.partner_env, pid, D, lane);
-    };
-    // Scalars needed one step ahead, ONE 32-bit register spread over the lanes of the group and broadcast with
-    // shuffles when used: lane 8 env[n], 9 score[n], 10 weight[n], 11 last_step[row] (row >= 0), 12 perm[k2],
-    // 13 partner[k2] (k2 >= 0: sorted position of the interaction after n).  The address is picked with
-    // selects and loaded with one predicated instruction (per-lane branches here cost 15 % of the kernel: ncu).
-    const bool has_w = a.weights != nullptr;
-    auto load_scalars = [&](int n, int row, int k2) -> int {
-        const int32_t* p = reinterpret_cast<const int32_t*>(a.envs + n);   // low word of the int64 (0 <= env < K)
-        bool on = lane == 8;
-        if (lane == 9) { p = reinterpret_cast<const int32_t*>(a.scores + n); on = true; }
-        if (lane == 10 && has_w) { p = reinterpret_cast<const int32_t*>(a.weights + n); on = true; }
-        if (LAZY && lane == 11 && row >= 0) { p = a.side.last_step + row; on = true; }
-        if (lane == 12 && k2 >= 0) { p = perm + k2; on = true; }
-        if (lane == 13 && k2 >= 0) { p = partner + k2; on = true; }
-        int v = (lane == 10) ? __float_as_int(1.f) : 0;
-        if (on) v = *p;
-        return v;
+        stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 6, a.side.partner_inv, p0, D, lane);
+        stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 7, a.side.partner_env, p0, D, lane);
+        request_scalars(meta + UM_SEGS + stg * 4, n0);
+        if (LAZY && lane == 11) cp_async<4>(smem_addr(meta + UM_SEGS + stg * 4 + 3), a.side.last_step + row);
     };
 
-    // cur = (d0, end0, sc0); next = (d1, end1): descriptors are loaded two segments ahead
-    int4 d0 = make_int4(0, 0, 0, 0), d1 = make_int4(0, 0, 0, 0);
-    int end0 = 0, end1 = 0, sc0 = 0;
-    if (s0 < n_seg) {
-        d0 = seg_desc[s0];
-        end0 = seg_off[s0 + 1];
-        issue_segment(0, d0.x, d0.w);
-        sc0 = load_scalars(d0.z, d0.x, d0.y + 1 < end0 ? d0.y + 1 : -1);
-    }
+    // prologue: descriptors of the first two segments (the only exposed latency), then group A_0
+    request_desc(0, s0);
+    request_desc(1, s0 + ng);
     cp_async_commit();
-    if (s0 + ng < n_seg) { d1 = seg_desc[s0 + ng]; end1 = seg_off[s0 + ng + 1]; }
-    int stg = 0;
-    for (int sgm = s0; sgm < n_seg; sgm += ng, stg ^= 1) {
-        int sc1 = 0;
-        if (sgm + ng < n_seg) {
-            issue_segment(stg ^ 1, d1.x, d1.w);
-            sc1 = load_scalars(d1.z, d1.x, d1.y + 1 < end1 ? d1.y + 1 : -1);
-        }
-        cp_async_commit();
-        int4 d2 = make_int4(0, 0, 0, 0);
-        int end2 = 0;
-        if (sgm + 2 * ng < n_seg) { d2 = seg_desc[sgm + 2 * ng]; end2 = seg_off[sgm + 2 * ng + 1]; }
+    cp_async_wait<0>();
+    __syncwarp(gmask);
+    if (s0 < n_seg) request_segment(0, meta + UM_DESC);
+    request_desc(2, s0 + 2 * ng);
+    cp_async_commit();
 
-        const int64_t row = d0.x;
-        const int beg = d0.y, end = end0;
-        int n = d0.z;
-        int e = __shfl_sync(gmask, sc0, gbase + 8);
-        float y = __int_as_float(__shfl_sync(gmask, sc0, gbase + 9));
-        float w = __int_as_float(__shfl_sync(gmask, sc0, gbase + 10));
-        const int last = LAZY ? __shfl_sync(gmask, sc0, gbase + 11) : 0;
-        int n_nx = __shfl_sync(gmask, sc0, gbase + 12), it_nx = __shfl_sync(gmask, sc0, gbase + 13);
+    int ord = 0;
+    for (int sgm = s0; sgm < n_seg; sgm += ng, ++ord) {
+        const int stg = ord & 1;
+        cp_async_wait<0>();      // A_ord: this segment's rows and scalars, the next segment's descriptor
+        __syncwarp(gmask);
+        if (sgm + ng < n_seg) request_segment(stg ^ 1, meta + UM_DESC + ((ord + 1) & 3) * 8);
+        request_desc(ord + 3, sgm + 3 * ng);     // its slot held this group's previous segment
+        cp_async_commit();       // A_{ord+1}
+
+        const int4 dA = *reinterpret_cast<const int4*>(meta + UM_DESC + (ord & 3) * 8);       // row, begin, end, n0
+        const int4 dB = *reinterpret_cast<const int4*>(meta + UM_DESC + (ord & 3) * 8 + 4);   // p0, n1, p1, -
+        const int4 sS = *reinterpret_cast<const int4*>(meta + UM_SEGS + stg * 4);
+        const int64_t row = dA.x;
+        const int beg = dA.y, end = dA.z;
+        int n = dA.w, n_a = dB.y, it_a = dB.z;     // this interaction's batch position; indices of the next one
+        int e = sS.x;
+        float y = __int_as_float(sS.y), w = __int_as_float(sS.z);
+        const int last = sS.w;
         const bool is_long = end - beg > long_len;
 
-        cp_async_wait<1>();   // everything but the group committed above has landed
         Row<VEC, NV> ra, rue, gi, ge;
         Row<VEC, NV> m_i, m_e, v_i, v_e;
         read_staged_row<VEC, NV>(ra, ring, stg * UP_SLOTS + 0, D, lane);
@@ -590,34 +600,39 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
                 for (int k = 0; k < KT; ++k) Q[k][x] = 0.f;
             }
             for (int k = beg; k < end; ++k) {
-                if (k > beg) cp_async_wait<0>();
+                const int par = (k - beg) & 1;
+                if (k > beg) {
+                    cp_async_wait<0>();      // G_{i-1}: this interaction's rows and scalars, the next one's indices
+                    __syncwarp(gmask);
+                    const int4 sI = *reinterpret_cast<const int4*>(meta + UM_ITS + par * 4);
+                    e = sI.x; y = __int_as_float(sI.y); w = __int_as_float(sI.z);
+                    if (k + 1 < end) {
+                        const int2 ix = *reinterpret_cast<const int2*>(meta + UM_ITI + (par ^ 1) * 2);
+                        n_a = ix.x; it_a = ix.y;
+                    }
+                }
                 Row<VEC, NV> rc, rie;
                 read_staged_row<VEC, NV>(rc, ring, stg * UP_SLOTS + 6, D, lane);
                 read_staged_row<VEC, NV>(rie, ring, stg * UP_SLOTS + 7, D, lane);
                 Inter<VEC, NV, KT> q;
-                inter_dots<VEC, NV, KT>(a, s.sE, s.sW, ra, rue, rc, rie, e, lane, q);
-                int sck = 0, n_k1 = 0;
+                inter_dots<VEC, NV, KT>(a, s.sE, s.sW, ra, rue, rc, rie, e, lane, q, D, K);
                 if (k + 1 < end) {
-                    // the item slots were read into registers (the sums below depend on every element): request
-                    // interaction k+1's rows into them, its scalars into a register, and k+2's indices
+                    // the item slots are in registers (the sums below depend on every element): request
+                    // interaction i+1's rows into them, its scalars, and the indices of interaction i+2
                     asm volatile("" ::"f"(q.z1), "f"(q.z2) : "memory");
-                    stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 6, a.side.partner_inv, it_nx, D, lane);
-                    stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 7, a.side.partner_env, it_nx, D, lane);
-                    cp_async_commit();
-                    sck = load_scalars(n_nx, -1, k + 2 < end ? k + 2 : -1);
-                    n_k1 = n_nx;
+                    stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 6, a.side.partner_inv, it_a, D, lane);
+                    stage_row_async<VEC, NV>(ring, stg * UP_SLOTS + 7, a.side.partner_env, it_a, D, lane);
+                    request_scalars(meta + UM_ITS + (par ^ 1) * 4, n_a);
+                    if (k + 2 < end) {
+                        if (lane == 12) cp_async<4>(smem_addr(meta + UM_ITI + par * 2 + 0), perm + k + 2);
+                        if (lane == 13) cp_async<4>(smem_addr(meta + UM_ITI + par * 2 + 1), partner + k + 2);
+                    }
+                    cp_async_commit();       // G_i
                 }
-                inter_grads<VEC, NV, KT>(a, cfg, myDE, s.sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, ge.x, st);
-                if (k + 1 < end) {
-                    n = n_k1;
-                    e = __shfl_sync(gmask, sck, gbase + 8);
-                    y = __int_as_float(__shfl_sync(gmask, sck, gbase + 9));
-                    w = __int_as_float(__shfl_sync(gmask, sck, gbase + 10));
-                    n_nx = __shfl_sync(gmask, sck, gbase + 12);
-                    it_nx = __shfl_sync(gmask, sck, gbase + 13);
-                }
+                inter_grads<VEC, NV, KT>(a, cfg, myDE, s.sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, ge.x, st, D, K);
+                n = n_a;
             }
-            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi);
+            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, K);
         }
         // the user rows' own L1/L2 terms (models.py:469-482): every occurrence in the batch counts
         const float cnt = (float)(end - beg);
@@ -653,14 +668,14 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
             store_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
             if (LAZY && lane == 0) a.side.last_step[row] = a.side.step;
         }
-        d0 = d1; end0 = end1; sc0 = sc1;
-        d1 = d2; end1 = end2;
     }
     cp_async_wait<0>();
     write_partials(a, s, KD, st, blockIdx.x);
 }
 
-inline size_t upass_ring_bytes(const Geometry& g) { return (size_t)2 * UP_SLOTS * g.NV * g.VEC * BLOCK * sizeof(float); }
+inline size_t upass_ring_bytes(const Geometry& g) {   // staged rows + per-group metadata
+    return (size_t)2 * UP_SLOTS * g.NV * g.VEC * BLOCK * sizeof(float) + (size_t)GROUPS_PER_BLOCK * UM_WORDS * 4;
+}
 inline bool upass_staged(const Geometry& g) {
     static const bool enabled = [] {
         const char* e = getenv("INVPREF_STAGED");   // INVPREF_STAGED=0: register-only rows kernel (A/B runs)
@@ -720,18 +735,23 @@ int launch_upass_rows(const Geometry& g, const UserPassArgs& a, int epi, int gri
         cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
         KERNEL<<<grid, BLOCK, smem, stream>>>(a, long_len);                                                      \
     } while (0)
-#define CALL(V, N, KT_)                                                                                          \
+#define CALL_X(V, N, KT_, X)                                                                                     \
     do {                                                                                                         \
-        if (lazy) LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_ADAM, true>));                                 \
-        else if (epi == EPI_ADAM) LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_ADAM, false>));                \
-        else LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_EXPORT, false>));                                   \
+        if (lazy) LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_ADAM, true, X>));                              \
+        else if (epi == EPI_ADAM) LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_ADAM, false, X>));             \
+        else LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_EXPORT, false, X>));                                \
     } while (0)
+#define CALL(V, N, KT_) CALL_X(V, N, KT_, false)
+#define CALL_EXACT(V, N, KT_) CALL_X(V, N, KT_, true)
         const int _k = g.KT;
-        if (g.VEC == 4) { INVPREF_DISPATCH_K(4, 1, _k, CALL); }
+        if (g.VEC == 4 && g.D == GROUP * 4 && g.K == g.KT) { INVPREF_DISPATCH_K(4, 1, _k, CALL_EXACT); }
+        else if (g.VEC == 4) { INVPREF_DISPATCH_K(4, 1, _k, CALL); }
         else if (g.VEC == 2 && g.NV == 1) { INVPREF_DISPATCH_K(2, 1, _k, CALL); }
         else if (g.VEC == 2) { INVPREF_DISPATCH_K(2, 2, _k, CALL); }
         else { INVPREF_DISPATCH_K(1, 4, _k, CALL); }
 #undef CALL
+#undef CALL_EXACT
+#undef CALL_X
 #undef LAUNCH
         count_launch();
         return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
