@@ -195,6 +195,132 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
     }
 }
 
+constexpr int RING = 4;   // interactions in flight per group (ring kernels)
+
+// One interaction of the ring kernels: its g-pack (shared by the group) and the two partner-row slices this
+// lane staged, accumulated exactly as accumulate_range does.
+template <int VEC, int NV, int KX>
+__device__ __forceinline__ void ring_consume(const float* __restrict__ gslot, const float* __restrict__ ring,
+                                             int rslot, const float* __restrict__ sE, const float* __restrict__ sW,
+                                             int D, int K, int GS, int lane, Row<VEC, NV>& gi, Row<VEC, NV>& ge) {
+    float gq[12];
+    {
+        const float4* gp = reinterpret_cast<const float4*>(gslot);
+        const float4 q0 = gp[0], q1 = gp[1];
+        gq[0] = q0.x; gq[1] = q0.y; gq[2] = q0.z; gq[3] = q0.w;
+        gq[4] = q1.x; gq[5] = q1.y; gq[6] = q1.z; gq[7] = q1.w;
+        if (GS > 8) {
+            const float4 q2 = gp[2];
+            gq[8] = q2.x; gq[9] = q2.y; gq[10] = q2.z; gq[11] = q2.w;
+        } else {
+            gq[8] = gq[9] = gq[10] = gq[11] = 0.f;
+        }
+    }
+    Row<VEC, NV> pc, pe;
+    read_staged_row<VEC, NV>(pc, ring, rslot * 2 + 0, D, lane);
+    read_staged_row<VEC, NV>(pe, ring, rslot * 2 + 1, D, lane);
+    const float g_z1 = gq[0], g_z2 = gq[1];
+    const int e = __float_as_int(gq[2]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int d0 = dim_of<VEC>(lane, j);
+        if (d0 < D) {
+            float ee[VEC], gpd[VEC];
+            ldv<VEC>(sE + e * D + d0, ee);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) gpd[v] = g_z1;
+#pragma unroll
+            for (int kk = 0; kk < (KX ? KX : INVPREF_MAX_ENVS); ++kk) {
+                if (kk < K) {
+                    float wk[VEC];
+                    ldv<VEC>(sW + kk * D + d0, wk);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) gpd[v] += gq[3 + kk] * wk[v];
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int x = j * VEC + v;
+                gi.x[x] += gpd[v] * pc.x[x];
+                ge.x[x] += g_z2 * pe.x[x] * ee[v];
+            }
+        }
+    }
+}
+
+// Ring version of bwd_chunks_kernel: a group walks its chunks (c = g, g + G, ...) with the producer RING-1
+// interactions ahead, across chunk boundaries.  Chunks are spread over the CTAs first (a few hundred chunks of
+// a few hundred sequential interactions each: the critical path of the item pass).
+template <int VEC, int NV, bool STASH, int KX>
+__global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_ring_kernel(BwdSideArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int D = KX ? GROUP * VEC * NV : a.D, K = KX ? KX : a.K, GS = KX ? (KX <= 5 ? 8 : 12) : a.GS, KD = K * D;
+    float* sE = smem;
+    float* sW = smem + KD;
+    float* sG = smem + ((2 * KD + 3) & ~3);
+    float* ring = sG + GROUPS_PER_BLOCK * (RING + 1) * 12;
+    stage_EW(a, sE, sW);
+    const int lane = threadIdx.x & (GROUP - 1);
+    const unsigned gmask = group_mask();
+    float* myG = sG + (threadIdx.x >> 4) * (RING + 1) * 12;
+    const int n_chunks = a.plan.counters[1];
+    const int4* __restrict__ chunk_desc = reinterpret_cast<const int4*>(a.plan.chunk_desc);
+    const int32_t* __restrict__ perm = a.plan.perm;
+    const int32_t* __restrict__ partner = STASH ? a.plan.pseg : a.plan.partner;
+    const float* __restrict__ pinv = STASH ? a.stash : a.partner_inv;
+    const float* __restrict__ penv = STASH ? a.stash + D : a.partner_env;
+    constexpr int pmul = STASH ? 2 : 1;
+    const int G = gridDim.x * GROUPS_PER_BLOCK;
+    const int g = blockIdx.x + gridDim.x * (threadIdx.x >> 4);
+
+    // producer: chunk pc, position pk in [.., pend); the next chunk's bounds are loaded one chunk ahead
+    int pc = g, pk = 0, pend = 0, nk = 0, nend = 0, n_q = 0, pid_q = 0;
+    auto p_enter = [&]() {
+        pk = nk; pend = nend;
+        if (pc + G < n_chunks) { const int4 d = chunk_desc[pc + G]; nk = d.y; nend = d.z; }
+    };
+    if (pc < n_chunks) {
+        const int4 d = chunk_desc[pc];
+        nk = d.y; nend = d.z;
+        p_enter();
+        n_q = perm[pk]; pid_q = partner[pk];
+    }
+    int wslot = 0, wgs = 0;
+    auto produce = [&]() {
+        if (pc < n_chunks) {
+            stage_row_async<VEC, NV>(ring, wslot * 2 + 0, pinv, (int64_t)pid_q * pmul, D, lane);
+            stage_row_async<VEC, NV>(ring, wslot * 2 + 1, penv, (int64_t)pid_q * pmul, D, lane);
+            if (lane * 4 < GS) cp_async<16>(smem_addr(myG + wgs * 12 + lane * 4), a.gpack + (int64_t)n_q * GS + lane * 4);
+            if (++pk == pend) { pc += G; if (pc < n_chunks) p_enter(); }
+            if (pc < n_chunks) { n_q = perm[pk]; pid_q = partner[pk]; }
+        }
+        cp_async_commit();
+        if (++wslot == RING) wslot = 0;
+        if (++wgs == RING + 1) wgs = 0;
+    };
+#pragma unroll
+    for (int q = 0; q < RING - 1; ++q) produce();
+
+    int rslot = 0, rgs = 0;
+    for (int c = g; c < n_chunks; c += G) {
+        const int4 desc = chunk_desc[c];
+        Row<VEC, NV> gi, ge;
+#pragma unroll
+        for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
+        for (int k = desc.y; k < desc.z; ++k) {
+            produce();
+            cp_async_wait<RING - 1>();
+            __syncwarp(gmask);
+            ring_consume<VEC, NV, KX>(myG + rgs * 12, ring, rslot, sE, sW, D, K, GS, lane, gi, ge);
+            if (++rslot == RING) rslot = 0;
+            if (++rgs == RING + 1) rgs = 0;
+        }
+        store_row<VEC, NV>(gi, a.chunk_part, (int64_t)c * 2, D, lane);
+        store_row<VEC, NV>(ge, a.chunk_part, (int64_t)c * 2 + 1, D, lane);
+    }
+    cp_async_wait<0>();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Ring rows kernel (row slices of <= 16 bytes per lane, i.e. D <= 64; Adam / export epilogues).
 //
@@ -208,8 +334,6 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
 //    -- and copies the partner rows (each lane its own slice) and the g-pack of every interaction global ->
 //    shared with cp.async: no register is held while the data is in flight;
 //  * per segment the arithmetic is accumulate_range's / finish_row's, value for value and in the same order.
-constexpr int RING = 4;
-
 // KX > 0: D = 16 * VEC * NV and K = KX are compile-time constants (every bounds guard folds away, row offsets are
 // shifts); KX = 0: any D, K.
 template <int VEC, int NV, int EPI, bool STASH, int KX>
@@ -322,49 +446,7 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
                     produce();
                     cp_async_wait<RING - 1>();
                     __syncwarp(gmask);   // the g-pack was copied by lanes 0..2 of this group
-                    float gq[12];
-                    {
-                        const float4* gp = reinterpret_cast<const float4*>(myG + rgs * 12);
-                        const float4 q0 = gp[0], q1 = gp[1];
-                        gq[0] = q0.x; gq[1] = q0.y; gq[2] = q0.z; gq[3] = q0.w;
-                        gq[4] = q1.x; gq[5] = q1.y; gq[6] = q1.z; gq[7] = q1.w;
-                        if (GS > 8) {
-                            const float4 q2 = gp[2];
-                            gq[8] = q2.x; gq[9] = q2.y; gq[10] = q2.z; gq[11] = q2.w;
-                        } else {
-                            gq[8] = gq[9] = gq[10] = gq[11] = 0.f;
-                        }
-                    }
-                    Row<VEC, NV> pc, pe;
-                    read_staged_row<VEC, NV>(pc, ring, rslot * 2 + 0, D, lane);
-                    read_staged_row<VEC, NV>(pe, ring, rslot * 2 + 1, D, lane);
-                    const float g_z1 = gq[0], g_z2 = gq[1];
-                    const int e = __float_as_int(gq[2]);
-#pragma unroll
-                    for (int j = 0; j < NV; ++j) {
-                        const int d0 = dim_of<VEC>(lane, j);
-                        if (d0 < D) {
-                            float ee[VEC], gpd[VEC];
-                            ldv<VEC>(sE + e * D + d0, ee);
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) gpd[v] = g_z1;
-#pragma unroll
-                            for (int kk = 0; kk < (KX ? KX : INVPREF_MAX_ENVS); ++kk) {
-                                if (kk < K) {
-                                    float wk[VEC];
-                                    ldv<VEC>(sW + kk * D + d0, wk);
-#pragma unroll
-                                    for (int v = 0; v < VEC; ++v) gpd[v] += gq[3 + kk] * wk[v];
-                                }
-                            }
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) {
-                                const int x = j * VEC + v;
-                                gi.x[x] += gpd[v] * pc.x[x];
-                                ge.x[x] += g_z2 * pe.x[x] * ee[v];
-                            }
-                        }
-                    }
+                    ring_consume<VEC, NV, KX>(myG + rgs * 12, ring, rslot, sE, sW, D, K, GS, lane, gi, ge);
                     if (++rslot == RING) rslot = 0;
                     if (++rgs == RING + 1) rgs = 0;
                 }
@@ -582,10 +664,51 @@ inline int grid_groups(int64_t n, int max_blocks) {
 
 }  // namespace
 
+static bool ring_enabled() {
+    static const bool enabled = [] {
+        const char* e = getenv("INVPREF_RING");   // INVPREF_RING=0: register-only rows / chunks kernels (A/B runs)
+        return !(e && e[0] == '0');
+    }();
+    return enabled;
+}
+
+static size_t ring_smem(const Geometry& g) {
+    return ((size_t)((2 * g.K * g.D + 3) & ~3) + (size_t)GROUPS_PER_BLOCK * (RING + 1) * 12 +
+            (size_t)RING * 2 * g.NV * g.VEC * BLOCK) * sizeof(float);
+}
+
 int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream) {
+    const bool stash = a.stash != nullptr;
+    if (ring_enabled() && g.NV * g.VEC <= 4) {
+        const size_t smem = ring_smem(g);
+        // chunk c goes to CTA c % grid: one CTA per SM first, up to three
+        int64_t need = a.plan.max_chunks;
+        const int grid = (int)(need < 1 ? 1 : (need < 148 * 3 ? need : 148 * 3));
+#define LAUNCH(KERNEL)                                                                                           \
+    do {                                                                                                         \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        KERNEL<<<grid, BLOCK, smem, stream>>>(a);                                                                \
+    } while (0)
+#define CALL(V, N, KX_)                                                                                          \
+    do {                                                                                                         \
+        if (stash) LAUNCH((bwd_chunks_ring_kernel<V, N, true, KX_>));                                            \
+        else LAUNCH((bwd_chunks_ring_kernel<V, N, false, KX_>));                                                 \
+    } while (0)
+        if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 2) { CALL(4, 1, 2); }
+        else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 4) { CALL(4, 1, 4); }
+        else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 6) { CALL(4, 1, 6); }
+        else if (g.VEC == 4) { CALL(4, 1, 0); }
+        else if (g.VEC == 2 && g.NV == 1) { CALL(2, 1, 0); }
+        else if (g.VEC == 2) { CALL(2, 2, 0); }
+        else { CALL(1, 4, 0); }
+#undef CALL
+#undef LAUNCH
+        count_launch();
+        return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+    }
     size_t smem = (size_t)2 * g.K * g.D * sizeof(float);
     int grid = grid_groups(a.plan.max_chunks, 148 * 8);
-    if (a.stash != nullptr) {
+    if (stash) {
 #define CALL(V, N) bwd_chunks_kernel<V, N, true><<<grid, BLOCK, smem, stream>>>(a)
         INVPREF_DISPATCH_VN(g, CALL);
 #undef CALL
@@ -599,18 +722,13 @@ int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stre
 }
 
 static bool use_ring(const Geometry& g, int epi) {
-    static const bool enabled = [] {
-        const char* e = getenv("INVPREF_RING");   // INVPREF_RING=0: register-only rows kernel (A/B runs)
-        return !(e && e[0] == '0');
-    }();
-    return enabled && g.NV * g.VEC <= 4 && (epi == EPI_ADAM || epi == EPI_EXPORT);
+    return ring_enabled() && g.NV * g.VEC <= 4 && (epi == EPI_ADAM || epi == EPI_EXPORT);
 }
 
 int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream_t stream) {
     const bool stash = a.stash != nullptr;
     if (use_ring(g, epi)) {
-        const size_t smem = ((size_t)((2 * g.K * g.D + 3) & ~3) + (size_t)GROUPS_PER_BLOCK * (RING + 1) * 12 +
-                             (size_t)RING * 2 * g.NV * g.VEC * BLOCK) * sizeof(float);
+        const size_t smem = ring_smem(g);
         const int grid = grid_groups(a.plan.max_seg, 148 * 3);   // three CTAs per SM are resident: one wave
         const int long_len = 2 * chunk_for(a.plan.B);
 #define LAUNCH(KERNEL)                                                                                           \

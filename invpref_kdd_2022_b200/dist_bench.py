@@ -23,6 +23,9 @@ def run(args, w):
     local = int(os.environ.get("LOCAL_RANK", rank))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    # stdout carries exactly one JSON line: NCCL's version banner / debug log (NCCL_DEBUG from the environment or
+    # nccl.conf) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
     drv = DistDriver()
     K, D = w["K"], w["D"]
