@@ -156,7 +156,7 @@ def make_tables(w, dev, U=None, I=None, seed=17373331):
     return out
 
 
-def cpu_baseline(w, threads, budget_s=25.0, scale=None, steps=2, warmup=1):
+def cpu_baseline(w, threads, budget_s=25.0, scale=None, steps=12, warmup=1):
     """The oracle's torch-eager port on the host cores, on a proportionally scaled replica of the
     workload (U, I and B divided by the same factor, so dense-Adam work per interaction is unchanged)."""
     from oracle import invpref_numpy as on

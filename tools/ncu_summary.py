@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise ncu output into profiles/: tools/ncu_summary.py <report.ncu-rep> <launches.csv> <out.md> [title]
+"""Summarise ncu output into profiles/: tools/ncu_summary.py <report.ncu-rep>[,<report2>...] <launches.csv> <out.md> [title]
 
   <report.ncu-rep>  from `ncu --set full --clock-control none --import-source on ...` (read with ncu -i, no GPU)
   <launches.csv>    from `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...`
@@ -35,13 +35,15 @@ def short(name):
 def main():
     rep, launches, out = sys.argv[1:4]
     title = sys.argv[4] if len(sys.argv) > 4 else rep
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units, data = rows[0], rows[1], rows[2:]
-    idx = {h: i for i, h in enumerate(hdr)}
     lines = [f"# {title}", "", "## Kernels captured with `ncu --set full --clock-control none` (one launch each)", ""]
-    for r in data:
-        lines.append(f"### `{short(r[idx['Kernel Name']])}`")
+    captured = []
+    for one in rep.split(","):
+        raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        captured += [(rows[0], rows[1], r, one) for r in rows[2:]]
+    for hdr, units, r, one in captured:
+        idx = {h: i for i, h in enumerate(hdr)}
+        lines.append(f"### `{short(r[idx['Kernel Name']])}`  ({one.split('/')[-1]})")
         lines.append("")
         lines.append("| metric | value |")
         lines.append("|---|---|")
