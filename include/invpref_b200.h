@@ -226,6 +226,26 @@ int invpref_gather_rows(const float* table, const int64_t* rows, int64_t n, int3
 int invpref_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, int32_t dim, float* table,
                              void* stream);
 
+/* ---- the same exchange over peer memory (NVLink loads; no collective on the data path) -------------
+ * `tables` / `grads`: HOST arrays of 2 * world device pointers, [t * world + rank] = base of item table t
+ * (0 invariant, 1 env-aware) / of the partial-gradient cache t of rank `rank`, the caller's own rank
+ * included; the peers' buffers must be mapped into this process (CUDA IPC / VMM, e.g. torch symmetric
+ * memory).  The caller orders producers and consumers across ranks with a barrier.
+ *
+ * invpref_fetch_rows_p2p: out_t[c, :] = tables[t * world + owner[c]][rows[c], :] for c < n, t = 0, 1
+ * (replaces invpref_gather_rows on the owners + an all-to-all of rows). */
+int invpref_fetch_rows_p2p(const float* const* tables, int32_t world, const int32_t* owner, const int64_t* rows,
+                           int64_t n, int32_t dim, float* out_inv, float* out_env, void* stream);
+
+/* invpref_owner_adam_p2p: for every row j < n_rows of the caller's item shard and t = 0, 1:
+ * g = sum over ranks p = 0..world-1 (in this order) of grads[t * world + p][pos[p * n_rows + j], :]
+ * (pos < 0: rank p has no partial for row j), then one dense torch.optim.Adam step on theta/m/v with g --
+ * the same order and arithmetic as zero-fill + invpref_scatter_add_rows per rank + invpref_adam_dense, in one
+ * kernel reading the partials where the ranks' item passes wrote them. */
+int invpref_owner_adam_p2p(float* theta_inv, float* theta_env, float* m_inv, float* m_env, float* v_inv, float* v_env,
+                           int64_t n_rows, int32_t dim, int32_t world, const float* const* grads, const int32_t* pos,
+                           const invpref_hyper* hyper, void* stream);
+
 /* Number of kernels the library has launched in this process (bench.py's gpu_launches). */
 int64_t invpref_launch_count(void);
 

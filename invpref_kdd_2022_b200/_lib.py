@@ -24,7 +24,7 @@ EXPORTS = (
     "invpref_backward", "invpref_train_step", "invpref_cluster", "invpref_stat_envs",
     "invpref_env_hist", "invpref_launch_count", "invpref_profile_enable", "invpref_profile_steps",
     "invpref_profile_read", "invpref_adam_dense", "invpref_gather_rows", "invpref_scatter_add_rows",
-    "invpref_user_sweep", "invpref_flush_users",
+    "invpref_user_sweep", "invpref_flush_users", "invpref_fetch_rows_p2p", "invpref_owner_adam_p2p",
 )
 # execution order; on the fused path "forward" is empty and chunks_users / rows_users are the fused user pass
 PHASES = ("plan", "forward", "chunks_users", "rows_users", "chunks_items", "rows_items", "sweep_items",
@@ -98,6 +98,9 @@ def load() -> C.CDLL:
                                        C.POINTER(Hyper), vp, i64, vp]
     lib.invpref_gather_rows.argtypes = [vp, vp, i64, C.c_int32, vp, vp]
     lib.invpref_scatter_add_rows.argtypes = [vp, vp, i64, C.c_int32, vp, vp]
+    lib.invpref_fetch_rows_p2p.argtypes = [C.POINTER(vp), C.c_int32, vp, vp, i64, C.c_int32, vp, vp, vp]
+    lib.invpref_owner_adam_p2p.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_int32, C.c_int32, C.POINTER(vp), vp,
+                                           C.POINTER(Hyper), vp]
     lib.invpref_profile_enable.argtypes = [C.c_int]
     lib.invpref_profile_read.argtypes = [C.c_int, C.POINTER(C.c_float)]
     for name in EXPORTS:

@@ -238,6 +238,20 @@ template <> __device__ __forceinline__ void ldv_stream<2>(const float* p, float*
 }
 template <> __device__ __forceinline__ void ldv_stream<1>(const float* p, float* r) { r[0] = __ldcs(p); }
 
+// system-scope (volatile) load: for memory another GPU writes between kernels (peer memory over NVLink):
+// never served from this SM's L1
+template <int VEC> __device__ __forceinline__ void ldv_sys(const float* p, float* r);
+template <> __device__ __forceinline__ void ldv_sys<4>(const float* p, float* r) {
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]) : "l"(p));
+}
+template <> __device__ __forceinline__ void ldv_sys<2>(const float* p, float* r) {
+    asm volatile("ld.volatile.global.v2.f32 {%0, %1}, [%2];" : "=f"(r[0]), "=f"(r[1]) : "l"(p));
+}
+template <> __device__ __forceinline__ void ldv_sys<1>(const float* p, float* r) {
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(r[0]) : "l"(p));
+}
+
 template <int VEC> __device__ __forceinline__ void stv(float* p, const float* r);
 template <> __device__ __forceinline__ void stv<4>(float* p, const float* r) {
     *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);

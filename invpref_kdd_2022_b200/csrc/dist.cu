@@ -5,6 +5,15 @@
 //  gather_rows_kernel      : packs the rows a peer asked for into a contiguous send buffer.
 //  scatter_add_rows_kernel : adds one peer's partial row gradients into the owner's shard; indices are
 //                            unique within a call, peers are applied in rank order => deterministic.
+//
+// Over peer memory (NVLink loads from the other ranks' buffers, mapped into this process -- e.g. torch
+// symmetric memory; no NCCL on the data path, the caller only needs a barrier between producers and consumers):
+//  fetch_rows_p2p_kernel   : cache[c] = table_of(owner[c])[rows[c]] for both item tables: replaces
+//                            gather_rows + all-to-all of rows.
+//  owner_adam_p2p_kernel   : for every row of the owner's shard, the partial gradients are read straight from
+//                            the ranks' gradient caches, summed in rank order (same order and arithmetic as
+//                            zero + scatter_add per rank) and consumed by Adam in registers: replaces the
+//                            all-to-all of gradients + zero-fill + G scatter-adds + adam_dense.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -71,6 +80,92 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(const float* __re
     }
 }
 
+constexpr int P2P_MAX_WORLD = 16;
+struct PeerPtrs { const float* p[2 * P2P_MAX_WORLD]; };   // [t * world + rank]: table t (0 inv, 1 env) of each rank
+
+template <int VEC>
+__global__ void __launch_bounds__(256) fetch_rows_p2p_kernel(PeerPtrs tables, int world,
+                                                             const int32_t* __restrict__ owner,
+                                                             const int64_t* __restrict__ rows, int64_t n, int dim,
+                                                             float* __restrict__ out0, float* __restrict__ out1) {
+    const int per_row = dim / VEC;
+    const int64_t per_table = n * per_row, total = 2 * per_table;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;   // independent remote loads in flight per thread
+    for (int64_t q0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q0 < total; q0 += U * stride) {
+        float r[U][VEC];
+        float* dst[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = q0 + u * stride;
+            dst[u] = nullptr;
+            if (q < total) {
+                const int t = q >= per_table ? 1 : 0;
+                const int64_t rem = q - t * per_table;
+                const int64_t j = rem / per_row;
+                const int c = (int)(rem - j * per_row) * VEC;
+                const float* src = tables.p[t * world + owner[j]] + rows[j] * dim + c;
+                ldv_sys<VEC>(src, r[u]);
+                dst[u] = (t ? out1 : out0) + j * dim + c;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (dst[u] != nullptr) stv<VEC>(dst[u], r[u]);
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) owner_adam_p2p_kernel(float* __restrict__ th0, float* __restrict__ th1,
+                                                             float* __restrict__ m0, float* __restrict__ m1,
+                                                             float* __restrict__ v0, float* __restrict__ v1,
+                                                             int64_t n_rows, int dim, int world, PeerPtrs grads,
+                                                             const int32_t* __restrict__ pos, AdamScalars s) {
+    const int per_row = dim / VEC;
+    const int64_t per_table = n_rows * per_row, total = 2 * per_table;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int t = q >= per_table ? 1 : 0;
+        const int64_t rem = q - t * per_table;
+        const int64_t j = rem / per_row;
+        const int c = (int)(rem - j * per_row) * VEC;
+        // all slots first, then all (independent) remote loads, then the sum in rank order
+        int sl[P2P_MAX_WORLD];
+        float part[P2P_MAX_WORLD][VEC];
+#pragma unroll
+        for (int p = 0; p < P2P_MAX_WORLD; ++p) sl[p] = (p < world) ? pos[(int64_t)p * n_rows + j] : -1;
+#pragma unroll
+        for (int p = 0; p < P2P_MAX_WORLD; ++p) {
+            if (sl[p] >= 0) {
+                ldv_sys<VEC>(grads.p[t * world + p] + (int64_t)sl[p] * dim + c, part[p]);
+            } else {
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) part[p][x] = 0.f;
+            }
+        }
+        float g[VEC];
+#pragma unroll
+        for (int x = 0; x < VEC; ++x) g[x] = 0.f;
+#pragma unroll
+        for (int p = 0; p < P2P_MAX_WORLD; ++p)
+            if (sl[p] >= 0) {
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) g[x] += part[p][x];
+            }
+        float* th = (t ? th1 : th0) + j * dim + c;
+        float* mm = (t ? m1 : m0) + j * dim + c;
+        float* vv = (t ? v1 : v0) + j * dim + c;
+        float pr[VEC], mr[VEC], vr[VEC];
+        ldv_stream<VEC>(th, pr);
+        ldv_stream<VEC>(mm, mr);
+        ldv_stream<VEC>(vv, vr);
+#pragma unroll
+        for (int x = 0; x < VEC; ++x) adam_update(pr[x], mr[x], vr[x], g[x], s);
+        stv<VEC>(th, pr);
+        stv_stream<VEC>(mm, mr);
+        stv_stream<VEC>(vv, vr);
+    }
+}
+
 inline int grid_1d(int64_t work, int max_blocks = 148 * 16) {
     int64_t need = (work + 255) / 256;
     if (need < 1) need = 1;
@@ -100,6 +195,32 @@ int launch_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, in
     const bool v4 = dim % 4 == 0 && ((uintptr_t)table % 16 == 0) && ((uintptr_t)src % 16 == 0);
     if (v4) scatter_add_rows_kernel<4><<<grid_1d(n * (dim / 4)), 256, 0, stream>>>(src, rows, n, dim, table);
     else scatter_add_rows_kernel<1><<<grid_1d(n * dim), 256, 0, stream>>>(src, rows, n, dim, table);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_fetch_rows_p2p(const float* const* tables_host, int world, const int32_t* owner, const int64_t* rows,
+                          int64_t n, int dim, float* out0, float* out1, cudaStream_t stream) {
+    if (world < 1 || world > P2P_MAX_WORLD) return INVPREF_ERR_BAD_ARG;
+    PeerPtrs pp = {};
+    bool v4 = dim % 4 == 0 && ((uintptr_t)out0 % 16 == 0) && ((uintptr_t)out1 % 16 == 0);
+    for (int i = 0; i < 2 * world; ++i) { pp.p[i] = tables_host[i]; v4 = v4 && ((uintptr_t)tables_host[i] % 16 == 0); }
+    if (v4) fetch_rows_p2p_kernel<4><<<grid_1d(2 * n * (dim / 4) / 4 + 256), 256, 0, stream>>>(pp, world, owner, rows, n, dim, out0, out1);
+    else fetch_rows_p2p_kernel<1><<<grid_1d(2 * n * dim / 4 + 256), 256, 0, stream>>>(pp, world, owner, rows, n, dim, out0, out1);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_owner_adam_p2p(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
+                          int world, const float* const* grads_host, const int32_t* pos, const AdamScalars& s,
+                          cudaStream_t stream) {
+    if (world < 1 || world > P2P_MAX_WORLD) return INVPREF_ERR_BAD_ARG;
+    PeerPtrs pp = {};
+    bool v4 = dim % 4 == 0;
+    for (float* q : {th0, th1, m0, m1, v0, v1}) v4 = v4 && ((uintptr_t)q % 16 == 0);
+    for (int i = 0; i < 2 * world; ++i) { pp.p[i] = grads_host[i]; v4 = v4 && ((uintptr_t)grads_host[i] % 16 == 0); }
+    if (v4) owner_adam_p2p_kernel<4><<<grid_1d(2 * n_rows * (dim / 4)), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, pp, pos, s);
+    else owner_adam_p2p_kernel<1><<<grid_1d(2 * n_rows * dim), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, pp, pos, s);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

@@ -36,9 +36,32 @@ def run(args, w):
     kw = dict(alpha=1.0, use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
     t = lambda a: torch.from_numpy(a).to(dev)
 
+    p2p_note = "off"
     if sharded:
+        cache_rows = min(I, Bg // world * 2 + 1024)
+        # item exchange over peer memory (NVLink loads from torch symmetric memory) unless unavailable or
+        # INVPREF_P2P=0; every rank must take the same path, so the outcome is agreed on with an all-reduce
+        store, why = None, "disabled (INVPREF_P2P=0)"
+        if os.environ.get("INVPREF_P2P", "1") != "0":
+            try:
+                from invpref_kdd_2022_b200.parallel import SymmetricItemStorage
+                store = SymmetricItemStorage(I, D, world, cache_rows, dev, dist.group.WORLD)
+                why = ""
+            except Exception as ex:      # noqa: BLE001 -- any failure means "use NCCL"
+                store, why = None, f"{type(ex).__name__}: {ex}"[:200]
+        ok = torch.tensor([1 if store is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            store = None
         tr = ShardedTrainer(U, I, K, D, w["implicit"], w["roe"], w["ree"], w["lr"], rank, world, dev,
-                            cache_rows=min(I, Bg // world * 2 + 1024))
+                            cache_rows=cache_rows, alloc=store.alloc if store is not None else None)
+        if store is not None:
+            tr.enable_p2p(store.ptrs("Iinv"), store.ptrs("Ienv"), store.ptrs("gcache0"), store.ptrs("gcache1"))
+            p2p_note = "peer memory (torch symmetric memory, NVLink loads)"
+        else:
+            p2p_note = "NCCL all-to-all (" + (why or "a peer could not map symmetric memory") + ")"
+        torch.cuda.synchronize()
+        dist.barrier()                   # every shard initialised before anyone reads a peer's rows
         prepared = []
         for (u, i, y, e) in batches:
             sb = drv.run(tr.prepare_gen(t(u), t(i), t(y)))
@@ -50,7 +73,7 @@ def run(args, w):
             sb, le, sw = prepared[s % nb]
             return drv.run(tr.step_gen(sb, le, sw, next_sb=prepared[(s + 1) % nb][0], **kw))
         mode = f"users+items row-sharded (mod {world}), interactions routed to the user's owner, " \
-               f"item rows/grads all-to-all, E/W/b all-reduce"
+               f"item rows/grads exchanged over {p2p_note}, E/W/b all-reduce"
     else:
         g = torch.Generator(device=dev).manual_seed(17373331)
         tr = ReplicatedTrainer(B.make_tables(w, dev), w["implicit"], w["roe"], w["ree"], w["lr"], rank, world)

@@ -91,9 +91,15 @@ class SimDriver:
 
     def run_all(self, gens: List):
         G = self.world
-        reqs = [next(g) for g in gens]
-        done = [False] * G
-        results = [None] * G
+        reqs, done, results = [None] * G, [False] * G, [None] * G
+        for k in range(G):
+            try:
+                reqs[k] = next(gens[k])
+            except StopIteration as stop:        # no collective at all (e.g. peer-memory fetch only)
+                done[k], results[k] = True, stop.value
+        if all(done):
+            return results
+        assert not any(done), "ranks finished at different points"
         while True:
             op = reqs[0][0]
             assert all(r[0] == op for r in reqs), "ranks diverged"
@@ -185,6 +191,11 @@ class ItemRoute:
         self.recv_splits = None    # list[G]     cache rows coming from each owner
         self.send_splits = None    # list[G]     rows of my shard going to each requester
         self.send_rows = None      # int64 [sum(send_splits)] owner-local row indices, grouped by requester
+        # peer-memory exchange (ShardedTrainer.enable_p2p)
+        self.slot_owner = None     # int32 [n_cache] owner rank of every cache slot
+        self.want_rows = None      # int64 [n_cache] owner-local row of every cache slot
+        self.peer_first = None     # list[G]     first slot, in requester p's cache, of the rows it wants from me
+        self.pos = None            # int32 [G, I_loc] slot of my row j in rank p's gradient cache, or -1
 
 
 def build_route_gen(items_global: torch.Tensor, world: int, route: ItemRoute):
@@ -205,7 +216,60 @@ def build_route_gen(items_global: torch.Tensor, world: int, route: ItemRoute):
     route.send_splits = [int(c) for c in send_counts.tolist()]
     route.send_rows = torch.empty(sum(route.send_splits), dtype=torch.int64, device=dev)
     yield ("all_to_all", route.send_rows, want_rows, route.send_splits, route.recv_splits)
+    # where, in every requester's cache, the block of rows it wants from me starts (peer-memory exchange)
+    route.slot_owner = owner[order].to(torch.int32).contiguous()
+    route.want_rows = want_rows
+    first = torch.cumsum(counts, 0) - counts                     # my cache: first slot of each owner's block
+    peer_first = torch.zeros(world, dtype=torch.int64, device=dev)
+    yield ("all_to_all", peer_first, first.to(torch.int64).contiguous(), [1] * world, [1] * world)
+    route.peer_first = [int(c) for c in peer_first.tolist()]
     return route
+
+
+def build_pos_table(route: ItemRoute, world: int, n_local_rows: int) -> torch.Tensor:
+    """pos[p, j] = slot of my item row j in rank p's gradient cache, -1 if rank p did not ask for it."""
+    dev = route.send_rows.device
+    pos = torch.full((world, max(n_local_rows, 1)), -1, dtype=torch.int32, device=dev)
+    o = 0
+    for p in range(world):
+        n = route.send_splits[p]
+        if n:
+            pos[p, route.send_rows[o:o + n]] = (route.peer_first[p] + torch.arange(n, device=dev)).to(torch.int32)
+        o += n
+    return pos
+
+
+class SymmetricItemStorage:
+    """Peer-visible storage of one rank's item shard and partial-gradient caches: ONE torch symmetric-memory
+    buffer [Iinv | Ienv | gcache0 | gcache1] with the same layout on every rank, so that a peer's table is
+    `buffer_ptrs[rank] + offset`.  Raises if symmetric memory is unavailable (callers fall back to NCCL)."""
+
+    def __init__(self, n_items, dim, world, cache_rows, device, group):
+        import torch.distributed._symmetric_memory as symm
+        rows_max = (n_items + world - 1) // world
+        pad = lambda n: (n + 63) // 64 * 64                      # 256-byte aligned sections
+        sizes = [("Iinv", pad(rows_max * dim)), ("Ienv", pad(rows_max * dim)),
+                 ("gcache0", pad(cache_rows * dim)), ("gcache1", pad(cache_rows * dim))]
+        self.offsets, o = {}, 0
+        for k, n in sizes:
+            self.offsets[k] = o
+            o += n
+        self.buf = symm.empty(o, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(self.base) != world:
+            raise RuntimeError("symmetric memory: unexpected number of peer buffers")
+
+    def alloc(self, name, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        o = self.offsets[name]
+        return self.buf[o:o + n].view(tuple(shape))
+
+    def ptrs(self, name):
+        return [b + 4 * self.offsets[name] for b in self.base]
 
 
 class ShardedBatch:
@@ -224,7 +288,10 @@ class ShardedTrainer:
     """User and item tables mod-sharded by row over `world` ranks (row r of rank g holds id r*world + g)."""
 
     def __init__(self, n_users, n_items, n_envs, dim, implicit, reg_only_embed, reg_env_embed, lr, rank, world,
-                 device, cache_rows, init=None, seed=17373331, lazy=True):
+                 device, cache_rows, init=None, seed=17373331, lazy=True, alloc=None):
+        """``alloc(name, shape) -> fp32 tensor``: storage for the buffers other ranks read in peer-memory mode
+        (``Iinv``, ``Ienv``, ``gcache0``, ``gcache1``), e.g. views of a torch symmetric-memory buffer; default:
+        ordinary device tensors (NCCL exchange, or simulated ranks in one process)."""
         self.rank, self.world, self.dev = rank, world, device
         self.U, self.I, self.K, self.D = n_users, n_items, n_envs, dim
         self.U_loc = (n_users - rank + world - 1) // world
@@ -236,12 +303,18 @@ class ShardedTrainer:
             uinv, uenv = init["Uinv"][rank::world].clone(), init["Uenv"][rank::world].clone()
             self.Iinv, self.Ienv = init["Iinv"][rank::world].clone(), init["Ienv"][rank::world].clone()
             small = [init[k].reshape(-1).clone() for k in SMALL]
+            if alloc is not None:
+                self.Iinv = alloc("Iinv", self.Iinv.shape).copy_(self.Iinv)
+                self.Ienv = alloc("Ienv", self.Ienv.shape).copy_(self.Ienv)
         else:
             g = torch.Generator(device=device).manual_seed(seed + rank)
             uinv = torch.randn((self.U_loc, dim), generator=g, **f32) * 0.01
             uenv = torch.randn((self.U_loc, dim), generator=g, **f32) * 0.01
             self.Iinv = torch.randn((self.I_loc, dim), generator=g, **f32) * 0.01
             self.Ienv = torch.randn((self.I_loc, dim), generator=g, **f32) * 0.01
+            if alloc is not None:
+                self.Iinv = alloc("Iinv", self.Iinv.shape).copy_(self.Iinv)
+                self.Ienv = alloc("Ienv", self.Ienv.shape).copy_(self.Ienv)
             g0 = torch.Generator(device=device).manual_seed(seed)          # replicated tensors: same on all ranks
             small = [torch.randn(n, generator=g0, **f32) * s for n, s in
                      ((n_envs * dim, 0.01), (n_envs * dim, 0.1), (n_envs, 0.1))]
@@ -258,7 +331,10 @@ class ShardedTrainer:
         self.loss = self.gsmall[2 * KD + n_envs:]
         # per-batch item cache (what the local kernels see as "the item tables") and its gradient
         self.cache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
-        self.gcache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
+        if alloc is not None:
+            self.gcache = [alloc(f"gcache{t}", (self.cache_rows, dim)).zero_() for t in range(2)]
+        else:
+            self.gcache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
         params = {"Uinv": uinv, "Uenv": uenv, "Iinv": self.cache[0], "Ienv": self.cache[1]}
         params.update(views(self.small))
         # lazy: the local user shard uses lazy dense Adam (bit-identical, see HotPath), so there is no dense
@@ -279,6 +355,18 @@ class ShardedTrainer:
         self._fetched = None                      # batch whose item rows are currently in the cache
         self.side = torch.cuda.Stream(device=device)
         self.phase_events = None                  # set to [] to record (name, event) marks per step (bench)
+        self.p2p = None                           # (tables ptr array, grads ptr array) once enable_p2p() ran
+        self.bar = torch.zeros(1, **f32)          # payload of the barrier all-reduce (peer-memory mode)
+
+    def enable_p2p(self, item_inv_ptrs, item_env_ptrs, gcache0_ptrs, gcache1_ptrs):
+        """Peer-memory item exchange (NVLink loads instead of NCCL all-to-alls): the arguments are, per rank
+        0..world-1, the device address IN THIS PROCESS of that rank's Iinv / Ienv shard and of its two
+        partial-gradient caches (own rank included)."""
+        G = self.world
+        assert len(item_inv_ptrs) == len(item_env_ptrs) == len(gcache0_ptrs) == len(gcache1_ptrs) == G
+        tables = (C.c_void_p * (2 * G))(*([int(x) for x in item_inv_ptrs] + [int(x) for x in item_env_ptrs]))
+        grads = (C.c_void_p * (2 * G))(*([int(x) for x in gcache0_ptrs] + [int(x) for x in gcache1_ptrs]))
+        self.p2p = (tables, grads)
 
     def _mark(self, name):
         if self.phase_events is not None:
@@ -318,6 +406,15 @@ class ShardedTrainer:
     def fetch_gen(self, sb: ShardedBatch):
         """All-to-all of item rows: owners pack the requested rows, requesters receive them as the cache."""
         r = sb.route
+        if self.p2p is not None:
+            # one kernel: every cache row is loaded straight from its owner's shard (the caller has made sure,
+            # with a barrier, that all owners finished their last update)
+            if r.n_cache:
+                _lib.check(self.hot.lib.invpref_fetch_rows_p2p(
+                    self.p2p[0], self.world, _lib.ptr(r.slot_owner, torch.int32), _lib.ptr(r.want_rows, torch.int64),
+                    r.n_cache, self.D, _lib.ptr(self.cache[0]), _lib.ptr(self.cache[1]), _lib.stream_ptr()),
+                    "fetch_rows_p2p")
+            return
         ns = int(r.send_rows.numel())
         send = self._buf("send_buf", ns)
         for t, (table, buf) in enumerate(zip((self.Iinv, self.Ienv), send)):
@@ -367,6 +464,34 @@ class ShardedTrainer:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
                 self.hot.user_sweep(sb.plan, sb.users.numel())
+        if self.p2p is not None:
+            # Peer-memory exchange.  Barrier 1 = the all-reduce of the replicated tensors' gradients: when it
+            # returns, every rank's item pass has written its partial-gradient cache.  Then ONE kernel per rank
+            # pulls the partials of its own rows over NVLink, sums them in rank order and applies Adam.
+            yield ("all_reduce", self.gsmall)
+            self._mark("grad_a2a")
+            if r.pos is None:
+                r.pos = build_pos_table(r, self.world, self.I_loc)
+            hyper = _lib.Hyper(0, 0, 0, 0, 0, 0, self.hot.lr, self.hot.betas[0], self.hot.betas[1], self.hot.eps,
+                               int(self.hot.step), 0, 0, 0, 0, 0)
+            _lib.check(self.hot.lib.invpref_owner_adam_p2p(
+                _lib.ptr(self.Iinv), _lib.ptr(self.Ienv), _lib.ptr(self.mI[0]), _lib.ptr(self.mI[1]),
+                _lib.ptr(self.vI[0]), _lib.ptr(self.vI[1]), self.I_loc, self.D, self.world, self.p2p[1],
+                _lib.ptr(r.pos, torch.int32), C.byref(hyper), _lib.stream_ptr()), "owner_adam_p2p")
+            self._mark("item_adam")
+            n_small = self.small.numel()
+            self.hot.adam_dense(self.small, self.msmall, self.vsmall, self.gsmall[:n_small])
+            # Barrier 2: every owner has updated its rows (and finished reading the gradient caches) before
+            # anyone fetches rows for the next batch or overwrites its cache in the next step.
+            yield ("all_reduce", self.bar)
+            self._mark("small")
+            if next_sb is not None:
+                yield from self.fetch_gen(next_sb)
+                self._fetched = next_sb
+            self._mark("prefetch_next")
+            main.wait_stream(self.side)
+            self._mark("sweep_wait")
+            return self.loss
         # partial item gradients back to the owners (reverse routing)
         ns = int(r.send_rows.numel())
         recv = self._buf("recv_g", ns)

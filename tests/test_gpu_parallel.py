@@ -44,10 +44,11 @@ def single_gpu(p, batches, implicit, roe, ree, lr):
     return hp, np.asarray(losses)
 
 
+@pytest.mark.parametrize("p2p", [False, True])
 @pytest.mark.parametrize("lazy", [True, False])
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("implicit,roe,ree", [(False, True, False), (True, False, True)])
-def test_sharded_matches_single_gpu(world, implicit, roe, ree, lazy):
+def test_sharded_matches_single_gpu(world, implicit, roe, ree, lazy, p2p):
     from invpref_kdd_2022_b200.parallel import ShardedTrainer, SimDriver
     dev = torch.device("cuda:0")
     U, I, K, D, B = 1000, 203, 4, 64, 20000
@@ -58,6 +59,10 @@ def test_sharded_matches_single_gpu(world, implicit, roe, ree, lazy):
     init = {k: torch.tensor(v, device=dev) for k, v in p.items()}
     ranks = [ShardedTrainer(U, I, K, D, implicit, roe, ree, 1e-2, r, world, dev, cache_rows=I, init=init, lazy=lazy)
              for r in range(world)]
+    if p2p:   # peer-memory exchange: the simulated ranks' buffers are plain tensors on the same device
+        for rk in ranks:
+            rk.enable_p2p([x.Iinv.data_ptr() for x in ranks], [x.Ienv.data_ptr() for x in ranks],
+                          [x.gcache[0].data_ptr() for x in ranks], [x.gcache[1].data_ptr() for x in ranks])
     sim = SimDriver(world)
     t = lambda a: torch.tensor(a, device=dev)
     losses = []
@@ -121,3 +126,41 @@ def test_replicated_matches_single_gpu(world):
         assert torch.equal(rk.flat, ranks[0].flat)
         for k in on.PARAM_ORDER:
             assert nerr(rk.params[k].cpu().numpy(), ref.params[k].cpu().numpy()) <= 2e-4, k
+
+
+def test_sharded_peer_memory_is_bitwise_the_collective_path():
+    """The peer-memory exchange (invpref_fetch_rows_p2p + invpref_owner_adam_p2p) sums the partial item
+    gradients in the same rank order with the same arithmetic as all-to-all + scatter-add + adam_dense."""
+    from invpref_kdd_2022_b200.parallel import ShardedTrainer, SimDriver
+    dev = torch.device("cuda:0")
+    world, U, I, K, D, B = 3, 700, 151, 4, 64, 12000
+    u, i, y, e, w, p = synth(U, I, 3 * B, K, D, False, 11)
+    init = {k: torch.tensor(v, device=dev) for k, v in p.items()}
+    t = lambda a: torch.tensor(a, device=dev)
+    out = []
+    for p2p in (False, True):
+        ranks = [ShardedTrainer(U, I, K, D, False, True, False, 1e-2, r, world, dev, cache_rows=I, init=init)
+                 for r in range(world)]
+        if p2p:
+            for rk in ranks:
+                rk.enable_p2p([x.Iinv.data_ptr() for x in ranks], [x.Ienv.data_ptr() for x in ranks],
+                              [x.gcache[0].data_ptr() for x in ranks], [x.gcache[1].data_ptr() for x in ranks])
+        sim = SimDriver(world)
+        losses = []
+        sbs_all = []
+        for s in range(3):
+            sl = slice(s * B, (s + 1) * B)
+            sbs_all.append(sim.run_all([rk.prepare_gen(t(u[sl]), t(i[sl]), t(y[sl])) for rk in ranks]))
+        for s in range(3):
+            sl = slice(s * B, (s + 1) * B)
+            sbs = sbs_all[s]
+            nxt = sbs_all[s + 1] if s + 1 < 3 else [None] * world
+            res = sim.run_all([rk.step_gen(sb, t(e[sl])[sb.sel].contiguous(), t(w[sl])[sb.sel].contiguous(),
+                                           next_sb=nx, **KW) for rk, sb, nx in zip(ranks, sbs, nxt)])
+            losses.append(res[0].clone())
+        out.append((losses, [{k: v.clone() for k, v in rk.local_tables().items()} for rk in ranks]))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert torch.equal(a, b)
+    for ta, tb in zip(out[0][1], out[1][1]):
+        for k in ta:
+            assert torch.equal(ta[k], tb[k]), k
