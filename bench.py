@@ -200,7 +200,9 @@ def run_reference(args, w):
     line = {"impl": "reference", "metric": "train interactions/sec (fwd+bwd+Adam)", "value": r["value"],
             "unit": "interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": w["name"]},
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "global_batch": w["B"],
+                       "params": 2 * (w["U"] + w["I"]) * w["D"] + 2 * w["K"] * w["D"] + w["K"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "cluster": {"value": r["cluster_samples_per_s"], "unit": "samples/s"},
             "e2e": {"value": r["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -9,9 +9,11 @@
 // ncu on the first version (round 1): 57 % of the warp samples waited on the long scoreboard (ids -> rows ->
 // perm_idx -> eps chains), 64-bit shared atomics were CAS loops.  Now the four rows of a sample are copied
 // global -> shared with cp.async two iterations before they are read (no register held, each lane copies the
-// slice it reads back: wait_group only, no barrier), ids are loaded one iteration before that, the per-sample
-// scalars at the top of the iteration, this lane's slice of E lives in registers, the K! x K tie-break table
-// in shared memory (K <= 6), and histogram / diff counts are per-group registers until the end.
+// slice it reads back: wait_group only, no barrier), ids (low words) are loaded two iterations before that, the
+// per-sample scalars one iteration ahead into one lane-distributed register, this lane's slice of E lives in
+// registers, the K! x K tie-break table in shared memory (K <= 6), the K env scores come out of one scattered
+// reduction and a (distance, k) butterfly takes the first minimum, and histogram / diff counts are per-group
+// registers until the end.  5.5 G samples/s = 0.90 of the measured HBM peak at C5.
 #include "common.cuh"
 #include "kernels.h"
 
