@@ -13,6 +13,7 @@ One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the definitio
   cluster    env re-assignment samples/s and its roofline;
   cpu_baseline  the oracle's torch-eager port (same ATen op sequence as the reference trainer) timed on
              the box's host cores on a bounded, proportionally scaled sample.
+  torch_eager_gpu  the same port on the same GPU at full size (the number the kernels must beat).
 """
 from __future__ import annotations
 
@@ -189,6 +190,31 @@ def cpu_baseline(w, threads, budget_s=25.0, scale=None, steps=12, warmup=1):
               f"{len(times)} train_a_batch after {warmup} warm-up; 1 cluster_a_batch")
     return {"value": B / t_step, "unit": "interactions/s", "cores": threads, "kind": "port", "sample": sample,
             "ms_per_step": t_step * 1e3, "cluster_samples_per_s": B / t_cl}
+
+
+def torch_eager_gpu(w, dev, dbatch, steps=3):
+    """"also time the reference on the B200 via torch eager -- the number the new kernels must
+    beat".  The oracle's torch port issues the reference's op sequence (13 embedding gathers + their dense
+    backward, autograd, torch.optim.Adam, six float() syncs per step); here it runs on the same GPU, same batch,
+    same shapes.  Baseline only (never the product path)."""
+    from oracle import invpref_numpy as on
+    from oracle import invpref_torch_cpu as ot
+    u, i, y, e, sw = dbatch
+    P = {k: v.requires_grad_(True) for k, v in make_tables(w, dev).items()}
+    hp = on.Hyper(alpha=1.0, lr=w["lr"], use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
+    tr = ot.CpuTrainer(P, on.Flags(w["implicit"], w["roe"], w["ree"]), hp)
+    tr.train_a_batch(u, i, y, e, sw, 1.0)                       # warm-up (allocates grads and Adam state)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_a_batch(u, i, y, e, sw, 1.0)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    out = {"value": u.numel() / dt, "unit": "interactions/s", "ms_per_step": dt * 1e3, "steps": steps,
+           "kind": "port: torch-eager op sequence of the reference, on the same B200, full-size batch"}
+    del tr, P
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args, w):
@@ -398,6 +424,11 @@ def run_ours_single(args, w):
             "dense_adam": dense, "cluster": cluster, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w, os.cpu_count() or 1)
+        try:
+            line["torch_eager_gpu"] = torch_eager_gpu(w, dev, dbatches[0])
+            line["torch_eager_gpu"]["speedup_of_value"] = line["value"] / line["torch_eager_gpu"]["value"]
+        except Exception as ex:      # noqa: BLE001 -- a baseline leg must never break the bench line
+            line["torch_eager_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
     print(json.dumps(line), flush=True)
 
 

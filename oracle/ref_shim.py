@@ -21,7 +21,7 @@ def available() -> bool:
 
 
 def load():
-    """Returns the reference modules (models, train, functions, utils) imported under
+    """Returns the reference modules (models, train, functions, utils, dataloader, evaluate) imported under
     private names so they never shadow the product package's modules."""
     if not available():
         raise RuntimeError(f"reference checkout not found at {REF_ROOT}")
@@ -41,7 +41,8 @@ def load():
         for k in saved:
             sys.modules.pop(k, None)
         import importlib
-        mods = {k: importlib.import_module(k) for k in ("functions", "utils", "models", "evaluate", "train")}
+        mods = {k: importlib.import_module(k) for k in ("functions", "utils", "models", "dataloader", "evaluate",
+                                                        "train")}
     finally:
         sys.path.remove(REF_ROOT)
         for k in list(saved):
