@@ -226,6 +226,18 @@ int invpref_gather_rows(const float* table, const int64_t* rows, int64_t n, int3
 int invpref_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, int32_t dim, float* table,
                              void* stream);
 
+/* ---- implicit evaluator helpers (evaluate.py:94-135; per-user item lists as CSR over user ids:
+ * off int64 [n_users + 1], items int64 [nnz], ascending and unique within a user) ---------------------
+ * invpref_mask_scores: for r < b: rating[r, items(users[r])] = value (add == 0: the train-positive mask,
+ * evaluate.py:98) or += value (add != 0: the item-pool highlight, evaluate.py:110).  rating: fp32 [b, n_items]. */
+int invpref_mask_scores(float* rating, int64_t b, int64_t n_items, const int64_t* users, const int64_t* off,
+                        const int64_t* items, float value, int32_t add, void* stream);
+
+/* invpref_hits_from_csr: hits[r, j] = 1 if top[r, j] is in items(users[r]) else 0 (evaluate.py:11-19 get_label);
+ * n_list[r] (nullable) = length of that list (the per-user ground-truth count of recall / IDCG). */
+int invpref_hits_from_csr(const int64_t* top, int64_t b, int32_t k, const int64_t* users, const int64_t* off,
+                          const int64_t* items, uint8_t* hits, int64_t* n_list, void* stream);
+
 /* ---- the same exchange over peer memory (NVLink loads; no collective on the data path) -------------
  * `tables` / `grads`: HOST arrays of 2 * world device pointers, [t * world + rank] = base of item table t
  * (0 invariant, 1 env-aware) / of the partial-gradient cache t of rank `rank`, the caller's own rank

@@ -25,6 +25,7 @@ EXPORTS = (
     "invpref_env_hist", "invpref_launch_count", "invpref_profile_enable", "invpref_profile_steps",
     "invpref_profile_read", "invpref_adam_dense", "invpref_gather_rows", "invpref_scatter_add_rows",
     "invpref_user_sweep", "invpref_flush_users", "invpref_fetch_rows_p2p", "invpref_owner_adam_p2p",
+    "invpref_mask_scores", "invpref_hits_from_csr",
 )
 # execution order; on the fused path "forward" is empty and chunks_users / rows_users are the fused user pass
 PHASES = ("plan", "forward", "chunks_users", "rows_users", "chunks_items", "rows_items", "sweep_items",
@@ -101,6 +102,8 @@ def load() -> C.CDLL:
     lib.invpref_fetch_rows_p2p.argtypes = [C.POINTER(vp), C.c_int32, vp, vp, i64, C.c_int32, vp, vp, vp]
     lib.invpref_owner_adam_p2p.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_int32, C.c_int32, C.POINTER(vp), vp,
                                            C.POINTER(Hyper), vp]
+    lib.invpref_mask_scores.argtypes = [vp, i64, i64, vp, vp, vp, C.c_float, C.c_int32, vp]
+    lib.invpref_hits_from_csr.argtypes = [vp, i64, C.c_int32, vp, vp, vp, vp, vp, vp]
     lib.invpref_profile_enable.argtypes = [C.c_int]
     lib.invpref_profile_read.argtypes = [C.c_int, C.POINTER(C.c_float)]
     for name in EXPORTS:

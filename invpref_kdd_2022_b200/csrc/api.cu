@@ -412,6 +412,20 @@ int invpref_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, i
     return launch_scatter_add_rows(src, rows, n, dim, table, (cudaStream_t)stream);
 }
 
+int invpref_mask_scores(float* rating, int64_t b, int64_t n_items, const int64_t* users, const int64_t* off,
+                        const int64_t* items, float value, int32_t add, void* stream) {
+    if (b < 0 || n_items < 1 || (b > 0 && (!rating || !users || !off))) return INVPREF_ERR_BAD_ARG;
+    if (b == 0 || !items) return INVPREF_OK;     // items == NULL: every list is empty
+    return launch_mask_scores(rating, b, n_items, users, off, items, value, add, (cudaStream_t)stream);
+}
+
+int invpref_hits_from_csr(const int64_t* top, int64_t b, int32_t k, const int64_t* users, const int64_t* off,
+                          const int64_t* items, uint8_t* hits, int64_t* n_list, void* stream) {
+    if (b < 0 || k < 1 || (b > 0 && (!top || !users || !off || !items || !hits))) return INVPREF_ERR_BAD_ARG;
+    if (b == 0) return INVPREF_OK;
+    return launch_hits_from_csr(top, b, k, users, off, items, hits, n_list, (cudaStream_t)stream);
+}
+
 int invpref_fetch_rows_p2p(const float* const* tables, int32_t world, const int32_t* owner, const int64_t* rows,
                            int64_t n, int32_t dim, float* out_inv, float* out_env, void* stream) {
     if (n < 0 || dim < 1 || !tables || (n > 0 && (!owner || !rows || !out_inv || !out_env))) return INVPREF_ERR_BAD_ARG;

@@ -138,6 +138,12 @@ int launch_owner_adam_p2p(float* th0, float* th1, float* m0, float* m1, float* v
                           int world, const float* const* grads_host, const int32_t* pos, const AdamScalars& s,
                           cudaStream_t stream);
 
+// ---- eval.cu ---------------------------------------------------------------------------------
+int launch_mask_scores(float* rating, int64_t b, int64_t n_items, const int64_t* users, const int64_t* off,
+                       const int64_t* items, float value, int add, cudaStream_t stream);
+int launch_hits_from_csr(const int64_t* top, int64_t b, int k, const int64_t* users, const int64_t* off,
+                         const int64_t* items, uint8_t* hits, int64_t* n_list, cudaStream_t stream);
+
 // ---- plan.cu ---------------------------------------------------------------------------------
 int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, PlanSide p, char* tmp,
                     size_t tmp_bytes, cudaStream_t stream);

@@ -3,8 +3,11 @@
 
 ``ExplicitTestManager``: MSE / RMSE / MAE of ``model.predict(test_users, test_items)`` (the fused
 predict kernel).  ``ImplicitTestManager``: recall / precision / NDCG @k per test user; the reference builds
-python index lists per user and counts hits with python sets (evaluate.py:94-135); here masks and ground truth
-are dense boolean matrices built once per batch on the device and the metrics are tensor expressions.
+python index lists per user and counts hits with python sets (evaluate.py:94-135).  On a CUDA model the per-user
+item lists (train positives, item pool, ground truth) are uploaded ONCE as CSR and two library kernels do the
+masking and the hit look-ups (``invpref_mask_scores`` / ``invpref_hits_from_csr``): no per-batch host work at all;
+otherwise (CPU stub models in the reference-parity tests) dense boolean matrices are built per batch.  The
+metrics are the same tensor expressions on both paths.
 """
 from __future__ import annotations
 
@@ -50,20 +53,70 @@ class ImplicitTestManager:
             m[torch.from_numpy(rows).to(device), torch.from_numpy(cols).to(device)] = True
         return m
 
-    def evaluate_batch(self, batch_users_tensor: torch.Tensor, batch_users_list: list, batch_users_ground_truth=None):
+    def _csr_on(self, name: str, device):
+        """(off, items) of the loader's CSR `name` as int64 tensors on `device`, uploaded once."""
+        cache = self.__dict__.setdefault("_csr_cache", {})
+        key = (name, str(device))
+        if key not in cache:
+            off = np.ascontiguousarray(getattr(self.data_loader, name + "_off"), dtype=np.int64)
+            items = np.ascontiguousarray(getattr(self.data_loader, name + "_items"), dtype=np.int64)
+            cache[key] = (torch.from_numpy(off).to(device), torch.from_numpy(items).to(device))
+        return cache[key]
+
+    def _hits_device(self, rating, users_t, kmax):
+        """CUDA path: masks, top-k and hit look-ups without leaving the device."""
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        b, n_items = rating.shape
+        users_t = users_t.contiguous()
+
+        def mask(name, value, add):
+            off, items = self._csr_on(name, rating.device)
+            _lib.check(lib.invpref_mask_scores(_lib.ptr(rating, torch.float32), b, n_items,
+                                               _lib.ptr(users_t, torch.int64), _lib.ptr(off, torch.int64),
+                                               _lib.ptr(items, torch.int64) if items.numel() else None,
+                                               C.c_float(value), add, _lib.stream_ptr()), "mask_scores")
+
+        mask("mask", -float(1 << 10), 0)                                                        # evaluate.py:98
+        if self.use_item_pool:
+            mask("pool", float(1 << 10), 1)                                                     # evaluate.py:110
+        _, top = torch.topk(rating, k=kmax)
+        top = top.contiguous()
+        off, items = self._csr_on("gt", rating.device)
+        hits = torch.empty((b, kmax), dtype=torch.uint8, device=rating.device)
+        n_gt = torch.empty(b, dtype=torch.int64, device=rating.device)
+        if items.numel():
+            _lib.check(lib.invpref_hits_from_csr(_lib.ptr(top, torch.int64), b, kmax, _lib.ptr(users_t, torch.int64),
+                                                 _lib.ptr(off, torch.int64), _lib.ptr(items, torch.int64),
+                                                 _lib.ptr(hits), _lib.ptr(n_gt), _lib.stream_ptr()), "hits_from_csr")
+        else:
+            hits.zero_()
+            n_gt.zero_()
+        return hits.double(), n_gt.double()
+
+    def _hits_host(self, rating, users: np.ndarray, kmax):
+        """Any device: dense boolean masks built per batch from the loader's CSR arrays."""
         dl = self.data_loader
-        users = np.asarray(batch_users_list, dtype=np.int64)
-        with torch.no_grad():
-            rating = self.model.predict(batch_users_tensor).clone()
         dev, n_items = rating.device, rating.shape[1]
         rating[self._dense(dl.mask_off, dl.mask_items, users, n_items, dev)] = -(1 << 10)      # evaluate.py:98
         if self.use_item_pool:
-            rating = rating + self._dense(dl.pool_off, dl.pool_items, users, n_items, dev).float() * (1 << 10)
-        kmax = max(self.top_k_list)
+            rating += self._dense(dl.pool_off, dl.pool_items, users, n_items, dev).float() * (1 << 10)
         _, top = torch.topk(rating, k=kmax)
         gt = self._dense(dl.gt_off, dl.gt_items, users, n_items, dev)
-        hits = torch.gather(gt, 1, top).double()                                                # [b, kmax] 0/1
-        n_gt = gt.sum(dim=1).double()
+        return torch.gather(gt, 1, top).double(), gt.sum(dim=1).double()
+
+    def evaluate_batch(self, batch_users_tensor: torch.Tensor, batch_users_list: list, batch_users_ground_truth=None,
+                       force_host: bool = False):
+        users = np.asarray(batch_users_list, dtype=np.int64)
+        with torch.no_grad():
+            rating = self.model.predict(batch_users_tensor).clone()
+        dev = rating.device
+        kmax = max(self.top_k_list)
+        if rating.is_cuda and not force_host:
+            hits, n_gt = self._hits_device(rating.contiguous(), batch_users_tensor.to(dev), kmax)
+        else:
+            hits, n_gt = self._hits_host(rating, users, kmax)                                   # [b, kmax] 0/1
         disc = 1.0 / torch.log2(torch.arange(2, kmax + 2, device=dev, dtype=torch.float64))
         pre, rec, ndcg = [], [], []
         for k in self.top_k_list:

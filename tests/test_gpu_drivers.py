@@ -85,3 +85,31 @@ def test_implicit_driver_main_synthetic():
     best, idx = drv.main(dev, drv.MODEL_CONFIG, tc, drv.EVALUATE_CONFIG, loader, 17373331, silent=True, auto=True,
                          query=False)
     assert 0.0 <= best <= 1.0 and len(idx) >= 1
+
+
+def test_implicit_evaluator_device_path_equals_host_path_with_item_pool():
+    """invpref_mask_scores / invpref_hits_from_csr (CSR lists resident on the device) against the dense-mask
+    path that tests/test_ref_loaders_evaluators.py pins to the live reference, with the item pool on."""
+    from invpref_kdd_2022_b200.dataloader import YahooImplicitBCELossDataLoader, _csr, synthetic_interactions
+    from invpref_kdd_2022_b200.evaluate import ImplicitTestManager
+    from invpref_kdd_2022_b200.models import InvPrefImplicit
+    dev = torch.device("cuda:0")
+    tr = synthetic_interactions(300, 211, 9000, True, seed=5)
+    te = synthetic_interactions(300, 211, 1500, True, seed=6)
+    te = te[te[:, 2] > 0]
+    loader = YahooImplicitBCELossDataLoader("", dev, train=tr, test=te)
+    pool = synthetic_interactions(300, 211, 6000, True, seed=7)
+    loader.has_item_pool = True
+    loader.pool_off, loader.pool_items = _csr(pool[:, 0], pool[:, 1], loader.user_num)
+    torch.manual_seed(1)
+    model = InvPrefImplicit(loader.user_num, loader.item_num, 2, 24).to(dev)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(30.0)
+    for use_pool in (False, True):
+        ev = ImplicitTestManager(model, loader, test_batch_size=64, top_k_list=[10, 3, 5], use_item_pool=use_pool)
+        users_t, users_l = loader.all_test_users_by_sorted_tensor, loader.all_test_users_by_sorted_list
+        a = ev.evaluate_batch(users_t, users_l)
+        b = ev.evaluate_batch(users_t, users_l, force_host=True)
+        for m in ("ndcg", "recall", "precision"):
+            assert np.allclose(a[m], b[m], rtol=0, atol=1e-9), (use_pool, m, a[m], b[m])
