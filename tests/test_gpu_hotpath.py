@@ -180,6 +180,30 @@ def test_cluster_without_random_sort_and_hist_only():
     assert np.array_equal(hp.env_hist(new).cpu().numpy(), hist.cpu().numpy())
 
 
+@pytest.mark.parametrize("implicit,K,D", [(False, 2, 64), (True, 4, 64), (False, 6, 64), (True, 8, 64), (False, 3, 64),
+                                          (True, 5, 40), (False, 7, 128), (True, 2, 30), (False, 4, 17)])
+def test_cluster_matches_oracle_all_geometries(implicit, K, D):
+    """EM re-assignment (with the tie-break table and the diff count) on every vector geometry and env capacity,
+    including the compile-time (D = 64, K = KT) instantiations and the global-memory eps table (K > 6)."""
+    from invpref_kdd_2022_b200.engine import HotPath
+    U, I, N = 800, 120, 30011
+    u, i, y, e, w, p = _synthetic(U, I, N, K, D, implicit, 5 * K + D)
+    if implicit:
+        y = (y > 0).astype(np.float32)
+    hp = HotPath({k: torch.tensor(v, device=dev()) for k, v in p.items()}, implicit, False, True, lr=1e-2)
+    t = lambda a: torch.tensor(a, device=dev())
+    eps = on.init_eps(K)
+    pidx = np.random.default_rng(K).integers(0, eps.shape[0], N)
+    new, hist, diff = hp.cluster(t(u), t(i), t(y), t(pidx), t(eps), t(e))
+    ref, dist = on.cluster_batch(p, u, i, y, on.Flags(implicit, False, True), pidx, eps)
+    new = new.cpu().numpy()
+    mism = new != ref
+    assert not (mism & ~on.near_tie_mask(dist)).any(), int(mism.sum())
+    assert mism.sum() <= 0.02 * N
+    assert np.array_equal(hist.cpu().numpy(), np.bincount(new, minlength=K))
+    assert int(diff) == int((new != e).sum())
+
+
 @pytest.mark.parametrize("B,rows", [(0, 10), (1, 1), (1000, 7), (50000, 300), (200000, 1 << 20), (4096, 4096)])
 def test_build_segments_bit_exact(B, rows):
     """perm must be bit-equal to torch.sort(stable=True)."""
@@ -219,6 +243,13 @@ def _synthetic(U, I, N, K, D, implicit, seed):
     (False, 3, 17, 100, 50, 3000),       # odd D (scalar loads)
     (False, 8, 256, 50, 60, 2000),       # maximum K and D
     (True, 1, 8, 20, 20, 500),           # single environment
+    # D = 64: the compile-time (D, K) instantiations for K = 2, 6, 8 (K = 4 is the first case) and, with K = 3 / 5,
+    # the generic-shape instantiations of the staged / ring kernels at the same row width
+    (True, 2, 64, 900, 60, 20000),
+    (False, 6, 64, 2500, 30, 50000),
+    (True, 8, 64, 300, 500, 12000),
+    (False, 3, 64, 700, 80, 15000),
+    (True, 5, 64, 400, 25, 30000),
 ])
 def test_train_step_matches_oracle_all_geometries(implicit, K, D, U, I, N):
     """Step vs the fp64 numpy oracle on shapes the fixtures do not cover: long (chunked) segments, every
