@@ -9,7 +9,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from invpref_kdd_2022_b200.parallel import DistDriver, ItemRoute, build_route_gen  # noqa: E402
+from invpref_kdd_2022_b200.parallel import DistDriver, ItemRoute, build_pos_table, build_route_gen  # noqa: E402
 
 
 def main():
@@ -52,7 +52,45 @@ def main():
 
     drv.run(red())
     ok_back = bool(torch.equal(gshard[:, 0], present[rank::world]))
-    print(json.dumps({"rank": rank, "fetch": ok_fetch, "back": ok_back, "n_cache": route.n_cache,
+
+    # ---- the peer-memory exchange's host-side tables, with "peer memory" emulated by all_gather ----
+    def gather_padded(t, rows_max):
+        pad = torch.zeros((rows_max,) + tuple(t.shape[1:]), dtype=t.dtype)
+        pad[:t.shape[0]] = t
+        bufs = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad)
+        return bufs
+
+    rows_max = (n_items + world - 1) // world
+    shards = gather_padded(shard, rows_max)                       # what invpref_fetch_rows_p2p reads
+    cache2 = torch.stack([shards[int(o)][int(r)] for o, r in zip(route.slot_owner.tolist(), route.want_rows.tolist())]) \
+        if route.n_cache else torch.zeros((0, dim))
+    ok_fetch_p2p = bool(torch.equal(cache2, cache))
+    # every rank's partial-gradient cache holds (rank + 1) in each cached row; the owner pulls through pos[p, j]
+    gcaches = gather_padded(torch.full((route.n_cache, dim), float(rank + 1)), n_items)
+    pos = build_pos_table(route, world, shard.shape[0])
+    pulled = torch.zeros_like(shard)
+    for p in range(world):
+        sl = pos[p].long()
+        has = sl >= 0
+        pulled[has] += gcaches[p][sl[has]]
+    # the same through the collective path: requesters send (rank + 1) for each cached row
+    recv2 = torch.zeros((int(route.send_rows.numel()), dim))
+
+    def back2():
+        yield ("all_to_all", recv2, torch.full((route.n_cache, dim), float(rank + 1)), route.send_splits,
+               route.recv_splits)
+
+    drv.run(back2())
+    want = torch.zeros_like(shard)
+    o = 0
+    for p in range(world):
+        n = route.send_splits[p]
+        want[route.send_rows[o:o + n]] += recv2[o:o + n]
+        o += n
+    ok_pull_p2p = bool(torch.equal(pulled, want))
+    print(json.dumps({"rank": rank, "fetch": ok_fetch, "back": ok_back, "fetch_p2p": ok_fetch_p2p,
+                      "pull_p2p": ok_pull_p2p, "n_cache": route.n_cache,
                       "recv": route.recv_splits, "send": route.send_splits}), flush=True)
     dist.destroy_process_group()
 
