@@ -137,9 +137,13 @@ int invpref_plan_bytes(const invpref_desc* desc, int64_t max_batch, size_t* out_
 /* ---- sort-segment plan ------------------------------------------------------------------
  * Replaces the duplicate handling of embedding_dense_backward (autograd of models.py:449-455):
  * a STABLE sort of the batch by user id and by item id, unique rows and segment offsets, the
- * split of long segments into fixed chunks, and a bitmap of touched rows.  A plan depends only
- * on (users, items) of the batch, which utils.mini_batch keeps fixed across epochs, so a
- * trainer builds it once per batch and reuses it. */
+ * split of long segments into fixed chunks, a bitmap of touched rows, one 32-byte descriptor per
+ * segment (row, bounds, the indices of its first two interactions) and cost-balanced contiguous
+ * segment ranges -- what the staged kernels need to request their data one step ahead.  The layout
+ * is private to the library (opaque bytes, invpref_plan_bytes).  A plan depends only on (users,
+ * items) of the batch, which utils.mini_batch keeps fixed across epochs, so a trainer builds it
+ * once per batch and reuses it; it only touches the sort scratch of `ws`, which a train step that
+ * is GIVEN a plan never uses, so the next batch's plan may be built on another stream meanwhile. */
 int invpref_build_plan(const invpref_desc* desc, const int64_t* users, const int64_t* items, int64_t B,
                        void* plan, size_t plan_bytes, void* ws, size_t ws_bytes, void* stream);
 
