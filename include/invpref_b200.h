@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define INVPREF_ABI_VERSION 1
+#define INVPREF_ABI_VERSION 2
 #define INVPREF_MAX_ENVS 8      /* drivers use K = 2, 4, 5, 6 */
 #define INVPREF_MAX_DIM 256     /* drivers use D = 30, 40; synthetic config D = 64 */
 #define INVPREF_NUM_LOSSES 6    /* train.py:836-843: invariant, env_aware, envs, L2, L1, loss */
@@ -134,6 +134,11 @@ int invpref_workspace_bytes(const invpref_desc* desc, int64_t max_batch, size_t*
 /* Bytes of one batch plan (both sort orders, see invpref_build_plan). */
 int invpref_plan_bytes(const invpref_desc* desc, int64_t max_batch, size_t* out_bytes);
 
+/* 1 if this shape runs the fused user pass (required by lazy Adam: invpref_adam.user_last_step), 0 if the
+ * shape only has the unfused path (K * D too large for the per-CTA dE/dW slices), negative = invpref_status.
+ * Callers that default to lazy Adam ask first and fall back to plain dense Adam. */
+int invpref_upass_supported(const invpref_desc* desc);
+
 /* ---- sort-segment plan ------------------------------------------------------------------
  * Replaces the duplicate handling of embedding_dense_backward (autograd of models.py:449-455):
  * a STABLE sort of the batch by user id and by item id, unique rows and segment offsets, the
@@ -146,6 +151,20 @@ int invpref_plan_bytes(const invpref_desc* desc, int64_t max_batch, size_t* out_
  * is GIVEN a plan never uses, so the next batch's plan may be built on another stream meanwhile. */
 int invpref_build_plan(const invpref_desc* desc, const int64_t* users, const int64_t* items, int64_t B,
                        void* plan, size_t plan_bytes, void* ws, size_t ws_bytes, void* stream);
+
+/* Id validation.  The reference raises IndexError (CPU) / a device-side assert (CUDA) on an id outside its
+ * table (nn.Embedding, models.py:449-455).  invpref_build_plan clamps such ids so that no kernel reads out of
+ * bounds and records the fact in the plan; invpref_plan_status reads that record back: it SYNCHRONISES the
+ * stream (the only entry point besides invpref_profile_read that does) and returns INVPREF_ERR_ID_RANGE if any
+ * user or item id of the batch was outside its table.  Call it once after building a cached plan. */
+int invpref_plan_status(const invpref_desc* desc, const void* plan, int64_t B, void* stream);
+
+/* Asynchronous validation for the entry points that take raw ids without a plan (invpref_forward,
+ * invpref_predict, invpref_cluster): ORs into the device word *flag (int32, caller-zeroed) bit 0 if a user id,
+ * bit 1 if an item id, bit 2 if an env id of [0, B) is outside [0, n_users) / [0, n_items) / [0, n_envs).
+ * Any of the three id pointers may be NULL. */
+int invpref_check_ids(const invpref_desc* desc, const int64_t* users, const int64_t* items, const int64_t* envs,
+                      int64_t B, int32_t* flag, void* stream);
 
 /* Stand-alone segment builder with int64 outputs, for callers/tests that want the raw result:
  * perm is bit-equal to torch.sort(ids, stable=True).indices; seg_row[0..n_seg) are the unique

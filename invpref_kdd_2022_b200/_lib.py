@@ -25,7 +25,8 @@ EXPORTS = (
     "invpref_env_hist", "invpref_launch_count", "invpref_profile_enable", "invpref_profile_steps",
     "invpref_profile_read", "invpref_adam_dense", "invpref_gather_rows", "invpref_scatter_add_rows",
     "invpref_user_sweep", "invpref_flush_users", "invpref_fetch_rows_p2p", "invpref_owner_adam_p2p",
-    "invpref_mask_scores", "invpref_hits_from_csr",
+    "invpref_mask_scores", "invpref_hits_from_csr", "invpref_upass_supported", "invpref_plan_status",
+    "invpref_check_ids",
 )
 # execution order; on the fused path "forward" is empty and chunks_users / rows_users are the fused user pass
 PHASES = ("plan", "forward", "chunks_users", "rows_users", "chunks_items", "rows_items", "sweep_items",
@@ -83,6 +84,9 @@ def load() -> C.CDLL:
     lib.invpref_workspace_bytes.argtypes = [C.POINTER(Desc), i64, C.POINTER(sz)]
     lib.invpref_plan_bytes.argtypes = [C.POINTER(Desc), i64, C.POINTER(sz)]
     lib.invpref_build_plan.argtypes = [C.POINTER(Desc), vp, vp, i64, vp, sz, vp, sz, vp]
+    lib.invpref_upass_supported.argtypes = [C.POINTER(Desc)]
+    lib.invpref_plan_status.argtypes = [C.POINTER(Desc), vp, i64, vp]
+    lib.invpref_check_ids.argtypes = [C.POINTER(Desc), vp, vp, vp, i64, vp, vp]
     lib.invpref_build_segments.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]
     lib.invpref_forward.argtypes = [C.POINTER(Desc), C.POINTER(Params), vp, vp, vp, i64, vp, vp, vp, vp]
     lib.invpref_predict.argtypes = [C.POINTER(Desc), C.POINTER(Params), vp, vp, i64, vp, vp]
@@ -114,9 +118,15 @@ def load() -> C.CDLL:
     return lib
 
 
+ABI_VERSION = 2
+ERR_ID_RANGE = -7
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().invpref_strerror(rc).decode()
+        if rc == ERR_ID_RANGE:          # what the reference's nn.Embedding raises on CPU (models.py:449-455)
+            raise IndexError(f"libinvpref_b200 {what}: {msg} (status {rc})")
         raise RuntimeError(f"libinvpref_b200 {what}: {msg} (status {rc})")
 
 

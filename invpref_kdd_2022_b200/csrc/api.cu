@@ -166,6 +166,40 @@ int invpref_build_plan(const invpref_desc* desc, const int64_t* users, const int
     return build_plan_impl(desc, users, items, B, (char*)plan, w.sort_tmp, w.sort_tmp_bytes, (cudaStream_t)stream);
 }
 
+int invpref_upass_supported(const invpref_desc* desc) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    return use_fused_user_pass(g) ? 1 : 0;
+}
+
+int invpref_plan_status(const invpref_desc* desc, const void* plan, int64_t B, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if (!plan || B < 0 || B > 0x7fffffffLL) return INVPREF_ERR_BAD_ARG;
+    PlanSide pu, pi;
+    carve_plan(desc, B, (char*)plan, &pu, &pi);
+    int32_t cu[4] = {0, 0, 0, 0}, ci[4] = {0, 0, 0, 0};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemcpyAsync(cu, pu.counters, sizeof(cu), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(ci, pi.counters, sizeof(ci), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess)
+        return INVPREF_ERR_CUDA;
+    return (cu[2] || ci[2]) ? INVPREF_ERR_ID_RANGE : INVPREF_OK;
+}
+
+int invpref_check_ids(const invpref_desc* desc, const int64_t* users, const int64_t* items, const int64_t* envs,
+                      int64_t B, int32_t* flag, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if (B < 0 || !flag) return INVPREF_ERR_BAD_ARG;
+    if (B == 0 || (!users && !items && !envs)) return INVPREF_OK;
+    return launch_check_ids(users, items, envs, B, desc->n_users, desc->n_items, desc->n_envs, flag,
+                            (cudaStream_t)stream);
+}
+
 int invpref_build_segments(const int64_t* ids, int64_t B, int64_t n_rows, int64_t* perm, int64_t* seg_row,
                            int64_t* seg_off, int64_t* n_seg, void* ws, size_t ws_bytes, void* stream) {
     if (B < 0 || B > 0x7fffffffLL || n_rows < 1 || n_rows > 0x7fffffffLL || !ws || !seg_off || !n_seg ||

@@ -686,7 +686,7 @@ int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stre
         const int grid = (int)(need < 1 ? 1 : (need < 148 * 3 ? need : 148 * 3));
 #define LAUNCH(KERNEL)                                                                                           \
     do {                                                                                                         \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        INVPREF_SET_SMEM_ONCE(KERNEL, smem);                                                                     \
         KERNEL<<<grid, BLOCK, smem, stream>>>(a);                                                                \
     } while (0)
 #define CALL(V, N, KX_)                                                                                          \
@@ -733,7 +733,7 @@ int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream
         const int long_len = 2 * chunk_for(a.plan.B);
 #define LAUNCH(KERNEL)                                                                                           \
     do {                                                                                                         \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        INVPREF_SET_SMEM_ONCE(KERNEL, smem);                                                                     \
         KERNEL<<<grid, BLOCK, smem, stream>>>(a, long_len);                                                      \
     } while (0)
 #define CALL(V, N, KX_)                                                                                          \

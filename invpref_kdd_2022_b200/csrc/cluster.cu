@@ -237,9 +237,7 @@ int launch_cluster(const Geometry& g, const ClusterArgs& a, cudaStream_t stream)
     int grid = (int)(need < 1 ? 1 : (need < 148 * 16 ? need : 148 * 16));
 #define CALL_X(V, N, KT_, X)                                                                                     \
     do {                                                                                                         \
-        if (smem > 48 * 1024)                                                                                    \
-            cudaFuncSetAttribute(cluster_kernel<V, N, KT_, X>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                 (int)smem);                                                                     \
+        INVPREF_SET_SMEM_ONCE((cluster_kernel<V, N, KT_, X>), smem);                                             \
         cluster_kernel<V, N, KT_, X><<<grid, BLOCK, smem, stream>>>(a, eps_rows);                                \
     } while (0)
 #define CALL(V, N, KT_) CALL_X(V, N, KT_, false)

@@ -94,6 +94,17 @@ inline int make_geometry(const invpref_desc* d, Geometry* g) {
 extern long long g_launch_count;   // host-side counter (api.cu)
 inline void count_launch(int n = 1) { g_launch_count += n; }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel instantiation (and again only if a larger size is
+// asked for), not on every launch: each textual expansion owns its static.  One process drives one GPU.
+#define INVPREF_SET_SMEM_ONCE(KERNEL, BYTES)                                                                     \
+    do {                                                                                                         \
+        static int _smem_set = 0;                                                                                \
+        if ((int)(BYTES) > _smem_set) {                                                                          \
+            cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(BYTES));             \
+            _smem_set = (int)(BYTES);                                                                            \
+        }                                                                                                        \
+    } while (0)
+
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 // ---- plan layout (one side = one sort order) ----------------------------------------------

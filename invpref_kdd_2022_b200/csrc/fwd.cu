@@ -376,9 +376,7 @@ int launch_fwd_train(const Geometry& g, const FwdTrainArgs& a, int grid, cudaStr
     size_t smem = (size_t)(4 + GROUPS_PER_BLOCK) * g.K * g.D * sizeof(float);
 #define CALL(V, N, KT_)                                                                                         \
     do {                                                                                                        \
-        if (smem > 48 * 1024)                                                                                   \
-            cudaFuncSetAttribute(fwd_train_kernel<V, N, KT_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                 (int)smem);                                                                    \
+        INVPREF_SET_SMEM_ONCE((fwd_train_kernel<V, N, KT_>), smem);                                             \
         fwd_train_kernel<V, N, KT_><<<grid, BLOCK, smem, stream>>>(a);                                          \
     } while (0)
     INVPREF_DISPATCH_GEOM(g, CALL);

@@ -27,6 +27,21 @@ __global__ void prep_keys_kernel(const int64_t* __restrict__ ids, int64_t B, int
     vals[n] = (int32_t)n;
 }
 
+// invpref_check_ids: bit 0 / 1 / 2 of *flag = some user / item / env id outside its table
+__global__ void __launch_bounds__(256) check_ids_kernel(const int64_t* __restrict__ users,
+                                                        const int64_t* __restrict__ items,
+                                                        const int64_t* __restrict__ envs, int64_t B, int64_t n_users,
+                                                        int64_t n_items, int64_t n_envs, int32_t* __restrict__ flag) {
+    int bad = 0;
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < B; n += (int64_t)gridDim.x * blockDim.x) {
+        if (users != nullptr) { const int64_t u = users[n]; if (u < 0 || u >= n_users) bad |= 1; }
+        if (items != nullptr) { const int64_t i = items[n]; if (i < 0 || i >= n_items) bad |= 2; }
+        if (envs != nullptr) { const int64_t e = envs[n]; if (e < 0 || e >= n_envs) bad |= 4; }
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (bad != 0 && (threadIdx.x & 31) == 0) atomicOr(flag, bad);
+}
+
 __global__ void flag_heads_kernel(const int32_t* __restrict__ sorted, int64_t B, int32_t* __restrict__ flag) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (k >= B) return;
@@ -53,8 +68,10 @@ __global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const 
     }
     if (other_ids != nullptr) {
         int64_t o = other_ids[perm[k]];
-        if (o < 0) o = 0;
-        if (o >= other_rows) o = other_rows - 1;
+        if (o < 0 || o >= other_rows) {
+            p.counters[2] = 1;   // flagged like an out-of-range key (prep_keys_kernel), clamped
+            o = o < 0 ? 0 : other_rows - 1;
+        }
         p.partner[k] = (int32_t)o;
     }
 }
@@ -206,6 +223,15 @@ int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_
                                                                                        other_ids != nullptr);
     write_ranges_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B) / 2, (int)plan_ranges(B));
     count_launch(6 + 6);   // 6 of ours + CUB's (radix passes, 2 scans; approximate)
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_check_ids(const int64_t* users, const int64_t* items, const int64_t* envs, int64_t B, int64_t n_users,
+                     int64_t n_items, int64_t n_envs, int32_t* flag, cudaStream_t stream) {
+    const int64_t need = (B + 255) / 256;
+    const int grid = (int)(need < 1 ? 1 : (need < 148 * 8 ? need : 148 * 8));
+    check_ids_kernel<<<grid, 256, 0, stream>>>(users, items, envs, B, n_users, n_items, n_envs, flag);
+    count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 

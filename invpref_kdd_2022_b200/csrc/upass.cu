@@ -288,7 +288,7 @@ int launch_upass_rows(const Geometry& g, const UserPassArgs& a, int epi, int gri
         const int long_len = 2 * chunk_for(a.side.plan.B);   // plan.cu: segments longer than this are chunked
 #define LAUNCH(KERNEL)                                                                                           \
     do {                                                                                                         \
-        cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                    \
+        INVPREF_SET_SMEM_ONCE(KERNEL, smem);                                                                     \
         KERNEL<<<grid, BLOCK, smem, stream>>>(a, long_len);                                                      \
     } while (0)
 #define CALL_X(V, N, KT_, X)                                                                                     \

@@ -184,7 +184,7 @@ int launch_upass_chunks(const Geometry& g, const UserPassArgs& a, int cta_offset
     const bool lazy = a.side.last_step != nullptr;
 #define LAUNCH(KERNEL)                                                                                           \
     do {                                                                                                         \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        INVPREF_SET_SMEM_ONCE(KERNEL, smem);                                                                     \
         KERNEL<<<UPASS_CHUNK_CTAS, BLOCK, smem, stream>>>(a, cta_offset);                                        \
     } while (0)
 #define CALL(V, N, KT_)                                                                                          \
@@ -204,7 +204,7 @@ int launch_upass_rows_regs(const Geometry& g, const UserPassArgs& a, int epi, in
     const size_t smem = upass_smem(g);
 #define LAUNCH(KERNEL)                                                                                           \
     do {                                                                                                         \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        INVPREF_SET_SMEM_ONCE(KERNEL, smem);                                                                     \
         KERNEL<<<grid, BLOCK, smem, stream>>>(a);                                                                \
     } while (0)
 #define CALL(V, N, KT_)                                                                                          \

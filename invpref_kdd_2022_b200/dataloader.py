@@ -67,9 +67,13 @@ class YahooImplicitBCELossDataLoader:
         # test users ascending (utils.py:228-233 sorts the user list)
         self.test_user_list = np.unique(te[:, 0]).tolist()
         self.test_users_tensor = torch.LongTensor(self.test_user_list).to(device)
-        if has_item_pool_file:
-            pool = _read_csv(os.path.join(dataset_path, "test_item_pool.csv"))
-            self.pool_off, self.pool_items = _csr(pool[:, 0], pool[:, 1], self._user_num)
+        if has_item_pool_file and train is None:
+            self.set_item_pool(_read_csv(os.path.join(dataset_path, "test_item_pool.csv")))
+
+    def set_item_pool(self, pool: np.ndarray):
+        """pool: int [n, >=2] (user_id, item_id) rows of test_item_pool.csv (dataloader.py:168-176)."""
+        self.has_item_pool = True
+        self.pool_off, self.pool_items = _csr(pool[:, 0], pool[:, 1], self._user_num)
 
     def _row(self, off, items, user_id):
         return set(items[off[user_id]:off[user_id + 1]].tolist())
@@ -97,6 +101,14 @@ class YahooImplicitBCELossDataLoader:
     @property
     def get_sorted_all_test_users_ground_truth(self) -> list:
         return [self.get_user_ground_truth(u) for u in self.test_user_list]
+
+
+def synthetic_item_pool(test: np.ndarray, n_users: int, n_items: int, extra: int = 50, seed: int = 11) -> np.ndarray:
+    """A stand-in for test_item_pool.csv on synthetic data: per test user its test items plus `extra` random ones."""
+    rng = np.random.default_rng(seed)
+    users = np.unique(test[:, 0])
+    rnd = np.stack([np.repeat(users, extra), rng.integers(0, n_items, users.size * extra)], axis=1)
+    return np.concatenate([test[:, :2], rnd]).astype(np.int64)
 
 
 def synthetic_interactions(n_users, n_items, n, implicit, seed=20220814):

@@ -29,13 +29,16 @@ RANDOM_SEED_LIST = [17373331, 17373511, 17373423]
 
 DATASET_PATH = '/MIND_all_data/'
 METRIC_LIST = ['ndcg', 'recall', 'precision']
+USE_ITEM_POOL = True            # MIND_InvPref.py:87, :201: evaluator ranks only the test item pool
+HAS_ITEM_POOL_FILE = True       # loader reads test_item_pool.csv
 SHAPE = (50000, 51283, 4194304)          # (users, items, train interactions) of the dataset this config was tuned on
 
 
 def main(device, model_config: dict, train_config: dict, evaluate_config: dict, data_loader, random_seed: int,
          silent: bool = False, auto: bool = False, query: bool = True):
     return _common.run_main(True, device, model_config, train_config, evaluate_config, data_loader,
-                            random_seed, silent=silent, auto=auto, query=query, metric_list=METRIC_LIST)
+                            random_seed, silent=silent, auto=auto, query=query, metric_list=METRIC_LIST,
+                            use_item_pool=USE_ITEM_POOL)
 
 
 if __name__ == '__main__':

@@ -29,13 +29,16 @@ RANDOM_SEED_LIST = [17373331, 17373511, 17373423]
 
 DATASET_PATH = '/MovieLens_all_data_thr_3/'
 METRIC_LIST = ['ndcg', 'recall', 'precision']
+USE_ITEM_POOL = False            # MovieLens_InvPref.py:90, :204: evaluator ranks all items
+HAS_ITEM_POOL_FILE = False       # loader reads test_item_pool.csv
 SHAPE = (6040, 3706, 1000000)          # (users, items, train interactions) of the dataset this config was tuned on
 
 
 def main(device, model_config: dict, train_config: dict, evaluate_config: dict, data_loader, random_seed: int,
          silent: bool = False, auto: bool = False, query: bool = True):
     return _common.run_main(True, device, model_config, train_config, evaluate_config, data_loader,
-                            random_seed, silent=silent, auto=auto, query=query, metric_list=METRIC_LIST)
+                            random_seed, silent=silent, auto=auto, query=query, metric_list=METRIC_LIST,
+                            use_item_pool=USE_ITEM_POOL)
 
 
 if __name__ == '__main__':

@@ -23,7 +23,10 @@ def default_device() -> torch.device:
 
 
 def run_main(implicit, device, model_config, train_config, evaluate_config, data_loader, random_seed,
-             silent=False, auto=False, query=True, metric_list=None):
+             silent=False, auto=False, query=True, metric_list=None, use_item_pool=False):
+    """``use_item_pool``: rank only the test item pool (Yahoo_InvPref_Implicit.py:87 and MIND_InvPref.py:87 pass
+    True, MovieLens_InvPref.py:90 False).  Returns ``(best, best_indexes, result_at_best)`` like the reference
+    mains (explicit: ``{metric: value}``; implicit: ``{'metric@k': value}``, utils.py:191-198)."""
     torch.manual_seed(random_seed)                      # seeding order as the reference (:68-71)
     torch.cuda.manual_seed(random_seed)
     torch.cuda.manual_seed_all(random_seed)
@@ -35,7 +38,7 @@ def run_main(implicit, device, model_config, train_config, evaluate_config, data
     if implicit:
         evaluator = ImplicitTestManager(model=model, data_loader=data_loader,
                                         test_batch_size=evaluate_config['test_batch_size'],
-                                        top_k_list=evaluate_config['top_k_list'], use_item_pool=False)
+                                        top_k_list=evaluate_config['top_k_list'], use_item_pool=use_item_pool)
     else:
         evaluator = ExplicitTestManager(model=model, data_loader=data_loader)
     train_tensor = torch.LongTensor(data_loader.train_data_np).to(device)
@@ -74,8 +77,13 @@ def run_main(implicit, device, model_config, train_config, evaluate_config, data
             f.write('rand seed: ' + str(random_seed) + '\n')
             for cfg in (model_config, train_config, evaluate_config):
                 f.write(json.dumps(cfg, indent=4) + '\n')
-    if implicit:
-        return best, best_indexes
+    if implicit:                                                        # utils.py:191-198
+        result = {}
+        for m in (metric_list or ['ndcg', 'recall', 'precision']):
+            by_k = merge_dict(merged[m], _show_me_a_list_func)
+            for kk in evaluate_config['top_k_list']:
+                result[f'{m}@{kk}'] = by_k[kk][best_indexes[0]]
+        return best, best_indexes, result
     result = {m: merged[m][best_indexes[0]] for m in (metric_list or ['mse', 'rmse', 'mae'])}
     return best, best_indexes, result
 
@@ -104,6 +112,12 @@ def cli(module, implicit, shape=None):
         if implicit:
             te = te[te[:, 2] > 0]
         loader = Loader(path, device, train=tr, test=te)
+        if implicit and getattr(module, 'HAS_ITEM_POOL_FILE', False):
+            # synthetic stand-in for test_item_pool.csv: every test user's pool = its test positives + random items
+            loader.set_item_pool(dl.synthetic_item_pool(te, U, I))
+    elif implicit:
+        loader = Loader(dataset_path=path, device=device,
+                        has_item_pool_file=getattr(module, 'HAS_ITEM_POOL_FILE', False))
     else:
         loader = Loader(dataset_path=path, device=device)
     bests = []

@@ -53,7 +53,12 @@ class HotPath:
         self._ws = None
         self._ws_batch = -1
         self.loss_buf = torch.zeros(6, dtype=torch.float32, device=self.device)
-        self.lazy = bool(lazy)
+        # lazy Adam needs the fused user pass; shapes that only have the unfused path (K * D too large for the
+        # per-CTA dE/dW slices, or INVPREF_FUSED=0) run plain dense Adam -- same results, more HBM traffic
+        self.lazy_supported = self.lib.invpref_upass_supported(C.byref(self.desc)) == 1
+        self.lazy_requested = bool(lazy)
+        self.lazy = bool(lazy) and self.lazy_supported
+        self.id_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.last_step = None        # int32 [n_users]
         self.sched = None            # fp32 [cap, 2]
         self._dirty = False          # some user rows are behind self.step
@@ -92,6 +97,8 @@ class HotPath:
         self.sched[t, 1] = 1.0 / math.sqrt(bc2)
 
     def set_lazy(self, lazy: bool):
+        self.lazy_requested = bool(lazy)
+        lazy = bool(lazy) and self.lazy_supported
         if bool(lazy) == self.lazy:
             return
         self.flush()
@@ -160,6 +167,33 @@ class HotPath:
     def plan_bytes(self, batch: int) -> int:
         return _lib.plan_bytes(self.desc, batch)
 
+    def plan_status(self, plan: torch.Tensor, B: int) -> None:
+        """Raises IndexError if a user / item id of the batch the plan was built for is outside its table
+        (``invpref_plan_status``; synchronises -- call it once per cached plan, not per step)."""
+        _lib.check(self.lib.invpref_plan_status(C.byref(self.desc), _lib.ptr(plan), int(B), _lib.stream_ptr()),
+                   "plan_status")
+
+    def check_ids(self, users=None, items=None, envs=None, sync: bool = True) -> None:
+        """``invpref_check_ids``: the reference's nn.Embedding raises on an id outside its table; here the ids are
+        validated by one small kernel.  ``sync=True`` reads the flag back and raises IndexError; ``sync=False``
+        only accumulates into ``self.id_flag`` (read it later with ``raise_if_bad_ids``)."""
+        B = next(t.numel() for t in (users, items, envs) if t is not None)
+        _lib.check(self.lib.invpref_check_ids(
+            C.byref(self.desc), _lib.ptr(users, torch.int64) if users is not None else None,
+            _lib.ptr(items, torch.int64) if items is not None else None,
+            _lib.ptr(envs, torch.int64) if envs is not None else None, B, _lib.ptr(self.id_flag, torch.int32),
+            _lib.stream_ptr()), "check_ids")
+        if sync:
+            self.raise_if_bad_ids()
+
+    def raise_if_bad_ids(self) -> None:
+        f = int(self.id_flag.item())
+        if f:
+            self.id_flag.zero_()
+            what = [n for b, n in ((1, "user"), (2, "item"), (4, "env")) if f & b]
+            raise IndexError(f"index out of range in self: {' / '.join(what)} id outside its embedding table "
+                             f"(users {self.n_users}, items {self.n_items}, envs {self.n_envs})")
+
     # ---- fused train step ---------------------------------------------------------------------
     def train_step(self, users, items, scores, envs, weights, *, c_inv, c_ea, c_env, c_L2, c_L1, alpha,
                    use_class_rw, use_rec_rw, plan: Optional[torch.Tensor] = None,
@@ -220,7 +254,11 @@ class HotPath:
                    "user_sweep")
 
     # ---- forward / backward (autograd-compatible path) ----------------------------------------
-    def forward(self, users, items, envs, want_logp=True):
+    def forward(self, users, items, envs, want_logp=True, trusted=False):
+        """``trusted``: the ids were validated before (e.g. the trainer's own tensors, checked at construction);
+        otherwise they are checked first and an IndexError is raised like the reference's embedding lookup."""
+        if not trusted and users.numel():
+            self.check_ids(users, items, envs)
         self.flush()
         B = users.numel()
         s_inv = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -233,7 +271,9 @@ class HotPath:
                    "forward")
         return s_inv, s_env, logp
 
-    def predict(self, users, items):
+    def predict(self, users, items, trusted=False):
+        if not trusted and users.numel():
+            self.check_ids(users, items, None)
         self.flush()
         B = users.numel()
         out = torch.empty(B, dtype=torch.float32, device=self.device)
@@ -257,8 +297,10 @@ class HotPath:
                                              C.byref(g), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "backward")
 
     # ---- EM re-assignment -------------------------------------------------------------------------
-    def cluster(self, users, items, scores, perm_idx, eps_table, old_envs):
+    def cluster(self, users, items, scores, perm_idx, eps_table, old_envs, trusted=False):
         """train.py:846-879 over a whole slice.  Returns (new_envs int64[B], hist int64[K], diff int64[1])."""
+        if not trusted and users.numel():
+            self.check_ids(users, items, None)
         self.flush()
         B = users.numel()
         new_envs = torch.empty(B, dtype=torch.int64, device=self.device)

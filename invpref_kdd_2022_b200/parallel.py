@@ -535,7 +535,7 @@ class ShardedTrainer:
             z = torch.zeros(0, dtype=torch.int64, device=self.dev)
             return z, torch.zeros(self.K, dtype=torch.int64, device=self.dev), torch.zeros(1, dtype=torch.int64,
                                                                                            device=self.dev)
-        return self.hot.cluster(sb.users, sb.route.slots, sb.scores, perm_idx, eps_table, old_envs)
+        return self.hot.cluster(sb.users, sb.route.slots, sb.scores, perm_idx, eps_table, old_envs, trusted=True)
 
     # ---- inspection (tests) -----------------------------------------------------------------------------
     def local_tables(self):

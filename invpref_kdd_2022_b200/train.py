@@ -71,6 +71,9 @@ class _InvPrefTrainManager:
         # HotPath); train_a_epoch flushes at the end of the epoch, train_a_batch after every call
         self.engine = model.hot_path(lr=lr, lazy=lazy_adam)
         self.engine.lr = float(lr)
+        # the reference's nn.Embedding raises IndexError on an id outside its table; validate the whole training
+        # set once here (the kernels below then take these tensors as trusted)
+        self.engine.check_ids(self.users_tensor, self.items_tensor, self.envs)
         self.optimizer = self.engine           # exposes .m / .v / .step (exp_avg, exp_avg_sq, step)
         self.cache_plans = cache_plans
         self._plans = {}
@@ -90,6 +93,7 @@ class _InvPrefTrainManager:
         plan = self._plans.get(key)
         if plan is None:
             plan = self.engine.new_plan(users, items)
+            self.engine.plan_status(plan, users.numel())       # IndexError on an out-of-range id (once per batch)
             self._plans[key] = plan
         return plan
 
@@ -105,10 +109,13 @@ class _InvPrefTrainManager:
     def train_a_batch(self, batch_users_tensor, batch_items_tensor, batch_scores_tensor, batch_envs_tensor,
                       batch_sample_weights, alpha) -> dict:
         """train.py:771-844.  One fused step; returns the six losses as python floats (one sync)."""
+        self.engine.check_ids(batch_users_tensor.contiguous(), batch_items_tensor.contiguous(),
+                              batch_envs_tensor.contiguous(), sync=False)
         out = self._step(batch_users_tensor, batch_items_tensor, batch_scores_tensor, batch_envs_tensor,
                          batch_sample_weights, alpha)
         self.engine.flush()
         vals = out.cpu().tolist()
+        self.engine.raise_if_bad_ids()
         return dict(zip(LOSS_KEYS, vals))
 
     def train_a_epoch(self) -> dict:
@@ -153,7 +160,8 @@ class _InvPrefTrainManager:
                      for lo in range(0, n, self.batch_size)]
             perm = torch.from_numpy(np.concatenate(draws).astype(np.int64)).to(self.device)
         new_envs, hist, diff = self.engine.cluster(self.users_tensor, self.items_tensor, self.scores_tensor, perm,
-                                                   self.eps_random_tensor if perm is not None else None, self.envs)
+                                                   self.eps_random_tensor if perm is not None else None, self.envs,
+                                                   trusted=True)
         self.envs = new_envs
         self._hist = hist
         return int(diff.item())

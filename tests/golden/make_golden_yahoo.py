@@ -1,0 +1,150 @@
+"""Golden fixture at a BASELINE config's NATIVE size: the reference's Yahoo!R3 explicit run
+(Yahoo_InvPref_explicit.py:17-41 -- U 15 400, I 1 000, N 311 704, K 5, D 40, B 131 072, alpha schedule) on the
+real ``dataset/Yahoo_explicit_all_data/train.csv``, executed by the LIVE reference (build container only).
+
+    python tests/golden/make_golden_yahoo.py        ->  tests/golden/yahoo_explicit_full.npz  (~3 MB)
+
+One full epoch (3 steps: 131 072 + 131 072 + 49 560 interactions) of the reference's ExplicitTrainManager on CPU
+in fp32, then cluster() + stat_envs().  To keep the file small the big tensors are sampled: the item tables
+(1 000 rows) are stored whole, the user tables every USER_STRIDE-th row; the fp64 step-0 gradients likewise, plus
+the reference's own fp32-vs-fp64 error per tensor over ALL rows (``grad0_ref_err``), which is what the repository's
+tolerance rule needs.  The initial parameters are not stored: they come from the seeded constructor (bit-equal
+RNG stream, tests/test_gpu_trainer.py) and are pinned here by an integer checksum of their bit patterns.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import ref_shim  # noqa: E402
+from oracle import invpref_numpy as on  # noqa: E402
+
+USER_STRIDE = 32
+CFG = dict(K=5, D=40, B=131072, roe=True, ree=False, lr=1e-3, c_inv=0.007375309563638757,
+           c_ea=7.207790368836971, c_env=7.30272189219841, c_L2=5.105587170019545, c_L1=0.004098813161410509,
+           crw=False, rrw=False, seed=17373331)
+USER_KEYS = ("embed_user_invariant.weight", "embed_user_env_aware.weight")
+
+
+def sample(k, v):
+    return v[::USER_STRIDE].copy() if k in USER_KEYS else v.copy()
+
+
+def bits_checksum(sd):
+    return np.int64(sum(int(np.ascontiguousarray(v).view(np.int32).astype(np.int64).sum()) for v in sd.values()))
+
+
+def main():
+    import pandas as pd
+    torch.set_num_threads(8)
+    ref = ref_shim.load()
+    cfg = CFG
+    data = pd.read_csv(os.path.join(ref_shim.REF_ROOT, "dataset", "Yahoo_explicit_all_data", "train.csv")).values
+    data = data.astype(np.int64)
+    U, I, N = int(data[:, 0].max()) + 1, int(data[:, 1].max()) + 1, len(data)
+    K, D, B = cfg["K"], cfg["D"], cfg["B"]
+
+    def build(double=False):
+        torch.manual_seed(cfg["seed"])
+        np.random.seed(cfg["seed"])
+        model = ref.models.InvPrefExplicit(U, I, K, D, cfg["roe"], cfg["ree"])
+        if double:
+            model = model.double()
+        tm = ref.train.ExplicitTrainManager(
+            model=model, evaluator=ref_shim.NullEvaluator(), device=torch.device("cpu"),
+            training_data=torch.LongTensor(data), batch_size=B, epochs=1, cluster_interval=1, evaluate_interval=1,
+            lr=cfg["lr"], invariant_coe=cfg["c_inv"], env_aware_coe=cfg["c_ea"], env_coe=cfg["c_env"],
+            L2_coe=cfg["c_L2"], L1_coe=cfg["c_L1"], alpha=None, use_class_re_weight=cfg["crw"],
+            use_recommend_re_weight=cfg["rrw"])
+        tm.stat_envs()
+        return model, tm
+
+    out = {"users": data[:, 0].astype(np.int16), "items": data[:, 1].astype(np.int16),
+           "scores": data[:, 2].astype(np.int8), "meta_keys": np.array(sorted(cfg)),
+           "meta_vals": np.array([str(cfg[k]) for k in sorted(cfg)]), "user_stride": np.int64(USER_STRIDE)}
+    model, tm = build()
+    sd0 = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+    out["init_checksum"] = bits_checksum(sd0)
+    out["envs0"] = tm.envs.numpy().astype(np.int8)
+    out["class_weights0"] = tm.class_weights.numpy().copy()
+
+    # step-0 gradients: fp64 truth (sampled rows) and the reference's own fp32 error against it (all rows)
+    alpha0 = on.alpha_schedule(0, 0, tm.batch_num)
+    out["alpha0"] = np.float64(alpha0)
+    sl = slice(0, B)
+    md, tmd = build(double=True)
+    tmd.train_a_batch(tmd.users_tensor[sl], tmd.items_tensor[sl], tmd.scores_tensor[sl].double(), tmd.envs[sl],
+                      tmd.sample_weights[sl].double(), alpha0)
+    g64 = {k: p.grad.numpy().copy() for k, p in md.named_parameters()}
+
+    losses = []
+    orig = tm.train_a_batch
+    ref_err = {}
+
+    def spy(**kw):
+        ld = orig(**kw)
+        losses.append([ld[k] for k in on.LOSS_KEYS])
+        if len(losses) == 1:
+            for k, p in model.named_parameters():
+                g32 = p.grad.numpy()
+                ref_err[k] = float(np.abs(g32.astype(np.float64) - g64[k]).max() / np.abs(g64[k]).max())
+                out["grad0/" + k] = sample(k, g32)
+        return ld
+
+    tm.train_a_batch = spy
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean_ld = tm.train_a_epoch()
+    for k, v in g64.items():
+        out["grad0_f64/" + k] = sample(k, v)
+    out["grad0_ref_err_keys"] = np.array(sorted(ref_err))
+    out["grad0_ref_err"] = np.array([ref_err[k] for k in sorted(ref_err)])
+    out["epoch_losses"] = np.asarray(losses, dtype=np.float64)
+    out["epoch_mean_loss"] = np.asarray([mean_ld[k] for k in on.LOSS_KEYS], dtype=np.float64)
+    for k, v in model.state_dict().items():
+        out["epoch1/" + k] = sample(k, v.detach().numpy())
+
+    # cluster() + stat_envs() on the trained parameters (train.py:912-957)
+    np.random.seed(cfg["seed"] + 1)
+    idx = [np.random.randint(0, tm.eps_random_tensor.shape[0], hi - lo) for lo, hi in on.mini_batch_bounds(N, B)]
+    out["cluster_perm_idx"] = np.concatenate(idx).astype(np.int8)              # K! = 120 rows
+    np.random.seed(cfg["seed"] + 1)
+    diff = tm.cluster()
+    out["cluster_envs"] = tm.envs.numpy().astype(np.int8)
+    out["cluster_diff"] = np.int64(diff)
+    cnt = tm.stat_envs()
+    out["stat_counts"] = np.asarray([cnt[k] for k in range(K)], dtype=np.int64)
+    out["stat_class_weights"] = tm.class_weights.numpy().copy()
+    p = on.params_from_state_dict({k: v.detach().numpy() for k, v in model.state_dict().items()})
+    dist = on.cluster_distances(p, data[:, 0], data[:, 1], data[:, 2], on.Flags(False, cfg["roe"], cfg["ree"]))
+    out["cluster_near_ties"] = np.int64(on.near_tie_mask(dist).sum())
+    # second cluster() with the env-aware tables scaled by 20: at the trained scale 93 % of the samples are fp32
+    # near-ties, here the K distances are separated and the assignments are a real check
+    with torch.no_grad():
+        for t in (model.embed_user_env_aware, model.embed_item_env_aware, model.embed_env):
+            t.weight.mul_(20.0)
+    np.random.seed(cfg["seed"] + 2)
+    out["sep_diff"] = np.int64(tm.cluster())
+    out["sep_envs"] = tm.envs.numpy().astype(np.int8)
+    p = on.params_from_state_dict({k: v.detach().numpy() for k, v in model.state_dict().items()})
+    dist = on.cluster_distances(p, data[:, 0], data[:, 1], data[:, 2], on.Flags(False, cfg["roe"], cfg["ree"]))
+    out["sep_near_ties"] = np.int64(on.near_tie_mask(dist).sum())
+    # samples whose two smallest distances are within 1e-3 relative: the ones a 5e-4 parameter drift may flip
+    srt = np.sort(dist.astype(np.float64), axis=1)
+    out["sep_loose_ties"] = np.int64(((srt[:, 1] - srt[:, 0]) <= 1e-3 * np.maximum(np.abs(srt[:, 1]), 1e-12)).sum())
+    path = os.path.join(HERE, "yahoo_explicit_full.npz")
+    np.savez_compressed(path, **out)
+    print(f"yahoo_explicit_full: U={U} I={I} N={N} steps={len(losses)} diff={diff} "
+          f"near_ties={int(out['cluster_near_ties'])} sep_diff={int(out['sep_diff'])} "
+          f"sep_ties={int(out['sep_near_ties'])} sep_loose={int(out['sep_loose_ties'])} ref_err={ref_err} -> {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

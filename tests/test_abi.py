@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert lib.invpref_abi_version() == 1
+    assert lib.invpref_abi_version() == _lib.ABI_VERSION
     assert lib.invpref_strerror(0) == b"ok"
     assert b"dimension" in lib.invpref_strerror(-1)
 

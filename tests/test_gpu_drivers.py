@@ -80,11 +80,19 @@ def test_implicit_driver_main_synthetic():
     dev = torch.device("cuda:0")
     tr = synthetic_interactions(500, 200, 30000, True, seed=3)
     te = synthetic_interactions(500, 200, 3000, True, seed=4)
-    loader = YahooImplicitBCELossDataLoader("", dev, train=tr, test=te[te[:, 2] > 0])
+    te = te[te[:, 2] > 0]
+    loader = YahooImplicitBCELossDataLoader("", dev, train=tr, test=te)
+    # the reference's Yahoo implicit main ranks only the test item pool (Yahoo_InvPref_Implicit.py:87, :207)
+    assert drv.USE_ITEM_POOL and drv.HAS_ITEM_POOL_FILE
+    from invpref_kdd_2022_b200.dataloader import synthetic_item_pool
+    loader.set_item_pool(synthetic_item_pool(te, 500, 200))
     tc = dict(drv.TRAIN_CONFIG, epochs=6, evaluate_interval=3, cluster_interval=2)
-    best, idx = drv.main(dev, drv.MODEL_CONFIG, tc, drv.EVALUATE_CONFIG, loader, 17373331, silent=True, auto=True,
-                         query=False)
+    best, idx, res = drv.main(dev, drv.MODEL_CONFIG, tc, drv.EVALUATE_CONFIG, loader, 17373331, silent=True,
+                              auto=True, query=False)                 # the reference's 3-tuple
     assert 0.0 <= best <= 1.0 and len(idx) >= 1
+    ks = drv.EVALUATE_CONFIG['top_k_list']
+    assert set(res) == {f"{m}@{k}" for m in ("ndcg", "recall", "precision") for k in ks}
+    assert res[f"{drv.EVALUATE_CONFIG['eval_metric']}@{drv.EVALUATE_CONFIG['eval_k']}"] == best
 
 
 def test_implicit_evaluator_device_path_equals_host_path_with_item_pool():

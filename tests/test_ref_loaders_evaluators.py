@@ -115,3 +115,19 @@ def test_explicit_evaluator_matches_reference(ref):
     assert set(got) == set(want) == {"mse", "rmse", "mae"}
     for k in want:
         assert abs(got[k] - want[k]) <= 1e-6 * abs(want[k]), (k, got[k], want[k])
+
+
+@pytest.mark.parametrize("name", ["Yahoo_InvPref_Implicit", "MIND_InvPref", "MovieLens_InvPref"])
+def test_driver_item_pool_flags_match_reference(name):
+    """Which implicit drivers rank only the test item pool (reference <driver>.py: ImplicitTestManager(...,
+    use_item_pool=...) and YahooImplicitBCELossDataLoader(..., has_item_pool_file=...))."""
+    import importlib
+    import re
+    src = open(os.path.join(ref_shim.REF_ROOT, name + ".py")).read()
+    use = re.search(r"use_item_pool=(True|False)", src).group(1) == "True"
+    has = re.search(r"has_item_pool_file=(True|False)", src).group(1) == "True"
+    drv = importlib.import_module("invpref_kdd_2022_b200.drivers." + name)
+    assert (drv.USE_ITEM_POOL, drv.HAS_ITEM_POOL_FILE) == (use, has)
+    for key in ("MODEL_CONFIG", "TRAIN_CONFIG", "EVALUATE_CONFIG"):
+        blk = re.search(key + r"[^=]*=\s*(\{.*?\n\})", src, flags=re.S).group(1)
+        assert getattr(drv, key) == eval(blk), key
