@@ -39,15 +39,15 @@ WORKLOADS = {
                coef=dict(c_inv=0.007375309563638757, c_ea=7.207790368836971, c_env=7.30272189219841,
                          c_L2=5.105587170019545, c_L1=0.004098813161410509)),
     "c4": dict(name="MIND-shaped synthetic, 50000 x 51283, dim 40, K=6, implicit, B=262144", U=50_000, I=51_283,
-               D=40, K=6, B=262_144, implicit=True, roe=True, ree=False, crw=True, rrw=False, lr=1e-3,
+               D=40, K=6, B=262_144, N=4_194_304, implicit=True, roe=True, ree=False, crw=True, rrw=False, lr=1e-3,
                coef=dict(c_inv=0.41343891722673093, c_ea=9.833594297680568, c_env=7.521558049068597,
                          c_L2=4.324061954456766, c_L1=0.33322012936680223)),
     "c3": dict(name="MovieLens-shaped synthetic, 6040 x 3706, dim 40, K=2, implicit, B=65536", U=6_040, I=3_706,
-               D=40, K=2, B=65_536, implicit=True, roe=True, ree=True, crw=False, rrw=True, lr=1e-2,
+               D=40, K=2, B=65_536, N=1_000_000, implicit=True, roe=True, ree=True, crw=False, rrw=True, lr=1e-2,
                coef=dict(c_inv=8.909348155983732, c_ea=1.233057369609993, c_env=8.064376793624795,
                          c_L2=3.4987474005653665, c_L1=0.9355983539586914)),
     "c2": dict(name="Yahoo!R3-shaped explicit, 15400 x 1000, dim 40, K=5, B=131072", U=15_400, I=1_000,
-               D=40, K=5, B=131_072, implicit=False, roe=True, ree=False, crw=False, rrw=False, lr=1e-3,
+               D=40, K=5, B=131_072, N=311_704, implicit=False, roe=True, ree=False, crw=False, rrw=False, lr=1e-3,
                coef=dict(c_inv=0.007375309563638757, c_ea=7.207790368836971, c_env=7.30272189219841,
                          c_L2=5.105587170019545, c_L1=0.004098813161410509)),
 }
@@ -217,18 +217,110 @@ def torch_eager_gpu(w, dev, dbatch, steps=3):
     return out
 
 
+class _NullEvaluator:
+    def evaluate(self):
+        return {"mse": 0.0}
+
+
+def config_leg(name, dev, with_eager=True):
+    """One of BASELINE.json's dataset-scale configs (C2 Yahoo explicit, C3 MovieLens, C4 MIND) through the PUBLIC
+    trainer API, built as the reference drivers build it: InvPref model + Explicit/ImplicitTrainManager on one
+    synthetic epoch of the config's shape, train_a_epoch() / cluster() / stat_envs().  Tables and
+    interactions are L2-resident: the figure of merit is interactions/s against torch-eager on the same GPU and the
+    launches per step (the trainer replays each epoch as one CUDA graph), not the HBM fraction."""
+    from invpref_kdd_2022_b200 import _lib
+    from invpref_kdd_2022_b200.dataloader import synthetic_interactions
+    from invpref_kdd_2022_b200.models import InvPrefExplicit, InvPrefImplicit
+    from invpref_kdd_2022_b200.train import ExplicitTrainManager, ImplicitTrainManager
+    w = WORKLOADS[name]
+    U, I, N, B, K, D = w["U"], w["I"], w["N"], w["B"], w["K"], w["D"]
+    data = synthetic_interactions(U, I, N, w["implicit"])
+    torch.manual_seed(17373331)
+    np.random.seed(17373331)
+    M, T = (InvPrefImplicit, ImplicitTrainManager) if w["implicit"] else (InvPrefExplicit, ExplicitTrainManager)
+    c = w["coef"]
+
+    def build(use_graph):
+        model = M(U, I, K, D, w["roe"], w["ree"]).to(dev)
+        tm = T(model=model, evaluator=_NullEvaluator(), device=dev, training_data=torch.LongTensor(data).to(dev),
+               batch_size=B, epochs=1, cluster_interval=1, evaluate_interval=1, lr=w["lr"], invariant_coe=c["c_inv"],
+               env_aware_coe=c["c_ea"], env_coe=c["c_env"], L2_coe=c["c_L2"], L1_coe=c["c_L1"], alpha=None,
+               use_class_re_weight=w["crw"], use_recommend_re_weight=w["rrw"], use_graph=use_graph)
+        tm.stat_envs()
+        return tm
+
+    def timed(tm, epochs):
+        for _ in range(3):                       # first epoch builds the plans, second captures the graph(s)
+            tm.train_a_epoch()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(epochs):
+            ld = tm.train_a_epoch()              # one host sync per epoch (the loss rows), as the trainer always does
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / epochs * 1e3
+        assert np.isfinite(ld["loss"])
+        return wall, (_lib.launch_count() - l0) / (epochs * tm.batch_num)
+
+    epochs = max(4, 60 // max(1, -(-N // B)))
+    tm = build(True)
+    g_ms, g_launch = timed(tm, epochs)
+    steps = tm.batch_num
+    tc0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        tm.cluster()
+        tm.stat_envs()
+    torch.cuda.synchronize()
+    cl_ms = (time.perf_counter() - tc0) / reps * 1e3
+    del tm
+    tm = build(False)
+    p_ms, p_launch = timed(tm, epochs)
+    P = 2 * (U + I) * D + 2 * K * D + K
+    leg = {"workload": w["name"], "interactions_per_epoch": N, "steps_per_epoch": steps, "global_batch": B, "params": P,
+           "value": N / (g_ms * 1e-3), "unit": "interactions/s", "ms_per_step": g_ms / steps, "ms_per_epoch": g_ms,
+           "launches_per_step": g_launch, "timing": "wall clock over %d train_a_epoch() calls incl. the per-epoch loss "
+           "read-back; epoch = one CUDA-graph launch" % epochs,
+           "no_graph": {"value": N / (p_ms * 1e-3), "ms_per_step": p_ms / steps, "launches_per_step": p_launch},
+           "cluster": {"value": N / (cl_ms * 1e-3), "unit": "samples/s", "ms": cl_ms,
+                       "note": "trainer.cluster() + stat_envs(): host-drawn tie-break indices (numpy stream, as the "
+                               "reference) + H2D + one kernel + diff read-back"},
+           "roofline_frac_8d": step_bytes(B, D, K, P) * steps / (g_ms * 1e-3) / 1e9 / measured_peaks()[0]}
+    del tm
+    torch.cuda.empty_cache()
+    if with_eager:
+        try:
+            sl = slice(0, B)
+            t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            u, i = t(data[sl, 0]), t(data[sl, 1])
+            y = t(data[sl, 2].astype(np.float32))
+            e = torch.randint(0, K, (B,), device=dev)
+            sw = torch.rand(B, device=dev)
+            eg = torch_eager_gpu(w, dev, (u, i, y, e, sw), steps=5)
+            leg["torch_eager_gpu"] = {"value": eg["value"], "ms_per_step": eg["ms_per_step"],
+                                      "speedup_of_value": leg["value"] / eg["value"]}
+        except Exception as ex:      # noqa: BLE001
+            leg["torch_eager_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+    return leg
+
+
 def run_reference(args, w):
     threads = os.cpu_count() or 1
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     r = cpu_baseline(w, threads, budget_s=150.0, steps=args.steps, warmup=min(args.warmup, 1))
+    scale = min(1.0, 262_144 / w["B"])
+    label = w["name"] if scale >= 1.0 else f"1/{round(1 / scale)}-scale replica (U, I and B divided by " \
+        f"{round(1 / scale)}: bounded CPU sample) of: " + w["name"]
     line = {"impl": "reference", "metric": "train interactions/sec (fwd+bwd+Adam)", "value": r["value"],
             "unit": "interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "global_batch": w["B"],
-                       "params": 2 * (w["U"] + w["I"]) * w["D"] + 2 * w["K"] * w["D"] + w["K"]},
+            "config": {"workload": label, "global_batch": max(int(w["B"] * scale), 8),
+                       "full_size_global_batch": w["B"], "scale": scale,
+                       "params": 2 * (max(int(w["U"] * scale), 8) + max(int(w["I"] * scale), 8)) * w["D"]
+                       + 2 * w["K"] * w["D"] + w["K"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "cluster": {"value": r["cluster_samples_per_s"], "unit": "samples/s"},
             "e2e": {"value": r["value"], "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -242,7 +334,7 @@ def run_ours_single(args, w):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     K, D = w["K"], w["D"]
-    nb = max(1, min(args.nbatch, args.steps + args.warmup))
+    nb = max(1, min(args.nbatch or (args.steps + args.warmup), args.steps + args.warmup))
     U, I, B, batches = synth_batches(w, nb)
     hp = HotPath(make_tables(w, dev), w["implicit"], w["roe"], w["ree"], lr=w["lr"])
     P = sum(t.numel() for t in hp.params.values())
@@ -290,7 +382,9 @@ def run_ours_single(args, w):
 
     peak, peak_src = measured_peaks()
     sbytes = step_bytes(B, D, K, P)
-    n_seg_u = int(plans[0][:4].view(torch.int32)[0].item())          # plan header: unique users of batch 0
+    # unique rows per batch (mean over the distinct batches): what the lazy step actually touches
+    n_seg_u = int(round(np.mean([torch.unique(b[0]).numel() for b in dbatches])))
+    n_seg_i = int(round(np.mean([torch.unique(b[1]).numel() for b in dbatches])))
     # (1) plain dense Adam: every user row is read and written every step
     d_ms, d_ph, d_launch, d_clk = timed(False)
     dense = {"value": B / (d_ms * 1e-3), "unit": "interactions/s", "ms_per_step": d_ms,
@@ -302,12 +396,19 @@ def run_ours_single(args, w):
                                  "achieved": a, "frac": a / peak}
     # (2) headline: lazy dense Adam (bit-identical results, tests/test_gpu_lazy.py), flush inside the region
     ms, ph_ms, launches, clk = timed(not args.dense_adam)
-    # whole step against SURVEY.md 8d's convention (B(32D+56+8K) + 24P: dense Adam traffic for all P parameters)
-    step_roof = {"bytes_per_step": sbytes, "achieved": sbytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
-                 "note": "ALGORITHMIC bytes of SURVEY.md 8d / step time.  The lazy-Adam path moves fewer bytes than "
-                         "that convention (rows outside the batch are not touched), so this frac is not a DRAM-counter "
-                         "fraction; dense_adam.roofline_frac is the same figure with every row swept every step."}
-    step_roof["frac"] = step_roof["achieved"] / peak
+    # whole step.  SURVEY.md 8d's convention (B(32D+56+8K) + 24P) charges dense Adam traffic for all P parameters; the
+    # lazy path does not move those bytes, so for this leg the fraction is taken over the bytes the step's kernels
+    # ACTUALLY have to move (unique-row counts of the batches): user pass (below), item pass (theta/m/v of the unique
+    # items 48 D, per interaction the stashed user-row pair 8 D + g-pack 32 + perm/pseg 8), item sweep (untouched
+    # items 48 D).  The final flush is timed but its bytes are not counted (a lower bound on the fraction).  The 8d
+    # figure is kept for the dense leg only (dense_adam.roofline_frac).
+    ub = n_seg_u * (48 * D + 8 * D + 4) + B * (8 * D + 36 + 32)
+    ib = n_seg_i * (48 * D + 16) + B * (8 * D + 32 + 8) + (I - n_seg_i) * 48 * D
+    step_roof = {"bytes_per_step_actual": ub + ib, "achieved": (ub + ib) / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                 "frac": (ub + ib) / (ms * 1e-3) / 1e9 / peak, "unique_users": n_seg_u, "unique_items": n_seg_i,
+                 "survey_8d_bytes_per_step": sbytes,
+                 "note": "fraction over the bytes the lazy step must move (unique rows of the batch), not over SURVEY.md "
+                         "8d's dense-Adam convention (that one: dense_adam.roofline_frac)"}
     # roofline object = the DOMINANT KERNEL: fused user pass.  Its algorithmic bytes per launch: per unique user
     # theta/m/v of two tables read + written (48 D) + the stashed row pair (8 D) + last_step (4); per interaction
     # two item rows (8 D), ids + perm + scalars (36), g-pack write (32).  Timed live by CUDA events recorded
@@ -315,7 +416,6 @@ def run_ours_single(args, w):
     roof = {"bound": "hbm", "kernel": "upass_rows (fused forward + losses + user-side segment reduce + Adam)",
             "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None}
     if ph_ms.get("rows_users"):
-        ub = n_seg_u * (48 * D + 8 * D + 4) + B * (8 * D + 36 + 32)
         a = ub / (ph_ms["rows_users"] * 1e-3) / 1e9
         roof.update({"achieved": a, "frac": a / peak, "bytes_per_launch": ub, "ms_per_launch": ph_ms["rows_users"],
                      "share_of_step": ph_ms["rows_users"] / ms})
@@ -422,6 +522,15 @@ def run_ours_single(args, w):
                        "parallelism": "1 GPU"},
             "roofline": roof, "adam": "dense" if args.dense_adam else "lazy (bit-identical to dense, flush timed)",
             "dense_adam": dense, "cluster": cluster, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk}
+    # second kernel of the step: the item pass (ring rows kernel), same accounting
+    if ph_ms.get("rows_items"):
+        ia = (ib - (I - n_seg_i) * 48 * D) / (ph_ms["rows_items"] * 1e-3) / 1e9
+        roof["item_pass"] = {"kernel": "bwd_rows_ring (item-side segment reduce + Adam)", "achieved": ia,
+                             "frac": ia / peak, "bytes_per_launch": ib - (I - n_seg_i) * 48 * D,
+                             "ms_per_launch": ph_ms["rows_items"]}
+        itr = ncu_traffic().get("item_rows")
+        if itr:
+            roof["item_pass"]["traffic"] = itr["bytes"]
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w, os.cpu_count() or 1)
         try:
@@ -429,6 +538,16 @@ def run_ours_single(args, w):
             line["torch_eager_gpu"]["speedup_of_value"] = line["value"] / line["torch_eager_gpu"]["value"]
         except Exception as ex:      # noqa: BLE001 -- a baseline leg must never break the bench line
             line["torch_eager_gpu"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:200]}
+    if not args.no_config_legs and args.workload == "c5":
+        # BASELINE.json configs 2-4 (C1 = Coat on CPU is the reference's own oracle case, parity-tested only)
+        del hp, plans, dbatches, stages, plan_bufs, cu, ci, cy, ce, pidx, losses
+        torch.cuda.empty_cache()
+        line["configs"] = {}
+        for name in ("c2", "c3", "c4"):
+            try:
+                line["configs"][name] = config_leg(name, dev, with_eager=not args.no_cpu_baseline)
+            except Exception as ex:      # noqa: BLE001 -- a leg must never break the headline line
+                line["configs"][name] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     print(json.dumps(line), flush=True)
 
 
@@ -439,7 +558,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
-    ap.add_argument("--nbatch", type=int, default=4, help="distinct synthetic batches cycled through")
+    ap.add_argument("--nbatch", type=int, default=0,
+                    help="distinct synthetic batches cycled through (0 = steps + warmup: every step its own batch)")
+    ap.add_argument("--no-config-legs", action="store_true", help="skip the C2/C3/C4 legs of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense-adam", action="store_true", help="headline with plain dense Adam instead of lazy")
     args = ap.parse_args()

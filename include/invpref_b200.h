@@ -93,6 +93,19 @@ typedef struct {
     int64_t B;
 } invpref_batch;
 
+/* The step-DEPENDENT scalars of one train step as a record in DEVICE memory (invpref_hyper.dyn).  Every other scalar
+ * of invpref_hyper is baked into the kernel launches; these four change from step to step (Adam's bias corrections,
+ * the alpha schedule of train.py:891-894, the step number of the lazy-Adam bookkeeping).  With hyper.dyn set the
+ * kernels read them from the record instead, so a CUDA graph captured over the steps of one epoch (invpref_graph_*)
+ * can be replayed for every later epoch after the caller has rewritten the records (one small H2D copy per epoch).
+ * Fill the host copy with invpref_dyn_fill so that the arithmetic (double, as torch does) lives in one place. */
+typedef struct {
+    float step_size;      /* lr / (1 - beta1^step) */
+    float inv_bc2_sqrt;   /* 1 / sqrt(1 - beta2^step) */
+    float neg_alpha;      /* -alpha (functions.py:13-16) */
+    int32_t step;         /* 1-based Adam step */
+} invpref_dyn;
+
 /* Loss coefficients (train.py:829-830), gradient-reversal alpha (functions.py:13-16) and
  * Adam settings.  bias corrections are derived from `step` in double, as torch does. */
 typedef struct {
@@ -108,6 +121,9 @@ typedef struct {
     int64_t global_batch;
     int32_t flags;           /* INVPREF_EXPORT_* | INVPREF_SKIP_PARAM_REG */
     int32_t _pad;
+    const invpref_dyn* dyn;  /* DEVICE record overriding (lr, betas, step) -> step_size / inv_bc2_sqrt, alpha and step at
+                                run time; NULL = use the fields above.  `step` above must still be an upper bound of
+                                the steps the record will hold (it sizes the lazy-Adam schedule check). */
 } invpref_hyper;
 
 /* invpref_hyper.flags.  An EXPORT flag makes invpref_train_step write the (partial) gradients of that
@@ -123,6 +139,22 @@ typedef struct {
                                          that it overlaps the NVLink exchange of the item gradients) */
 
 const char* invpref_strerror(int status);
+
+/* Host helper: the record invpref_hyper.dyn would hold for `hyper` (its lr, betas, step and alpha). */
+int invpref_dyn_fill(const invpref_hyper* hyper, invpref_dyn* out_host);
+
+/* ---- CUDA-graph capture of a sequence of library calls (train.py:881-910 runs 3-31 steps per epoch on the dataset
+ * configs: launch latency and host overhead, not HBM, bound them) --------------------------------------------------
+ * invpref_graph_begin puts `stream` (not the legacy default stream) into capture mode; every library call issued on
+ * it until invpref_graph_end is recorded instead of executed.  invpref_graph_end instantiates the graph and returns an
+ * opaque handle; invpref_graph_launch replays it on a stream; invpref_graph_destroy frees it.  The captured calls must
+ * use invpref_hyper.dyn for whatever changes between replays; all buffers they name must stay alive and in place. */
+int invpref_graph_begin(void* stream);
+int invpref_graph_end(void* stream, void** out_graph);
+int invpref_graph_launch(void* graph, void* stream);
+int invpref_graph_destroy(void* graph);
+/* Kernel launches recorded in the graph (what one invpref_graph_launch adds to invpref_launch_count). */
+int64_t invpref_graph_launches(void* graph);
 int invpref_abi_version(void);
 
 /* ---- sizes -------------------------------------------------------------------------- */

@@ -26,7 +26,8 @@ EXPORTS = (
     "invpref_profile_read", "invpref_adam_dense", "invpref_gather_rows", "invpref_scatter_add_rows",
     "invpref_user_sweep", "invpref_flush_users", "invpref_fetch_rows_p2p", "invpref_owner_adam_p2p",
     "invpref_mask_scores", "invpref_hits_from_csr", "invpref_upass_supported", "invpref_plan_status",
-    "invpref_check_ids",
+    "invpref_check_ids", "invpref_dyn_fill", "invpref_graph_begin", "invpref_graph_end", "invpref_graph_launch",
+    "invpref_graph_destroy", "invpref_graph_launches",
 )
 # execution order; on the fused path "forward" is empty and chunks_users / rows_users are the fused user pass
 PHASES = ("plan", "forward", "chunks_users", "rows_users", "chunks_items", "rows_items", "sweep_items",
@@ -57,7 +58,13 @@ class Hyper(C.Structure):
     _fields_ = [("c_inv", C.c_double), ("c_ea", C.c_double), ("c_env", C.c_double), ("c_L2", C.c_double),
                 ("c_L1", C.c_double), ("alpha", C.c_double), ("lr", C.c_double), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("step", C.c_int64), ("use_class_rw", C.c_int32),
-                ("use_rec_rw", C.c_int32), ("global_batch", C.c_int64), ("flags", C.c_int32), ("_pad", C.c_int32)]
+                ("use_rec_rw", C.c_int32), ("global_batch", C.c_int64), ("flags", C.c_int32), ("_pad", C.c_int32),
+                ("dyn", C.c_void_p)]
+
+
+class Dyn(C.Structure):
+    """invpref_dyn: the step-dependent scalars of one train step (device record for CUDA-graph replay)."""
+    _fields_ = [("step_size", C.c_float), ("inv_bc2_sqrt", C.c_float), ("neg_alpha", C.c_float), ("step", C.c_int32)]
 
 
 EXPORT_USER_GRADS, EXPORT_ITEM_GRADS, EXPORT_SMALL_GRADS, SKIP_PARAM_REG, DEFER_USER_SWEEP = 1, 2, 4, 8, 16
@@ -87,6 +94,13 @@ def load() -> C.CDLL:
     lib.invpref_upass_supported.argtypes = [C.POINTER(Desc)]
     lib.invpref_plan_status.argtypes = [C.POINTER(Desc), vp, i64, vp]
     lib.invpref_check_ids.argtypes = [C.POINTER(Desc), vp, vp, vp, i64, vp, vp]
+    lib.invpref_dyn_fill.argtypes = [C.POINTER(Hyper), C.POINTER(Dyn)]
+    lib.invpref_graph_begin.argtypes = [vp]
+    lib.invpref_graph_end.argtypes = [vp, C.POINTER(vp)]
+    lib.invpref_graph_launch.argtypes = [vp, vp]
+    lib.invpref_graph_destroy.argtypes = [vp]
+    lib.invpref_graph_launches.argtypes = [vp]
+    lib.invpref_graph_launches.restype = C.c_int64
     lib.invpref_build_segments.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, sz, vp]
     lib.invpref_forward.argtypes = [C.POINTER(Desc), C.POINTER(Params), vp, vp, vp, i64, vp, vp, vp, vp]
     lib.invpref_predict.argtypes = [C.POINTER(Desc), C.POINTER(Params), vp, vp, i64, vp, vp]
@@ -112,7 +126,7 @@ def load() -> C.CDLL:
     lib.invpref_profile_read.argtypes = [C.c_int, C.POINTER(C.c_float)]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("invpref_strerror", "invpref_abi_version", "invpref_launch_count"):
+        if name not in ("invpref_strerror", "invpref_abi_version", "invpref_launch_count", "invpref_graph_launches"):
             fn.restype = C.c_int
     _lib = lib
     return lib

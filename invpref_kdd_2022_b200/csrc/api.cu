@@ -109,6 +109,75 @@ int invpref_abi_version(void) { return INVPREF_ABI_VERSION; }
 
 int64_t invpref_launch_count(void) { return (int64_t)g_launch_count; }
 
+int invpref_dyn_fill(const invpref_hyper* hyper, invpref_dyn* out_host) {
+    if (!hyper || !out_host || hyper->step < 1) return INVPREF_ERR_BAD_ARG;
+    const AdamScalars s = make_adam(hyper);
+    out_host->step_size = s.step_size;
+    out_host->inv_bc2_sqrt = s.inv_bc2_sqrt;
+    out_host->neg_alpha = (float)(-hyper->alpha);
+    out_host->step = (int32_t)hyper->step;
+    return INVPREF_OK;
+}
+
+// ---- CUDA-graph capture / replay of a sequence of library calls ----
+struct GraphHandle {
+    cudaGraphExec_t exec;
+    long long launches;
+};
+static long long g_capture_launch0 = -1;
+
+int invpref_graph_begin(void* stream) {
+    if (stream == nullptr || g_capture_launch0 >= 0) return INVPREF_ERR_BAD_ARG;   // not the legacy stream; not nested
+    if (cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return INVPREF_ERR_CUDA;
+    }
+    g_capture_launch0 = g_launch_count;
+    return INVPREF_OK;
+}
+
+int invpref_graph_end(void* stream, void** out_graph) {
+    if (g_capture_launch0 < 0 || !out_graph) return INVPREF_ERR_BAD_ARG;
+    const long long n = g_launch_count - g_capture_launch0;
+    g_launch_count = g_capture_launch0;       // recorded, not executed: they count when the graph is launched
+    g_capture_launch0 = -1;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamEndCapture((cudaStream_t)stream, &graph) != cudaSuccess || graph == nullptr) {
+        cudaGetLastError();
+        return INVPREF_ERR_CUDA;
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t rc = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (rc != cudaSuccess) {
+        cudaGetLastError();
+        return INVPREF_ERR_CUDA;
+    }
+    *out_graph = new GraphHandle{exec, n};
+    return INVPREF_OK;
+}
+
+int invpref_graph_launch(void* graph, void* stream) {
+    if (!graph) return INVPREF_ERR_BAD_ARG;
+    GraphHandle* h = (GraphHandle*)graph;
+    if (cudaGraphLaunch(h->exec, (cudaStream_t)stream) != cudaSuccess) {
+        cudaGetLastError();
+        return INVPREF_ERR_CUDA;
+    }
+    g_launch_count += h->launches;
+    return INVPREF_OK;
+}
+
+int invpref_graph_destroy(void* graph) {
+    if (!graph) return INVPREF_OK;
+    GraphHandle* h = (GraphHandle*)graph;
+    cudaGraphExecDestroy(h->exec);
+    delete h;
+    return INVPREF_OK;
+}
+
+int64_t invpref_graph_launches(void* graph) { return graph ? (int64_t)((GraphHandle*)graph)->launches : 0; }
+
 int invpref_profile_enable(int max_steps) {
     for (cudaEvent_t e : g_prof_events) cudaEventDestroy(e);
     g_prof_events.clear();
@@ -309,12 +378,12 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     si.grad_inv = wr_i ? grads_out->Iinv : nullptr; si.grad_env = wr_i ? grads_out->Ienv : nullptr;
     si.plan = pi; si.chunk_part = w.chunk_part_i;
     si.reg2 = su.reg2; si.reg1 = su.reg1; si.adam = as;
-    su.last_step = nullptr; su.sched = nullptr; su.step = (int)hyper->step; su.stash = nullptr;
-    si.last_step = nullptr; si.sched = nullptr; si.step = (int)hyper->step; si.stash = nullptr;
+    su.last_step = nullptr; su.sched = nullptr; su.step = (int)hyper->step; su.stash = nullptr; su.dyn = hyper->dyn;
+    si.last_step = nullptr; si.sched = nullptr; si.step = (int)hyper->step; si.stash = nullptr; si.dyn = hyper->dyn;
     if (lazy) {
         su.last_step = adam->user_last_step; su.sched = (const float2*)adam->sched; su.stash = w.stash;
         si.stash = w.stash;     // the item pass reads the user rows of this step from the stash
-        if ((rc = launch_sched_write((float2*)adam->sched, (int)hyper->step, as, st)) != INVPREF_OK) return rc;
+        if ((rc = launch_sched_write((float2*)adam->sched, (int)hyper->step, as, hyper->dyn, st)) != INVPREF_OK) return rc;
     }
 
     const int P = fwd_partial_floats(g);
@@ -348,7 +417,7 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
         f.c_inv = (float)hyper->c_inv; f.c_ea = (float)hyper->c_ea; f.c_env = (float)hyper->c_env;
         f.neg_alpha = (float)(-hyper->alpha); f.invB = 1.f / (float)Bg;
         f.gpack = w.gpack; f.partials = w.partials; f.P = P;
-        f.up_s_inv = f.up_s_env = f.up_logp = nullptr; f.generic = 0;
+        f.up_s_inv = f.up_s_env = f.up_logp = nullptr; f.generic = 0; f.dyn = hyper->dyn;
         n_partials = fwd_train_grid(B);
         if ((rc = launch_fwd_train(g, f, n_partials, st)) != INVPREF_OK) return rc;
         pm.mark();
@@ -380,7 +449,7 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     t.mE = adam->m.E; t.mW = adam->m.W; t.mb = adam->m.b; t.vE = adam->v.E; t.vW = adam->v.W; t.vb = adam->v.b;
     t.gE = wr_s ? grads_out->E : nullptr; t.gW = wr_s ? grads_out->W : nullptr;
     t.gb = wr_s ? grads_out->b : nullptr;
-    t.loss_out = loss_out; t.adam = as; t.epi = exp_s ? EPI_EXPORT : EPI_ADAM;
+    t.loss_out = loss_out; t.adam = as; t.epi = exp_s ? EPI_EXPORT : EPI_ADAM; t.dyn = hyper->dyn;
     rc = launch_tail(t, st);
     pm.mark();
     pm.done();
@@ -405,6 +474,7 @@ int invpref_flush_users(const invpref_desc* desc, invpref_params* params, invpre
     if (h1.step < 1) h1.step = 1;
     su.adam = make_adam(&h1);
     su.last_step = adam->user_last_step; su.sched = (const float2*)adam->sched; su.step = (int)hyper->step;
+    su.dyn = hyper->dyn;
     return launch_flush(g, su, (cudaStream_t)stream);
 }
 
@@ -422,7 +492,7 @@ int invpref_user_sweep(const invpref_desc* desc, const invpref_params* pin, invp
     BwdSideArgs su = {};
     su.own_inv_in = pin->Uinv; su.own_env_in = pin->Uenv; su.own_inv_out = pout->Uinv; su.own_env_out = pout->Uenv;
     su.m_inv = adam->m.Uinv; su.m_env = adam->m.Uenv; su.v_inv = adam->v.Uinv; su.v_env = adam->v.Uenv;
-    su.plan = pu; su.D = g.D; su.K = g.K; su.GS = g.GS; su.adam = make_adam(hyper);
+    su.plan = pu; su.D = g.D; su.K = g.K; su.GS = g.GS; su.adam = make_adam(hyper); su.dyn = hyper->dyn;
     return launch_sweep(g, su, (cudaStream_t)stream);
 }
 
@@ -515,7 +585,7 @@ int invpref_backward(const invpref_desc* desc, const invpref_params* params, con
     f.implicit = desc->implicit; f.reg_env_embed = 0; f.use_class_rw = 0; f.use_rec_rw = 0;
     f.c_inv = f.c_ea = f.c_env = 0.f; f.neg_alpha = (float)(-alpha); f.invB = 0.f;
     f.gpack = w.gpack; f.partials = w.partials; f.P = fwd_partial_floats(g);
-    f.up_s_inv = g_s_inv; f.up_s_env = g_s_env; f.up_logp = g_logp; f.generic = 1;
+    f.up_s_inv = g_s_inv; f.up_s_env = g_s_env; f.up_logp = g_logp; f.generic = 1; f.dyn = nullptr;
     const int fgrid = fwd_train_grid(B);
     if ((rc = launch_fwd_train(g, f, fgrid, st)) != INVPREF_OK) return rc;
 

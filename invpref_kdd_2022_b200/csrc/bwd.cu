@@ -98,6 +98,7 @@ __device__ __forceinline__ void finish_row(const BwdSideArgs& a, int64_t row, fl
                                            Row<VEC, NV>& th_e, Row<VEC, NV>& m_i, Row<VEC, NV>& m_e,
                                            Row<VEC, NV>& v_i, Row<VEC, NV>& v_e, Row<VEC, NV>& gi, Row<VEC, NV>& ge,
                                            int lane, int D) {
+    const AdamScalars adam = with_dyn(a.adam, a.dyn);   // read where it is used: no register held over the segment
     if (EPI == EPI_ADAM || EPI == EPI_EXPORT) {
 #pragma unroll
         for (int x = 0; x < NV * VEC; ++x) {
@@ -112,8 +113,8 @@ __device__ __forceinline__ void finish_row(const BwdSideArgs& a, int64_t row, fl
     if (EPI == EPI_ADAM) {
 #pragma unroll
         for (int x = 0; x < NV * VEC; ++x) {
-            adam_update(th_i.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.adam);
-            adam_update(th_e.x[x], m_e.x[x], v_e.x[x], ge.x[x], a.adam);
+            adam_update(th_i.x[x], m_i.x[x], v_i.x[x], gi.x[x], adam);
+            adam_update(th_e.x[x], m_e.x[x], v_e.x[x], ge.x[x], adam);
         }
         store_row<VEC, NV>(th_i, a.own_inv_out, row, D, lane);
         store_row<VEC, NV>(th_e, a.own_env_out, row, D, lane);
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(BLOCK) sweep_kernel(BwdSideArgs a) {
     const int64_t rows = a.plan.rows;
     const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
     const uint32_t* __restrict__ touched = a.plan.touched;
+    const AdamScalars adam = with_dyn(a.adam, a.dyn);
     for (int64_t row = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4); row < rows; row += ngroups) {
         if ((touched[row >> 5] >> (row & 31)) & 1u) continue;
         Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
@@ -476,8 +478,8 @@ __global__ void __launch_bounds__(BLOCK) sweep_kernel(BwdSideArgs a) {
         load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
 #pragma unroll
         for (int x = 0; x < NV * VEC; ++x) {
-            adam_zero_step(th_i.x[x], m_i.x[x], v_i.x[x], a.adam, a.adam.step_size, a.adam.inv_bc2_sqrt);
-            adam_zero_step(th_e.x[x], m_e.x[x], v_e.x[x], a.adam, a.adam.step_size, a.adam.inv_bc2_sqrt);
+            adam_zero_step(th_i.x[x], m_i.x[x], v_i.x[x], adam, adam.step_size, adam.inv_bc2_sqrt);
+            adam_zero_step(th_e.x[x], m_e.x[x], v_e.x[x], adam, adam.step_size, adam.inv_bc2_sqrt);
         }
         store_row<VEC, NV, true>(th_i, a.own_inv_out, row, D, lane);
         store_row<VEC, NV, true>(th_e, a.own_env_out, row, D, lane);
@@ -504,9 +506,10 @@ __global__ void __launch_bounds__(BLOCK) flush_kernel(BwdSideArgs a) {
     const int lane = threadIdx.x & (GROUP - 1);
     const int64_t rows = a.plan.rows;
     const int64_t ngroups = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
+    const int step = a.dyn ? a.dyn->step : a.step;
     for (int64_t row = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4); row < rows; row += ngroups) {
         const int last = a.last_step[row];
-        if (last >= a.step) continue;
+        if (last >= step) continue;
         Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
         load_row<VEC, NV, true>(th_i, a.own_inv_in, row, D, lane);
         load_row<VEC, NV, true>(th_e, a.own_env_in, row, D, lane);
@@ -514,7 +517,7 @@ __global__ void __launch_bounds__(BLOCK) flush_kernel(BwdSideArgs a) {
         load_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
         load_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
         load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
-        for (int j = last + 1; j <= a.step; ++j) {
+        for (int j = last + 1; j <= step; ++j) {
             const float2 sc = a.sched[j];
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) {
@@ -528,12 +531,14 @@ __global__ void __launch_bounds__(BLOCK) flush_kernel(BwdSideArgs a) {
         store_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
         store_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
         store_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
-        if (lane == 0) a.last_step[row] = a.step;
+        if (lane == 0) a.last_step[row] = step;
     }
 }
 
-__global__ void sched_write_kernel(float2* sched, int step, float step_size, float inv_bc2_sqrt) {
-    sched[step] = make_float2(step_size, inv_bc2_sqrt);
+__global__ void sched_write_kernel(float2* sched, int step, float step_size, float inv_bc2_sqrt,
+                                   const invpref_dyn* dyn) {
+    if (dyn != nullptr) sched[dyn->step] = make_float2(dyn->step_size, dyn->inv_bc2_sqrt);
+    else sched[step] = make_float2(step_size, inv_bc2_sqrt);
 }
 
 constexpr int TAIL_THREADS = 256;
@@ -570,6 +575,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
     }
     __syncthreads();
     const double Bf = (double)a.B, Df = (double)D;
+    const AdamScalars adam = with_dyn(a.adam, a.dyn);
     if (a.epi == EPI_ADAM || a.epi == EPI_EXPORT) {
         const bool do_adam = a.epi == EPI_ADAM;
         // classifier norms (models.py:210-217), only when it is regularised
@@ -629,10 +635,10 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
             if (a.gW) { a.gW[idx] = gW; a.gE[idx] = gE; }
             if (do_adam) {
                 float m = a.mW[idx], v = a.vW[idx];
-                adam_update(w, m, v, gW, a.adam);
+                adam_update(w, m, v, gW, adam);
                 a.W_out[idx] = w; a.mW[idx] = m; a.vW[idx] = v;
                 m = a.mE[idx]; v = a.vE[idx];
-                adam_update(e, m, v, gE, a.adam);
+                adam_update(e, m, v, gE, adam);
                 a.E_out[idx] = e; a.mE[idx] = m; a.vE[idx] = v;
             }
         }
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
             if (a.gb) a.gb[tid] = gb;
             if (do_adam) {
                 float m = a.mb[tid], v = a.vb[tid];
-                adam_update(bb, m, v, gb, a.adam);
+                adam_update(bb, m, v, gb, adam);
                 a.b_out[tid] = bb; a.mb[tid] = m; a.vb[tid] = v;
             }
         }
@@ -800,8 +806,8 @@ int launch_flush(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream) {
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 
-int launch_sched_write(float2* sched, int step, const AdamScalars& s, cudaStream_t stream) {
-    sched_write_kernel<<<1, 1, 0, stream>>>(sched, step, s.step_size, s.inv_bc2_sqrt);
+int launch_sched_write(float2* sched, int step, const AdamScalars& s, const invpref_dyn* dyn, cudaStream_t stream) {
+    sched_write_kernel<<<1, 1, 0, stream>>>(sched, step, s.step_size, s.inv_bc2_sqrt, dyn);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

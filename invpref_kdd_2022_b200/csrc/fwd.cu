@@ -206,7 +206,9 @@ __global__ void __launch_bounds__(BLOCK, 3) fwd_train_kernel(FwdTrainArgs a) {
             out[1] = g_z2;
             out[2] = __int_as_float(e);
 #pragma unroll
-            for (int k = 0; k < 9; ++k) out[3 + k] = (k < KT) ? a.neg_alpha * gl[k < KT ? k : 0] : 0.f;
+            const float neg_alpha = a.dyn ? a.dyn->neg_alpha : a.neg_alpha;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out[3 + k] = (k < KT) ? neg_alpha * gl[k < KT ? k : 0] : 0.f;
             *reinterpret_cast<float4*>(gp) = make_float4(out[0], out[1], out[2], out[3]);
             *reinterpret_cast<float4*>(gp + 4) = make_float4(out[4], out[5], out[6], out[7]);
             if (KT > 5 && a.GS > 8) *reinterpret_cast<float4*>(gp + 8) = make_float4(out[8], out[9], out[10], out[11]);

@@ -20,6 +20,7 @@ struct FwdTrainArgs {
     // generic autograd backward (invpref_backward): upstream grads instead of the built-in losses
     const float *up_s_inv, *up_s_env, *up_logp;
     int generic;
+    const invpref_dyn* dyn;   // optional device record overriding neg_alpha
 };
 
 struct FwdOnlyArgs {
@@ -59,13 +60,15 @@ struct BwdSideArgs {
     int step;                                 // Adam step of this call
     float* stash;                             // user pass: OUT [n_seg, 2, D] caught-up rows before this step;
                                               // item pass: partner rows are read from here via plan.pseg
+    const invpref_dyn* dyn;                   // optional device record overriding adam.step_size / inv_bc2_sqrt, step
+                                              // (and UserPassArgs.neg_alpha): CUDA-graph replay
 };
 
 int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);
 int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream_t stream);
 int launch_sweep(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);
 int launch_flush(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);     // lazy rows -> step a.step
-int launch_sched_write(float2* sched, int step, const AdamScalars& s, cudaStream_t stream);
+int launch_sched_write(float2* sched, int step, const AdamScalars& s, const invpref_dyn* dyn, cudaStream_t stream);
 
 // ---- upass.cu: fused forward + user-side backward + Adam ---------------------------------------------
 constexpr int UPASS_CHUNK_CTAS = 74;   // CTAs of the (usually idle) long-user-segment kernel
@@ -101,6 +104,7 @@ struct TailArgs {
     float* loss_out;          // [6]
     AdamScalars adam;
     int epi;
+    const invpref_dyn* dyn;
 };
 
 int launch_tail(const TailArgs& a, cudaStream_t stream);

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
     extern __shared__ __align__(16) float smem[];
     const int D = EXACT ? GROUP * VEC * NV : a.side.D, K = EXACT ? KT : a.side.K, KD = K * D;
     const Smem s = carve_smem(smem, KD);
-    float* ring = smem + (((4 + 2 * GROUPS_PER_BLOCK) * KD + INVPREF_MAX_ENVS + 3) & ~3);   // [2][8][NV][BLOCK][VEC]
+    float* ring = smem + (((4 + 2 * GROUPS_PER_BLOCK) * KD + SB_WORDS + 3) & ~3);   // [2][8][NV][BLOCK][VEC]
     int32_t* meta = reinterpret_cast<int32_t*>(ring + (size_t)2 * UP_SLOTS * NV * VEC * BLOCK) +
                     (threadIdx.x >> 4) * UM_WORDS;                                          // this group's words
     Running st;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
             read_staged_row<VEC, NV>(m_e, ring, stg * UP_SLOTS + 3, D, lane);
             read_staged_row<VEC, NV>(v_i, ring, stg * UP_SLOTS + 4, D, lane);
             read_staged_row<VEC, NV>(v_e, ring, stg * UP_SLOTS + 5, D, lane);
-            replay_steps<VEC, NV>(a.side, last, a.side.step - 1, ra, rue, m_i, m_e, v_i, v_e);
+            replay_steps<VEC, NV>(a.side, last, __float_as_int(s.sB[SB_STEP]) - 1, ra, rue, m_i, m_e, v_i, v_e);
             store_row<VEC, NV>(ra, a.side.stash, (int64_t)sgm * 2, D, lane);
             store_row<VEC, NV>(rue, a.side.stash, (int64_t)sgm * 2 + 1, D, lane);
             // the caught-up moments go back to their (own) slots: no registers held over the interactions
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
                 inter_grads<VEC, NV, KT>(a, cfg, myDE, s.sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, ge.x, st, D, K);
                 n = n_a;
             }
-            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, K);
+            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, K, s.sB);
         }
         // the user rows' own L1/L2 terms (models.py:469-482): every occurrence in the batch counts
         const float cnt = (float)(end - beg);
@@ -232,10 +232,11 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
             read_staged_row<VEC, NV>(m_e, ring, stg * UP_SLOTS + 3, D, lane);
             read_staged_row<VEC, NV>(v_i, ring, stg * UP_SLOTS + 4, D, lane);
             read_staged_row<VEC, NV>(v_e, ring, stg * UP_SLOTS + 5, D, lane);
+            const AdamScalars adam = adam_from_smem(a.side.adam, s.sB);
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) {
-                adam_update(ra.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.side.adam);
-                adam_update(rue.x[x], m_e.x[x], v_e.x[x], ge.x[x], a.side.adam);
+                adam_update(ra.x[x], m_i.x[x], v_i.x[x], gi.x[x], adam);
+                adam_update(rue.x[x], m_e.x[x], v_e.x[x], ge.x[x], adam);
             }
             store_row<VEC, NV>(ra, a.side.own_inv_out, row, D, lane);
             store_row<VEC, NV>(rue, a.side.own_env_out, row, D, lane);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
             store_row<VEC, NV, true>(m_e, a.side.m_env, row, D, lane);
             store_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
             store_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
-            if (LAZY && lane == 0) a.side.last_step[row] = a.side.step;
+            if (LAZY && lane == 0) a.side.last_step[row] = __float_as_int(s.sB[SB_STEP]);
         }
     }
     cp_async_wait<0>();

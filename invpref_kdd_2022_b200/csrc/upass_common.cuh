@@ -11,6 +11,10 @@ namespace invpref {
 namespace {
 
 constexpr int P_DB = 8, P_CNT = 16, P_DW = 24;
+// sB: the classifier bias [INVPREF_MAX_ENVS], then the step-dependent scalars (launch arguments, or the device record
+// invpref_hyper.dyn for CUDA-graph replay), read from shared memory where they are used so that no register holds them
+constexpr int SB_STEP_SIZE = INVPREF_MAX_ENVS, SB_INV_BC2 = INVPREF_MAX_ENVS + 1, SB_NEG_ALPHA = INVPREF_MAX_ENVS + 2,
+              SB_STEP = INVPREF_MAX_ENVS + 3, SB_WORDS = INVPREF_MAX_ENVS + 4;
 
 // Per-lane sums that persist over all segments a group handles.  The eleven-plus scalar sums (three losses,
 // db[K], env counts[K]) are spread over the lanes of the group, one register each, instead of every lane
@@ -82,7 +86,7 @@ __device__ __forceinline__ void inter_grads(const UserPassArgs& a, const LossCfg
     for (int kk = 0; kk < KT; ++kk) lg[kk] = (kk < K) ? group_sum(q.lg[kk], gmask) + sB[kk] : -INFINITY;
 
     float g_z1, g_z2, gl[KT], lw[3];
-    loss_grads<KT>(cfg, z1, z2, lg, y, w, e, g_z1, g_z2, gl, lw);
+    loss_grads<KT, true>(cfg, z1, z2, lg, y, w, e, g_z1, g_z2, gl, lw, lane, gmask);
     st.sq += q.sq;
     st.ab += q.ab;
     {
@@ -118,8 +122,9 @@ __device__ __forceinline__ void inter_grads(const UserPassArgs& a, const LossCfg
         out[0] = g_z1;
         out[1] = g_z2;
         out[2] = __int_as_float(e);
+        const float neg_alpha = sB[SB_NEG_ALPHA];
 #pragma unroll
-        for (int kk = 0; kk < 9; ++kk) out[3 + kk] = (kk < KT) ? a.neg_alpha * gl[kk < KT ? kk : 0] : 0.f;
+        for (int kk = 0; kk < 9; ++kk) out[3 + kk] = (kk < KT) ? neg_alpha * gl[kk < KT ? kk : 0] : 0.f;
         *reinterpret_cast<float4*>(gp) = make_float4(out[0], out[1], out[2], out[3]);
         *reinterpret_cast<float4*>(gp + 4) = make_float4(out[4], out[5], out[6], out[7]);
         if (KT > 5 && GS > 8)
@@ -158,7 +163,8 @@ template <int VEC, int NV, int KT>
 __device__ __forceinline__ void finish_range(const UserPassArgs& a, const float* __restrict__ sW,
                                              float* __restrict__ myDW, const Row<VEC, NV>& ra, int lane,
                                              const float (&acc0)[NV * VEC], const float (&Q)[KT][NV * VEC],
-                                             Row<VEC, NV>& gi, int D, int K) {
+                                             Row<VEC, NV>& gi, int D, int K, const float* __restrict__ sB) {
+    const float neg_alpha = sB[SB_NEG_ALPHA];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const int d0 = dim_of<VEC>(lane, j);
@@ -174,7 +180,7 @@ __device__ __forceinline__ void finish_range(const UserPassArgs& a, const float*
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
                         const int x = j * VEC + v;
-                        gi.x[x] += a.neg_alpha * wk[v] * Q[kk][x];
+                        gi.x[x] += neg_alpha * wk[v] * Q[kk][x];
                         dw[v] += ra.x[x] * Q[kk][x];
                     }
                     stv<VEC>(myDW + kk * D + d0, dw);
@@ -206,6 +212,12 @@ struct Smem {
     float *sE, *sW, *sRed, *sDE, *sDW, *sB;
 };
 
+__device__ __forceinline__ AdamScalars adam_from_smem(AdamScalars s, const float* sB) {
+    s.step_size = sB[SB_STEP_SIZE];
+    s.inv_bc2_sqrt = sB[SB_INV_BC2];
+    return s;
+}
+
 __device__ __forceinline__ Smem carve_smem(float* smem, int KD) {
     Smem s;
     s.sE = smem;
@@ -221,6 +233,13 @@ __device__ __forceinline__ void stage(const UserPassArgs& a, const Smem& s, int 
     for (int t = threadIdx.x; t < KD; t += BLOCK) { s.sE[t] = a.side.E[t]; s.sW[t] = a.side.W[t]; }
     for (int t = threadIdx.x; t < 2 * GROUPS_PER_BLOCK * KD; t += BLOCK) s.sDE[t] = 0.f;   // sDE and sDW
     if (threadIdx.x < INVPREF_MAX_ENVS) s.sB[threadIdx.x] = ((int)threadIdx.x < a.side.K) ? a.b[threadIdx.x] : 0.f;
+    if (threadIdx.x == 32) {
+        const invpref_dyn* dyn = a.side.dyn;
+        s.sB[SB_STEP_SIZE] = dyn ? dyn->step_size : a.side.adam.step_size;
+        s.sB[SB_INV_BC2] = dyn ? dyn->inv_bc2_sqrt : a.side.adam.inv_bc2_sqrt;
+        s.sB[SB_NEG_ALPHA] = dyn ? dyn->neg_alpha : a.neg_alpha;
+        s.sB[SB_STEP] = __int_as_float(dyn ? dyn->step : a.side.step);
+    }
     __syncthreads();
     st.stat1 = st.stat2 = st.sq = st.ab = 0.f;
 }
@@ -266,7 +285,7 @@ __device__ __forceinline__ void write_partials(const UserPassArgs& a, const Smem
 
 
 inline size_t upass_smem(const Geometry& g) {
-    return ((size_t)(4 + 2 * GROUPS_PER_BLOCK) * g.K * g.D + INVPREF_MAX_ENVS) * sizeof(float);
+    return ((size_t)(4 + 2 * GROUPS_PER_BLOCK) * g.K * g.D + SB_WORDS) * sizeof(float);
 }
 
 }  // namespace

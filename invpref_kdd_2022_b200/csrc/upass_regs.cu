@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_chunks_kernel(UserPassArgs a, 
             load_row<VEC, NV>(m_e, a.side.m_env, row, D, lane);
             load_row<VEC, NV>(v_i, a.side.v_inv, row, D, lane);
             load_row<VEC, NV>(v_e, a.side.v_env, row, D, lane);
-            replay_steps<VEC, NV>(a.side, a.side.last_step[row], a.side.step - 1, ra, rue, m_i, m_e, v_i, v_e);
+            replay_steps<VEC, NV>(a.side, a.side.last_step[row], __float_as_int(s.sB[SB_STEP]) - 1, ra, rue, m_i, m_e, v_i, v_e);
         }
         float acc0[NV * VEC], Q[KT][NV * VEC];
 #pragma unroll
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_chunks_kernel(UserPassArgs a, 
             for (int k = 0; k < KT; ++k) Q[k][x] = 0.f;
         }
         fused_range<VEC, NV, KT>(a, cfg, s.sE, s.sW, myDE, s.sB, ra, rue, desc.y, desc.z, lane, gmask, acc0, Q, ge.x, st);
-        finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, a.side.K);
+        finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, a.side.K, s.sB);
         store_row<VEC, NV>(gi, a.side.chunk_part, (int64_t)c * 2, D, lane);
         store_row<VEC, NV>(ge, a.side.chunk_part, (int64_t)c * 2 + 1, D, lane);
     }
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
             load_row<VEC, NV, true>(m_e, a.side.m_env, row, D, lane);
             load_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
             load_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
-            replay_steps<VEC, NV>(a.side, a.side.last_step[row], a.side.step - 1, ra, rue, m_i, m_e, v_i, v_e);
+            replay_steps<VEC, NV>(a.side, a.side.last_step[row], __float_as_int(s.sB[SB_STEP]) - 1, ra, rue, m_i, m_e, v_i, v_e);
             store_row<VEC, NV>(ra, a.side.stash, (int64_t)sgm * 2, D, lane);
             store_row<VEC, NV>(rue, a.side.stash, (int64_t)sgm * 2 + 1, D, lane);
         }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
                 for (int k = 0; k < KT; ++k) Q[k][x] = 0.f;
             }
             fused_range<VEC, NV, KT>(a, cfg, s.sE, s.sW, myDE, s.sB, ra, rue, beg, end, lane, gmask, acc0, Q, ge.x, st);
-            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, a.side.K);
+            finish_range<VEC, NV, KT>(a, s.sW, myDW, ra, lane, acc0, Q, gi, D, a.side.K, s.sB);
         }
         // the user rows' own L1/L2 terms (models.py:469-482): every occurrence in the batch counts
         const float cnt = (float)(end - beg);
@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
                 load_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
                 load_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
             }
+            const AdamScalars adam = adam_from_smem(a.side.adam, s.sB);
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) {
-                adam_update(ra.x[x], m_i.x[x], v_i.x[x], gi.x[x], a.side.adam);
-                adam_update(rue.x[x], m_e.x[x], v_e.x[x], ge.x[x], a.side.adam);
+                adam_update(ra.x[x], m_i.x[x], v_i.x[x], gi.x[x], adam);
+                adam_update(rue.x[x], m_e.x[x], v_e.x[x], ge.x[x], adam);
             }
             store_row<VEC, NV>(ra, a.side.own_inv_out, row, D, lane);
             store_row<VEC, NV>(rue, a.side.own_env_out, row, D, lane);
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_kernel(UserPassArgs a) {
             store_row<VEC, NV, true>(m_e, a.side.m_env, row, D, lane);
             store_row<VEC, NV, true>(v_i, a.side.v_inv, row, D, lane);
             store_row<VEC, NV, true>(v_e, a.side.v_env, row, D, lane);
-            if (LAZY && lane == 0) a.side.last_step[row] = a.side.step;
+            if (LAZY && lane == 0) a.side.last_step[row] = __float_as_int(s.sB[SB_STEP]);
         }
         row1 = row2; beg1 = beg2; pid1 = pid2; n1 = n2;
         row2 = row3; beg2 = beg3;

@@ -59,6 +59,8 @@ class HotPath:
         self.lazy_requested = bool(lazy)
         self.lazy = bool(lazy) and self.lazy_supported
         self.id_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.generation = 0          # bumped whenever a buffer a captured CUDA graph may name is re-allocated
+        self.parity = 0              # number of double-buffer swaps so far, mod 2
         self.last_step = None        # int32 [n_users]
         self.sched = None            # fp32 [cap, 2]
         self._dirty = False          # some user rows are behind self.step
@@ -68,14 +70,22 @@ class HotPath:
         if self.lazy:
             if self.last_step is None:
                 raise RuntimeError("internal: lazy state not initialised")
-            if self.step + 2 >= self.sched.shape[0]:
-                grown = torch.zeros((self.sched.shape[0] * 4, 2), dtype=torch.float32, device=self.device)
-                grown[:self.sched.shape[0]] = self.sched
-                self.sched = grown
+            self.reserve_steps(1)
             a.user_last_step = _lib.ptr(self.last_step, torch.int32)
             a.sched = _lib.ptr(self.sched, torch.float32)
             a.sched_cap = self.sched.shape[0]
         return a
+
+    def reserve_steps(self, n: int):
+        """Lazy mode: room in the schedule table for the next ``n`` steps (grows it: re-allocation)."""
+        if self.lazy and self.sched is not None and self.step + n + 2 >= self.sched.shape[0]:
+            cap = self.sched.shape[0]
+            while self.step + n + 2 >= cap:
+                cap *= 4
+            grown = torch.zeros((cap, 2), dtype=torch.float32, device=self.device)
+            grown[:self.sched.shape[0]] = self.sched
+            self.sched = grown
+            self.generation += 1
 
     def _ensure_lazy(self):
         """Called with self.step == number of COMPLETED steps: every row is current at that step."""
@@ -85,6 +95,7 @@ class HotPath:
             while cap <= self.step + 2:
                 cap *= 4
             self.sched = torch.zeros((cap, 2), dtype=torch.float32, device=self.device)
+            self.generation += 1
 
     def write_sched(self):
         """Lazy mode, a step without a local batch (multi-GPU: nothing routed here): only record the step's
@@ -105,13 +116,15 @@ class HotPath:
         self.lazy = bool(lazy)
         self.last_step = None
         self.sched = None
+        self.generation += 1
 
-    def flush(self):
-        """Lazy mode: bring every user row up to the last completed step (no-op otherwise)."""
+    def flush(self, dyn: Optional[int] = None):
+        """Lazy mode: bring every user row up to the last completed step (no-op otherwise).  ``dyn``: device
+        address of the ``invpref_dyn`` record of that step (CUDA-graph capture, see ``StepGraph``)."""
         if not (self.lazy and self._dirty):
             return
         hyper = _lib.Hyper(0, 0, 0, 0, 0, 0, self.lr, self.betas[0], self.betas[1], self.eps, int(self.step), 0, 0,
-                           0, 0, 0)
+                           0, 0, 0, dyn)
         p = _lib.make_params(self.params)
         adam = self._adam_struct()
         _lib.check(self.lib.invpref_flush_users(C.byref(self.desc), C.byref(p), C.byref(adam), C.byref(hyper),
@@ -123,11 +136,13 @@ class HotPath:
         if self.m is None:
             self.m = {k: torch.zeros_like(self.params[k]) for k in PARAM_FIELDS}
             self.v = {k: torch.zeros_like(self.params[k]) for k in PARAM_FIELDS}
+            self.generation += 1
         if self.shadow is None:
             self.shadow = {}
         for k in shadow_for:
             if k not in self.shadow:
                 self.shadow[k] = self.params[k].clone()
+                self.generation += 1
 
     def adam_dense(self, theta, m, v, grad, step=None):
         """``invpref_adam_dense``: in-place Adam on flat fp32 tensors with a materialised gradient."""
@@ -142,6 +157,7 @@ class HotPath:
             n = _lib.workspace_bytes(self.desc, batch)
             self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
             self._ws_batch = batch
+            self.generation += 1
         return self._ws
 
     def new_plan(self, users: torch.Tensor, items: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -198,8 +214,11 @@ class HotPath:
     def train_step(self, users, items, scores, envs, weights, *, c_inv, c_ea, c_env, c_L2, c_L1, alpha,
                    use_class_rw, use_rec_rw, plan: Optional[torch.Tensor] = None,
                    loss_out: Optional[torch.Tensor] = None, grads_out: Optional[Dict[str, torch.Tensor]] = None,
-                   global_batch: int = 0, flags: int = 0):
+                   global_batch: int = 0, flags: int = 0, dyn: Optional[int] = None):
         """train.py:771-844 in one library call.  Returns the device tensor holding the six losses.
+
+        ``dyn``: device address of an ``invpref_dyn`` record; the kernels then read Adam's bias corrections,
+        alpha and the step number from it instead of from the launch arguments (CUDA-graph replay).
 
         ``flags`` / ``global_batch``: data-parallel use, see ``invpref_hyper`` in the header; tables of an
         exported group are neither updated nor swapped."""
@@ -212,7 +231,7 @@ class HotPath:
         self.step += 1
         hyper = _lib.Hyper(float(c_inv), float(c_ea), float(c_env), float(c_L2), float(c_L1), float(alpha), self.lr,
                            self.betas[0], self.betas[1], self.eps, self.step, int(bool(use_class_rw)),
-                           int(bool(use_rec_rw)), int(global_batch), int(flags), 0)
+                           int(bool(use_rec_rw)), int(global_batch), int(flags), 0, dyn)
         p_in = _lib.make_params(self.params)
         out = dict(self.params)
         swap = [k for k in TABLES if not (flags & (_lib.EXPORT_USER_GRADS if k[0] == "U" else _lib.EXPORT_ITEM_GRADS))
@@ -236,9 +255,35 @@ class HotPath:
         # the updated rows are in the other buffer set: swap
         for k in swap:
             self.params[k], self.shadow[k] = self.shadow[k], self.params[k]
+        if swap:
+            self.parity ^= 1
         if self.on_swap is not None:
             self.on_swap(self.params)
         return loss_out
+
+    # ---- host-side bookkeeping of a captured / replayed sequence of steps (StepGraph) ----------------
+    def host_state(self):
+        return (self.step, dict(self.params), dict(self.shadow or {}), self._dirty, self.parity)
+
+    def restore_host_state(self, st):
+        self.step, self.params, shadow, self._dirty, self.parity = st[0], dict(st[1]), dict(st[2]), st[3], st[4]
+        if self.shadow is not None:
+            self.shadow = shadow
+        if self.on_swap is not None:
+            self.on_swap(self.params)
+
+    def advance(self, n_steps: int, flushed: bool):
+        """What ``n_steps`` plain (no export flags) train steps do to the host-side state: the step counter and
+        the double-buffer roles.  Called after a graph replay that ran those steps on the device."""
+        self.step += int(n_steps)
+        if n_steps % 2:
+            for k in TABLES:
+                if not (self.lazy and k[0] == "U"):
+                    self.params[k], self.shadow[k] = self.shadow[k], self.params[k]
+            self.parity ^= 1
+            if self.on_swap is not None:
+                self.on_swap(self.params)
+        self._dirty = self.lazy and not flushed
 
     def user_sweep(self, plan: torch.Tensor, B: int):
         """The deferred dense sweep of the step that just ran with ``DEFER_USER_SWEEP`` (call it after
@@ -331,6 +376,68 @@ class HotPath:
         _lib.check(self.lib.invpref_stat_envs(_lib.ptr(envs, torch.int64), N, self.n_envs, _lib.ptr(hist, torch.int64),
                                               _lib.ptr(cw), _lib.ptr(sw), _lib.stream_ptr()), "stat_envs")
         return cw, sw
+
+
+class StepGraph:
+    """A CUDA graph over a fixed sequence of library calls (``invpref_graph_*``) plus the device records
+    (``invpref_dyn``) through which the captured kernels see what changes between replays: Adam's bias corrections,
+    alpha, the step number.  Replaying costs one H2D copy of the records and one graph launch, instead of ~10
+    kernel launches and their host-side marshalling per step."""
+
+    def __init__(self, hot: HotPath, n_records: int):
+        self.hot, self.n = hot, int(n_records)
+        self.dyn_dev = torch.zeros((self.n, 4), dtype=torch.float32, device=hot.device)
+        self.dyn_host = torch.zeros((self.n, 4), dtype=torch.float32).pin_memory()
+        self.stream = torch.cuda.Stream(device=hot.device)
+        self.handles = {}            # start parity of the double buffers -> graph handle
+        self.generation = hot.generation
+
+    def record_ptr(self, j: int) -> int:
+        return self.dyn_dev.data_ptr() + 16 * int(j)
+
+    def fill(self, j: int, step: int, alpha: float):
+        h = self.hot
+        hyper = _lib.Hyper(0, 0, 0, 0, 0, float(alpha), h.lr, h.betas[0], h.betas[1], h.eps, int(step), 0, 0, 0, 0, 0)
+        rec = C.cast(C.c_void_p(self.dyn_host.data_ptr() + 16 * int(j)), C.POINTER(_lib.Dyn))
+        _lib.check(h.lib.invpref_dyn_fill(C.byref(hyper), rec), "dyn_fill")
+
+    def upload(self):
+        self.dyn_dev.copy_(self.dyn_host, non_blocking=True)
+
+    def valid(self) -> bool:
+        if self.generation != self.hot.generation:
+            self.drop()
+            self.generation = self.hot.generation
+        return True
+
+    def capture(self, key, fn):
+        """Records the library calls ``fn()`` issues on the current stream (must be ``self.stream``)."""
+        lib = self.hot.lib
+        _lib.check(lib.invpref_graph_begin(_lib.stream_ptr()), "graph_begin")
+        try:
+            fn()
+        finally:
+            out = C.c_void_p()
+            rc = lib.invpref_graph_end(_lib.stream_ptr(), C.byref(out))
+        _lib.check(rc, "graph_end")
+        self.handles[key] = out
+
+    def launch(self, key):
+        _lib.check(self.hot.lib.invpref_graph_launch(self.handles[key], _lib.stream_ptr()), "graph_launch")
+
+    def launches(self, key) -> int:
+        return int(self.hot.lib.invpref_graph_launches(self.handles[key]))
+
+    def drop(self):
+        for h in self.handles.values():
+            self.hot.lib.invpref_graph_destroy(h)
+        self.handles = {}
+
+    def __del__(self):
+        try:
+            self.drop()
+        except Exception:
+            pass
 
 
 def build_segments(ids: torch.Tensor, n_rows: int):

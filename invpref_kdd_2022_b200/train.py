@@ -32,7 +32,8 @@ class _InvPrefTrainManager:
             invariant_coe: float, env_aware_coe: float, env_coe: float, L2_coe: float, L1_coe: float,
             alpha: float = None, use_class_re_weight: bool = False, test_begin_epoch: int = 0,
             begin_cluster_epoch: int = None, stop_cluster_epoch: int = None, cluster_use_random_sort: bool = True,
-            use_recommend_re_weight: bool = True, cache_plans: bool = True, lazy_adam: bool = True
+            use_recommend_re_weight: bool = True, cache_plans: bool = True, lazy_adam: bool = True,
+            use_graph: bool = True
     ):
         self.model = model
         self.evaluator = evaluator
@@ -78,6 +79,13 @@ class _InvPrefTrainManager:
         self.cache_plans = cache_plans
         self._plans = {}
         self._loss_rows = None
+        # CUDA-graph replay of the epoch (train.py:881-910 issues 3-31 steps per epoch on the dataset configs, every
+        # one of them a fixed sequence of launches on fixed buffers): from the second epoch on, one graph launch per
+        # epoch instead of ~10 launches + their host-side marshalling per step.  Bit-identical to the plain loop.
+        self.use_graph = bool(use_graph) and cache_plans and self.batch_num <= 256
+        self._graph = None
+        self._g_envs = None
+        self._g_sw = None
 
     def _init_eps(self) -> torch.Tensor:
         """train.py:763-769, same torch expression so the fp32 table is bit-identical."""
@@ -118,20 +126,78 @@ class _InvPrefTrainManager:
         self.engine.raise_if_bad_ids()
         return dict(zip(LOSS_KEYS, vals))
 
+    def _alpha_at(self, batch_index: int) -> float:
+        if self.update_alpha:                                                     # train.py:891-894
+            p = float(batch_index + (self.epoch_cnt + 1) * self.batch_num) / float(
+                (self.epoch_cnt + 1) * self.batch_num)
+            self.alpha = 2. / (1. + np.exp(-10. * p)) - 1.
+        return self.alpha
+
+    def _graph_epoch(self) -> bool:
+        """One epoch as ONE CUDA-graph launch.  Returns False (nothing done) when the graph path does not apply yet:
+        the first epoch runs launch by launch (it builds and validates the plans and allocates every buffer)."""
+        eng, n = self.engine, self.batch_num
+        if not (self.use_graph and self.epoch_cnt >= 1 and len(self._plans) == n and eng.m is not None):
+            return False
+        from .engine import StepGraph
+        N = self.users_tensor.shape[0]
+        if self._graph is None or self._graph.hot is not eng:
+            self._graph = StepGraph(eng, n)
+            self._g_envs = torch.empty(N, dtype=torch.int64, device=self.device)
+            self._g_sw = torch.empty(N, dtype=torch.float32, device=self.device)
+        g = self._graph
+        eng.reserve_steps(n)
+        g.valid()
+        main = torch.cuda.current_stream()
+        g.stream.wait_stream(main)
+        with torch.cuda.stream(g.stream):
+            # cluster() / stat_envs() re-bind self.envs / self.sample_weights to new tensors (as the reference does):
+            # the captured kernels read these stable copies
+            self._g_envs.copy_(self.envs)
+            self._g_sw.copy_(self.sample_weights)
+            for b in range(n):
+                g.fill(b, eng.step + 1 + b, self._alpha_at(b))
+            g.upload()
+            key = eng.parity
+            if key not in g.handles:
+                saved = eng.host_state()
+
+                def issue():
+                    for b, (u, i, y, e, w) in enumerate(mini_batch(
+                            self.batch_size, self.users_tensor, self.items_tensor, self.scores_tensor, self._g_envs,
+                            self._g_sw)):
+                        eng.train_step(u, i, y, e, w, c_inv=self.invariant_coe, c_ea=self.env_aware_coe,
+                                       c_env=self.env_coe, c_L2=self.L2_coe, c_L1=self.L1_coe, alpha=0.0,
+                                       use_class_rw=self.use_class_re_weight, use_rec_rw=self.use_recommend_re_weight,
+                                       plan=self._plans[b], loss_out=self._loss_rows[b], dyn=g.record_ptr(b))
+                    eng.flush(dyn=g.record_ptr(n - 1))
+
+                try:
+                    g.capture(key, issue)
+                finally:
+                    eng.restore_host_state(saved)     # capture records, it does not run: undo the host bookkeeping
+            g.launch(key)
+            eng.advance(n, flushed=True)
+        main.wait_stream(g.stream)
+        return True
+
     def train_a_epoch(self) -> dict:
         """train.py:881-910.  Losses stay on the device until the end of the epoch (one sync per epoch
         instead of six per batch); the returned dict is the same np.mean of per-batch floats."""
         self.model.train()
         if self._loss_rows is None or self._loss_rows.shape[0] != self.batch_num:
             self._loss_rows = torch.zeros((self.batch_num, 6), dtype=torch.float32, device=self.device)
+            if self._graph is not None:
+                self._graph.drop()
+        if self._graph_epoch():
+            self.epoch_cnt += 1
+            rows = self._loss_rows.cpu().tolist()
+            return merge_dict([dict(zip(LOSS_KEYS, r)) for r in rows], _mean_merge_dict_func)
         for batch_index, (u, i, y, e, w) in enumerate(mini_batch(
                 self.batch_size, self.users_tensor, self.items_tensor, self.scores_tensor, self.envs,
                 self.sample_weights)):
-            if self.update_alpha:                                                 # train.py:891-894
-                p = float(batch_index + (self.epoch_cnt + 1) * self.batch_num) / float(
-                    (self.epoch_cnt + 1) * self.batch_num)
-                self.alpha = 2. / (1. + np.exp(-10. * p)) - 1.
-            self._step(u, i, y, e, w, self.alpha, loss_out=self._loss_rows[batch_index], plan_key=batch_index)
+            self._step(u, i, y, e, w, self._alpha_at(batch_index), loss_out=self._loss_rows[batch_index],
+                       plan_key=batch_index)
         self.epoch_cnt += 1
         self.engine.flush()
         rows = self._loss_rows.cpu().tolist()

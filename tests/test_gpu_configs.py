@@ -73,9 +73,8 @@ def test_native_shape_step_matches_torch_eager_on_the_gpu(name):
 
 
 @pytest.mark.parametrize("name", SHAPES)
-def test_native_shape_lazy_is_bitwise_dense_and_graph_epoch_is_bitwise_loop(name):
-    """Three batches, five steps (rows skipped for a step, then hit again): lazy Adam == dense Adam, and the
-    trainer's CUDA-graph epoch == the same epoch issued launch by launch, bit for bit."""
+def test_native_shape_lazy_is_bitwise_dense(name):
+    """Three batches, five steps (rows skipped for a step, then hit again): lazy Adam == dense Adam, bit for bit."""
     from invpref_kdd_2022_b200.engine import HotPath
     w, dev, dbs, kw = _setup(name, nb=3)
     init = bench.make_tables(w, dev, seed=5)
@@ -96,6 +95,56 @@ def test_native_shape_lazy_is_bitwise_dense_and_graph_epoch_is_bitwise_loop(name
     for grp in (1, 2, 3):
         for k in on.PARAM_ORDER:
             assert torch.equal(res["dense"][grp][k], res["lazy"][grp][k]), (name, grp, k)
+
+
+class _NullEvaluator0:
+    def evaluate(self):
+        return {"mse": 0.0}
+
+
+@pytest.mark.parametrize("name", SHAPES)
+@pytest.mark.parametrize("lazy", [True, False])
+def test_native_shape_graph_epochs_are_bitwise_the_plain_loop(name, lazy):
+    """The trainer replays every epoch after the first as ONE CUDA graph (invpref_graph_*, step-dependent scalars in
+    device records): four epochs with a cluster() + stat_envs() in between (they re-bind envs / sample_weights) and
+    an odd number of batches (the double buffers end an epoch swapped) must equal the launch-by-launch loop bit for
+    bit -- losses, every table, every Adam moment."""
+    from invpref_kdd_2022_b200.models import InvPrefExplicit, InvPrefImplicit
+    from invpref_kdd_2022_b200.train import ExplicitTrainManager, ImplicitTrainManager
+    w = bench.WORKLOADS[name]
+    dev = torch.device("cuda:0")
+    U, I, B, batches = bench.synth_batches(w, 3)
+    data = np.concatenate([np.stack([u, i, y.astype(np.int64)], axis=1) for (u, i, y, e) in batches])
+    data = data[:2 * B + B // 3]                              # 3 batches, the last one short
+    data[0, 0], data[0, 1] = U - 1, I - 1
+    out = {}
+    for use_graph in (False, True):
+        torch.manual_seed(11)
+        np.random.seed(11)
+        M, T = (InvPrefImplicit, ImplicitTrainManager) if w["implicit"] else (InvPrefExplicit, ExplicitTrainManager)
+        model = M(U, I, w["K"], w["D"], w["roe"], w["ree"]).to(dev)
+        c = w["coef"]
+        tm = T(model=model, evaluator=_NullEvaluator0(), device=dev, training_data=torch.LongTensor(data).to(dev),
+               batch_size=B, epochs=4, cluster_interval=2, evaluate_interval=100, lr=w["lr"],
+               invariant_coe=c["c_inv"], env_aware_coe=c["c_ea"], env_coe=c["c_env"], L2_coe=c["c_L2"],
+               L1_coe=c["c_L1"], alpha=None, use_class_re_weight=w["crw"], use_recommend_re_weight=w["rrw"],
+               lazy_adam=lazy, use_graph=use_graph)
+        assert tm.batch_num == 3
+        (losses, _), _, (diffs, cnts, _) = tm.train(silent=True, auto=True)
+        if use_graph:
+            assert tm._graph is not None and len(tm._graph.handles) == 2      # both start parities were captured
+            assert tm._graph.launches(0) >= 3 * 5
+        eng = tm.engine
+        eng.flush()
+        out[use_graph] = (losses, diffs, cnts, {k: v.clone() for k, v in eng.params.items()},
+                          {k: v.clone() for k, v in eng.m.items()}, {k: v.clone() for k, v in eng.v.items()},
+                          eng.step, tm.alpha)
+    a, b = out[False], out[True]
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[6] == b[6] == 12 and a[7] == b[7]
+    for grp in (3, 4, 5):
+        for k in on.PARAM_ORDER:
+            assert torch.equal(a[grp][k], b[grp][k]), (name, lazy, grp, k)
+    assert all(np.isfinite(list(d.values())).all() for d in a[0])
 
 
 @pytest.mark.parametrize("name", SHAPES)
