@@ -562,6 +562,7 @@ def main():
                     help="distinct synthetic batches cycled through (0 = steps + warmup: every step its own batch)")
     ap.add_argument("--no-config-legs", action="store_true", help="skip the C2/C3/C4 legs of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the parity_vs_1gpu leg")
     ap.add_argument("--dense-adam", action="store_true", help="headline with plain dense Adam instead of lazy")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

@@ -106,6 +106,21 @@ typedef struct {
     int32_t step;         /* 1-based Adam step */
 } invpref_dyn;
 
+/* Row-sharded multi-GPU training, PUSH export of the partial item gradients (invpref_hyper.push, with
+ * INVPREF_EXPORT_ITEM_GRADS): instead of writing row c of its partial item gradient into grads_out, the item pass
+ * stores it straight into the staging buffer of the rank that OWNS the row, over NVLink (posted writes that overlap
+ * the rest of the pass): table t (0 invariant, 1 env-aware) of cache row c goes to
+ *     base[t * world + owner[c]] + index[c] * dim .
+ * The owner then reduces from LOCAL memory (invpref_owner_adam_push).  All pointers are device pointers; `base` is a
+ * DEVICE array of 2 * world pointers into the peers' mapped staging buffers. */
+typedef struct {
+    float* const* base;      /* device array [2 * world] */
+    const int32_t* owner;    /* [cache rows] owner rank of every cache row */
+    const int32_t* index;    /* [cache rows] row in the owner's staging buffer */
+    int32_t world;
+    int32_t _pad;
+} invpref_push;
+
 /* Loss coefficients (train.py:829-830), gradient-reversal alpha (functions.py:13-16) and
  * Adam settings.  bias corrections are derived from `step` in double, as torch does. */
 typedef struct {
@@ -124,6 +139,7 @@ typedef struct {
     const invpref_dyn* dyn;  /* DEVICE record overriding (lr, betas, step) -> step_size / inv_bc2_sqrt, alpha and step at
                                 run time; NULL = use the fields above.  `step` above must still be an upper bound of
                                 the steps the record will hold (it sizes the lazy-Adam schedule check). */
+    const invpref_push* push; /* HOST pointer; NULL = exported item gradients go to grads_out */
 } invpref_hyper;
 
 /* invpref_hyper.flags.  An EXPORT flag makes invpref_train_step write the (partial) gradients of that
@@ -293,6 +309,21 @@ int invpref_mask_scores(float* rating, int64_t b, int64_t n_items, const int64_t
 int invpref_hits_from_csr(const int64_t* top, int64_t b, int32_t k, const int64_t* users, const int64_t* off,
                           const int64_t* items, uint8_t* hits, int64_t* n_list, void* stream);
 
+/* invpref_eval_topk: the whole of ImplicitTestManager.evaluate_batch's device work (evaluate.py:88-135) for one
+ * batch of b test users in ONE kernel, without materialising the [b, n_items] rating matrix:
+ *   rating[r, i] = predict(users[r])[i]   (models.py:393-407: sigmoid(<Uinv[u], Iinv[i]>); explicit model: no sigmoid)
+ *   rating[r, mask items of users[r]] = -1024 (evaluate.py:98);  rating[r, pool items] += 1024 (evaluate.py:110)
+ *   top_items[r, :] = the k items of largest rating, descending (torch.topk, evaluate.py:113; ties, which torch
+ *   leaves unspecified, go to the lower item id);  hits[r, j] = top_items[r, j] in ground truth (evaluate.py:11-19);
+ *   n_gt[r] = size of the user's ground-truth list.
+ * Lists are CSR over user ids as for invpref_mask_scores (ascending unique items per user); mask / pool / gt may be
+ * NULL (no masking / no pool / no hit look-up: hits and n_gt must then be NULL).  1 <= k <= 256, k <= n_items.
+ * top_scores (nullable): the adjusted ratings of the selected items. */
+int invpref_eval_topk(const invpref_desc* desc, const invpref_params* params, const int64_t* users, int64_t b,
+                      const int64_t* mask_off, const int64_t* mask_items, const int64_t* pool_off,
+                      const int64_t* pool_items, const int64_t* gt_off, const int64_t* gt_items, int32_t k,
+                      int64_t* top_items, float* top_scores, uint8_t* hits, int64_t* n_gt, void* stream);
+
 /* ---- the same exchange over peer memory (NVLink loads; no collective on the data path) -------------
  * `tables` / `grads`: HOST arrays of 2 * world device pointers, [t * world + rank] = base of item table t
  * (0 invariant, 1 env-aware) / of the partial-gradient cache t of rank `rank`, the caller's own rank
@@ -312,6 +343,19 @@ int invpref_fetch_rows_p2p(const float* const* tables, int32_t world, const int3
 int invpref_owner_adam_p2p(float* theta_inv, float* theta_env, float* m_inv, float* m_env, float* v_inv, float* v_env,
                            int64_t n_rows, int32_t dim, int32_t world, const float* const* grads, const int32_t* pos,
                            const invpref_hyper* hyper, void* stream);
+
+/* invpref_owner_adam_push: the push counterpart of invpref_owner_adam_p2p, reading LOCAL memory and writing peers.
+ * For every row j < n_rows of the caller's item shard and t = 0, 1:
+ *   g = sum over ranks p = 0..world-1 (in this order) of stage_t[spos[p * n_rows + j], :]   (spos < 0: no partial)
+ *   one dense torch.optim.Adam step on theta/m/v with g  (same order and arithmetic as invpref_owner_adam_p2p), then
+ *   for every rank p with npos[p * n_rows + j] >= 0: caches[t * world + p][npos[p * n_rows + j], :] = updated row
+ * i.e. the updated row is pushed into the slot it has in rank p's row cache for the NEXT batch (posted NVLink
+ * writes; replaces invpref_fetch_rows_p2p).  stage_*: the caller's own staging buffers, filled by the ranks' item
+ * passes (invpref_push).  caches: HOST array of 2 * world device pointers; npos / caches may be NULL (last batch). */
+int invpref_owner_adam_push(float* theta_inv, float* theta_env, float* m_inv, float* m_env, float* v_inv, float* v_env,
+                            int64_t n_rows, int32_t dim, int32_t world, const float* stage_inv, const float* stage_env,
+                            const int32_t* spos, float* const* caches, const int32_t* npos,
+                            const invpref_hyper* hyper, void* stream);
 
 /* Number of kernels the library has launched in this process (bench.py's gpu_launches). */
 int64_t invpref_launch_count(void);

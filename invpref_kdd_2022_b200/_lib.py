@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libinvpref_b200.so")
+# INVPREF_LIB: another build of the same library (A/B runs of kernel variants in bench.py; see tools/build_variants.sh)
+LIB_PATH = os.environ.get("INVPREF_LIB") or os.path.join(_HERE, "libinvpref_b200.so")
 
 MAX_ENVS = 8
 MAX_DIM = 256
@@ -27,7 +28,7 @@ EXPORTS = (
     "invpref_user_sweep", "invpref_flush_users", "invpref_fetch_rows_p2p", "invpref_owner_adam_p2p",
     "invpref_mask_scores", "invpref_hits_from_csr", "invpref_upass_supported", "invpref_plan_status",
     "invpref_check_ids", "invpref_dyn_fill", "invpref_graph_begin", "invpref_graph_end", "invpref_graph_launch",
-    "invpref_graph_destroy", "invpref_graph_launches",
+    "invpref_graph_destroy", "invpref_graph_launches", "invpref_owner_adam_push", "invpref_eval_topk",
 )
 # execution order; on the fused path "forward" is empty and chunks_users / rows_users are the fused user pass
 PHASES = ("plan", "forward", "chunks_users", "rows_users", "chunks_items", "rows_items", "sweep_items",
@@ -59,7 +60,13 @@ class Hyper(C.Structure):
                 ("c_L1", C.c_double), ("alpha", C.c_double), ("lr", C.c_double), ("beta1", C.c_double),
                 ("beta2", C.c_double), ("eps", C.c_double), ("step", C.c_int64), ("use_class_rw", C.c_int32),
                 ("use_rec_rw", C.c_int32), ("global_batch", C.c_int64), ("flags", C.c_int32), ("_pad", C.c_int32),
-                ("dyn", C.c_void_p)]
+                ("dyn", C.c_void_p), ("push", C.c_void_p)]
+
+
+class Push(C.Structure):
+    """invpref_push: where the item pass stores its exported partial gradients in peer memory."""
+    _fields_ = [("base", C.c_void_p), ("owner", C.c_void_p), ("index", C.c_void_p), ("world", C.c_int32),
+                ("_pad", C.c_int32)]
 
 
 class Dyn(C.Structure):
@@ -120,11 +127,17 @@ def load() -> C.CDLL:
     lib.invpref_fetch_rows_p2p.argtypes = [C.POINTER(vp), C.c_int32, vp, vp, i64, C.c_int32, vp, vp, vp]
     lib.invpref_owner_adam_p2p.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_int32, C.c_int32, C.POINTER(vp), vp,
                                            C.POINTER(Hyper), vp]
+    lib.invpref_owner_adam_push.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_int32, C.c_int32, vp, vp, vp,
+                                            C.POINTER(vp), vp, C.POINTER(Hyper), vp]
+    lib.invpref_eval_topk.argtypes = [C.POINTER(Desc), C.POINTER(Params), vp, i64, vp, vp, vp, vp, vp, vp, C.c_int32,
+                                      vp, vp, vp, vp, vp]
     lib.invpref_mask_scores.argtypes = [vp, i64, i64, vp, vp, vp, C.c_float, C.c_int32, vp]
     lib.invpref_hits_from_csr.argtypes = [vp, i64, C.c_int32, vp, vp, vp, vp, vp, vp]
     lib.invpref_profile_enable.argtypes = [C.c_int]
     lib.invpref_profile_read.argtypes = [C.c_int, C.POINTER(C.c_float)]
     for name in EXPORTS:
+        if os.environ.get("INVPREF_LIB") and not hasattr(lib, name):
+            continue                     # an older variant build: entry points added since are simply absent
         fn = getattr(lib, name)
         if name not in ("invpref_strerror", "invpref_abi_version", "invpref_launch_count", "invpref_graph_launches"):
             fn.restype = C.c_int

@@ -328,6 +328,9 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     const bool exp_u = hyper->flags & INVPREF_EXPORT_USER_GRADS, exp_i = hyper->flags & INVPREF_EXPORT_ITEM_GRADS;
     const bool exp_s = hyper->flags & INVPREF_EXPORT_SMALL_GRADS;
     if ((exp_u || exp_i || exp_s) && !grads_out) return INVPREF_ERR_BAD_ARG;
+    const invpref_push* push = hyper->push;
+    if (push && (!exp_i || !push->base || !push->owner || !push->index || push->world < 1 || push->world > 16))
+        return INVPREF_ERR_BAD_ARG;
     const bool lazy = adam->user_last_step != nullptr;
     if (lazy) {
         // lazy user rows: fused pass only, in place, Adam (not export), schedule table with room for this step
@@ -380,6 +383,9 @@ int invpref_train_step(const invpref_desc* desc, const invpref_params* pin, invp
     si.reg2 = su.reg2; si.reg1 = su.reg1; si.adam = as;
     su.last_step = nullptr; su.sched = nullptr; su.step = (int)hyper->step; su.stash = nullptr; su.dyn = hyper->dyn;
     si.last_step = nullptr; si.sched = nullptr; si.step = (int)hyper->step; si.stash = nullptr; si.dyn = hyper->dyn;
+    su.push_base = nullptr; su.push_owner = nullptr; su.push_index = nullptr; su.push_world = 0;
+    si.push_base = push ? push->base : nullptr; si.push_owner = push ? push->owner : nullptr;
+    si.push_index = push ? push->index : nullptr; si.push_world = push ? push->world : 0;
     if (lazy) {
         su.last_step = adam->user_last_step; su.sched = (const float2*)adam->sched; su.stash = w.stash;
         si.stash = w.stash;     // the item pass reads the user rows of this step from the stash
@@ -530,6 +536,23 @@ int invpref_hits_from_csr(const int64_t* top, int64_t b, int32_t k, const int64_
     return launch_hits_from_csr(top, b, k, users, off, items, hits, n_list, (cudaStream_t)stream);
 }
 
+int invpref_eval_topk(const invpref_desc* desc, const invpref_params* params, const int64_t* users, int64_t b,
+                      const int64_t* mask_off, const int64_t* mask_items, const int64_t* pool_off,
+                      const int64_t* pool_items, const int64_t* gt_off, const int64_t* gt_items, int32_t k,
+                      int64_t* top_items, float* top_scores, uint8_t* hits, int64_t* n_gt, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if (!params || !params->Uinv || !params->Iinv) return INVPREF_ERR_BAD_ARG;
+    if (b < 0 || k < 1 || k > 256 || k > desc->n_items || (b > 0 && (!users || !top_items))) return INVPREF_ERR_BAD_ARG;
+    if ((mask_off && !mask_items) || (pool_off && !pool_items) || (gt_off && !gt_items)) return INVPREF_ERR_BAD_ARG;
+    if ((hits || n_gt) && !gt_off) return INVPREF_ERR_BAD_ARG;
+    if (b == 0) return INVPREF_OK;
+    return launch_eval_topk(params->Uinv, params->Iinv, desc->n_items, g.D, desc->implicit, users, b, mask_off,
+                            mask_items, pool_off, pool_items, gt_off, gt_items, k, top_items, top_scores, hits, n_gt,
+                            (cudaStream_t)stream);
+}
+
 int invpref_fetch_rows_p2p(const float* const* tables, int32_t world, const int32_t* owner, const int64_t* rows,
                            int64_t n, int32_t dim, float* out_inv, float* out_env, void* stream) {
     if (n < 0 || dim < 1 || !tables || (n > 0 && (!owner || !rows || !out_inv || !out_env))) return INVPREF_ERR_BAD_ARG;
@@ -549,6 +572,22 @@ int invpref_owner_adam_p2p(float* theta_inv, float* theta_env, float* m_inv, flo
     if (n_rows == 0) return INVPREF_OK;
     return launch_owner_adam_p2p(theta_inv, theta_env, m_inv, m_env, v_inv, v_env, n_rows, dim, world, grads, pos,
                                  make_adam(hyper), (cudaStream_t)stream);
+}
+
+int invpref_owner_adam_push(float* theta_inv, float* theta_env, float* m_inv, float* m_env, float* v_inv, float* v_env,
+                            int64_t n_rows, int32_t dim, int32_t world, const float* stage_inv, const float* stage_env,
+                            const int32_t* spos, float* const* caches, const int32_t* npos,
+                            const invpref_hyper* hyper, void* stream) {
+    if (n_rows < 0 || dim < 1 || world < 1 || world > 16 || !hyper || hyper->step < 1) return INVPREF_ERR_BAD_ARG;
+    if (n_rows > 0 && (!theta_inv || !theta_env || !m_inv || !m_env || !v_inv || !v_env || !spos || !stage_inv ||
+                       !stage_env))
+        return INVPREF_ERR_BAD_ARG;
+    if ((caches == nullptr) != (npos == nullptr)) return INVPREF_ERR_BAD_ARG;
+    for (int i = 0; caches && i < 2 * world; ++i)
+        if (!caches[i]) return INVPREF_ERR_BAD_ARG;
+    if (n_rows == 0) return INVPREF_OK;
+    return launch_owner_adam_push(theta_inv, theta_env, m_inv, m_env, v_inv, v_env, n_rows, dim, world, stage_inv,
+                                  stage_env, spos, caches, npos, make_adam(hyper), (cudaStream_t)stream);
 }
 
 int invpref_backward(const invpref_desc* desc, const invpref_params* params, const invpref_batch* batch, double alpha,

@@ -105,7 +105,13 @@ __device__ __forceinline__ void finish_row(const BwdSideArgs& a, int64_t row, fl
             gi.x[x] += cnt * (a.reg2 * th_i.x[x] + mul_sign(a.reg1, th_i.x[x]));
             ge.x[x] += cnt * (a.reg2 * th_e.x[x] + mul_sign(a.reg1, th_e.x[x]));
         }
-        if (a.grad_inv != nullptr) {
+        if (EPI == EPI_EXPORT && a.push_base != nullptr) {
+            // straight into the owner's staging buffer over NVLink (posted writes)
+            const int o = a.push_owner[row];
+            const int64_t idx = a.push_index[row];
+            store_row<VEC, NV>(gi, a.push_base[o], idx, D, lane);
+            store_row<VEC, NV>(ge, a.push_base[a.push_world + o], idx, D, lane);
+        } else if (a.grad_inv != nullptr) {
             store_row<VEC, NV>(gi, a.grad_inv, row, D, lane);
             store_row<VEC, NV>(ge, a.grad_env, row, D, lane);
         }
@@ -362,6 +368,71 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
     const int G = gridDim.x * GROUPS_PER_BLOCK;
     const int g = blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x >> 4);
 
+    // ---- hot rows (more than HOT_CHUNKS chunk partials): one CTA per row.  Group q sums the q-th contiguous slice
+    //      of the row's partials in chunk order (two row pairs in flight), the 16 slice sums meet in shared memory and
+    //      group 0 adds them in slice order and finishes the row: a fixed two-level order, no atomics.  The ring
+    //      below skips these rows.  (The ring's shared memory is free until the first produce().)
+    {
+        const int n_hot = a.plan.counters[4];
+        const int grp = threadIdx.x >> 4;
+        float* sHot = ring;                                   // [16 groups][2 rows][16 lanes][NV * VEC]
+        for (int h = blockIdx.x; h < n_hot; h += gridDim.x) {
+            const int cs = a.plan.hot_list[h];
+            const int c0 = a.plan.seg_chunk[cs], c1 = a.plan.seg_chunk[cs + 1];
+            const int per = (c1 - c0 + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
+            const int cb = c0 + grp * per, ce = (cb + per < c1) ? cb + per : c1;
+            Row<VEC, NV> gi, ge;
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
+            for (int c = cb; c < ce; c += 2) {
+                Row<VEC, NV> pi[2], pe[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (c + q < ce) {
+                        load_row<VEC, NV>(pi[q], a.chunk_part, (int64_t)(c + q) * 2, D, lane);
+                        load_row<VEC, NV>(pe[q], a.chunk_part, (int64_t)(c + q) * 2 + 1, D, lane);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    if (c + q < ce) {
+#pragma unroll
+                        for (int x = 0; x < NV * VEC; ++x) { gi.x[x] += pi[q].x[x]; ge.x[x] += pe[q].x[x]; }
+                    }
+                }
+            }
+            float* mine = sHot + ((size_t)(grp * 2) * GROUP + lane) * (NV * VEC);
+#pragma unroll
+            for (int x = 0; x < NV * VEC; ++x) {
+                mine[x] = gi.x[x];
+                mine[GROUP * NV * VEC + x] = ge.x[x];
+            }
+            __syncthreads();
+            if (grp == 0) {
+#pragma unroll
+                for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
+                for (int q = 0; q < GROUPS_PER_BLOCK; ++q) {
+                    const float* sl = sHot + ((size_t)(q * 2) * GROUP + lane) * (NV * VEC);
+#pragma unroll
+                    for (int x = 0; x < NV * VEC; ++x) { gi.x[x] += sl[x]; ge.x[x] += sl[GROUP * NV * VEC + x]; }
+                }
+                const int64_t row = seg_row[cs];
+                Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
+                load_row<VEC, NV>(th_i, a.own_inv_in, row, D, lane);
+                load_row<VEC, NV>(th_e, a.own_env_in, row, D, lane);
+                if (EPI == EPI_ADAM) {
+                    load_row<VEC, NV, true>(m_i, a.m_inv, row, D, lane);
+                    load_row<VEC, NV, true>(m_e, a.m_env, row, D, lane);
+                    load_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
+                    load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
+                }
+                finish_row<VEC, NV, EPI>(a, row, (float)(seg_off[cs + 1] - seg_off[cs]), th_i, th_e, m_i, m_e, v_i, v_e,
+                                         gi, ge, lane, D);
+            }
+            __syncthreads();
+        }
+    }
+
     // ---- producer cursor: the next interaction to request.  (pr, ps, pk): range, segment, sorted position;
     //      pr >= NR: exhausted.  Long segments (pre-reduced by the chunks kernel) are skipped.
     int pr = g, ps = 0, psb = 0, pk = 0, pend = 0, pend_nx = 0, nsa = 0, nsb = 0, n_q = 0, pid_q = 0;
@@ -421,6 +492,11 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
             cend = cend_nx;
             cend_nx = (cs + 2 <= n_seg) ? seg_off[cs + 2] : 0;
             if (cs + 1 < n_seg) row_nx = seg_row[cs + 1];
+            int c0 = 0, c1 = 0;
+            if (end - beg > long_len) {
+                c0 = a.plan.seg_chunk[cs]; c1 = a.plan.seg_chunk[cs + 1];
+                if (c1 - c0 > HOT_CHUNKS) continue;           // reduced by a whole CTA above
+            }
             Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
             load_row<VEC, NV>(th_i, a.own_inv_in, row, D, lane);
             load_row<VEC, NV>(th_e, a.own_env_in, row, D, lane);
@@ -434,7 +510,6 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
             if (end - beg > long_len) {
-                const int c0 = a.plan.seg_chunk[cs], c1 = a.plan.seg_chunk[cs + 1];
                 for (int c = c0; c < c1; ++c) {
                     Row<VEC, NV> pi, pe;
                     load_row<VEC, NV>(pi, a.chunk_part, (int64_t)c * 2, D, lane);
@@ -541,12 +616,15 @@ __global__ void sched_write_kernel(float2* sched, int step, float step_size, flo
     else sched[step] = make_float2(step_size, inv_bc2_sqrt);
 }
 
-constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_THREADS = 256;     // threads that run the epilogue
+constexpr int TAIL_SLICES = 4;        // the column sums over the per-CTA partials are cut into this many row slices,
+                                      // one per group of TAIL_THREADS threads (the sum was 30-40 us of a 0.38 ms step
+                                      // on the dataset-scale configs with one slice)
 constexpr int P_DB = 8, P_CNT = 16, P_DW = 24;
 
 __device__ __forceinline__ double block_sum_double(double v, double* sbuf) {
     __syncthreads();
-    sbuf[threadIdx.x] = v;
+    if (threadIdx.x < TAIL_THREADS) sbuf[threadIdx.x] = v;
     __syncthreads();
     for (int s = TAIL_THREADS / 2; s > 0; s >>= 1) {
         if ((int)threadIdx.x < s) sbuf[threadIdx.x] += sbuf[threadIdx.x + s];
@@ -555,24 +633,41 @@ __device__ __forceinline__ double block_sum_double(double v, double* sbuf) {
     return sbuf[0];
 }
 
-__global__ void __launch_bounds__(TAIL_THREADS) tail_kernel(TailArgs a) {
-    extern __shared__ double stot[];          // [P] totals, then [TAIL_THREADS] scratch
+__global__ void __launch_bounds__(TAIL_THREADS * TAIL_SLICES) tail_kernel(TailArgs a) {
+    extern __shared__ double stot[];          // [P] totals, [TAIL_THREADS] scratch, [TAIL_SLICES][P] slice sums
     double* sbuf = stot + a.P;
-    const int tid = threadIdx.x;
+    double* sslice = sbuf + TAIL_THREADS;
     const int K = a.K, D = a.D, KD = a.K * a.D;
-    for (int idx = tid; idx < a.P; idx += TAIL_THREADS) {
-        // four interleaved accumulators (fixed assignment => still deterministic) keep four loads in flight
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int b = 0;
-        for (; b + 3 < a.n_partials; b += 4) {
-            s0 += (double)a.partials[(int64_t)b * a.P + idx];
-            s1 += (double)a.partials[(int64_t)(b + 1) * a.P + idx];
-            s2 += (double)a.partials[(int64_t)(b + 2) * a.P + idx];
-            s3 += (double)a.partials[(int64_t)(b + 3) * a.P + idx];
+    {
+        // fixed-order column sums: slice q = rows [q * per, (q+1) * per) of the per-CTA partials, four interleaved
+        // accumulators per thread (fixed assignment => deterministic), then the slices in order
+        const int q = threadIdx.x / TAIL_THREADS, t = threadIdx.x % TAIL_THREADS;
+        const int per = (a.n_partials + TAIL_SLICES - 1) / TAIL_SLICES;
+        const int b0 = q * per, b1 = (b0 + per < a.n_partials) ? b0 + per : a.n_partials;
+        for (int idx = t; idx < a.P; idx += TAIL_THREADS) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int b = b0;
+            for (; b + 3 < b1; b += 4) {
+                s0 += (double)a.partials[(int64_t)b * a.P + idx];
+                s1 += (double)a.partials[(int64_t)(b + 1) * a.P + idx];
+                s2 += (double)a.partials[(int64_t)(b + 2) * a.P + idx];
+                s3 += (double)a.partials[(int64_t)(b + 3) * a.P + idx];
+            }
+            for (; b < b1; ++b) s0 += (double)a.partials[(int64_t)b * a.P + idx];
+            sslice[q * a.P + idx] = (s0 + s1) + (s2 + s3);
         }
-        for (; b < a.n_partials; ++b) s0 += (double)a.partials[(int64_t)b * a.P + idx];
-        stot[idx] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (threadIdx.x < TAIL_THREADS) {
+            for (int idx = t; idx < a.P; idx += TAIL_THREADS) {
+                double s = 0.0;
+#pragma unroll
+                for (int qq = 0; qq < TAIL_SLICES; ++qq) s += sslice[qq * a.P + idx];
+                stot[idx] = s;
+            }
+        }
     }
+    // the epilogue below runs on the first TAIL_THREADS threads; the others only take part in the barriers
+    const int tid = threadIdx.x < TAIL_THREADS ? (int)threadIdx.x : (1 << 30);
     __syncthreads();
     const double Bf = (double)a.B, Df = (double)D;
     const AdamScalars adam = with_dyn(a.adam, a.dyn);
@@ -813,8 +908,9 @@ int launch_sched_write(float2* sched, int step, const AdamScalars& s, const invp
 }
 
 int launch_tail(const TailArgs& a, cudaStream_t stream) {
-    size_t smem = (size_t)(a.P + TAIL_THREADS) * sizeof(double);
-    tail_kernel<<<1, TAIL_THREADS, smem, stream>>>(a);
+    size_t smem = (size_t)(a.P * (1 + TAIL_SLICES) + TAIL_THREADS) * sizeof(double);
+    INVPREF_SET_SMEM_ONCE(tail_kernel, smem);
+    tail_kernel<<<1, TAIL_THREADS * TAIL_SLICES, smem, stream>>>(a);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

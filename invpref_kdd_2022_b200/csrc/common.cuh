@@ -6,6 +6,14 @@
 
 #include "invpref_b200.h"
 
+// A/B switches of the round-2 instruction diet (compile-time; -DNAME=0 builds the round-1 arithmetic)
+#ifndef INVPREF_FTZ_ADAM
+#define INVPREF_FTZ_ADAM 1
+#endif
+#ifndef INVPREF_DIST_SOFTMAX
+#define INVPREF_DIST_SOFTMAX 1
+#endif
+
 namespace invpref {
 
 // One embedding row is handled by a GROUP of 16 lanes; lane l owns NV vectors of VEC floats at
@@ -124,8 +132,16 @@ struct PlanSide {
     int32_t* range_start; // [R+1] cost-balanced contiguous segment ranges: range r = segments
                           //       [range_start[r], range_start[r+1]); R = counters[3] = plan_ranges(B)
     uint32_t* touched;    // [ceil(rows/32)] bitmap of rows that have a segment
+    int32_t* hot_list;    // [max_chunks / HOT_CHUNKS + 1] segments with more than HOT_CHUNKS chunks (counters[4] of
+                          //       them, in no particular order): their chunk partials are summed by a whole CTA
     int64_t max_seg, max_chunks, rows, B;
 };
+
+// A segment that was cut into more than HOT_CHUNKS chunks (a hot item: > 16 * chunk interactions in one batch) would
+// have its chunk partials summed one after the other by a single 16-lane group -- the critical path of the whole item
+// pass on the dataset-scale configs (Yahoo: item 0 = 820 partials = 0.3 ms of a 0.38 ms step).  Such rows are listed
+// by the plan and reduced by all 16 groups of a CTA in a fixed two-level order.
+constexpr int HOT_CHUNKS = 16;
 
 inline int64_t plan_max_seg(int64_t B, int64_t rows) { return B < rows ? B : rows; }
 // Work ranges of the ring rows kernel: contiguous runs of segments of about equal cost (PLAN_CSEG per segment
@@ -152,6 +168,7 @@ inline size_t plan_side_bytes(int64_t B, int64_t rows) {
     n += align_up((size_t)S * 32);
     n += align_up((size_t)(plan_ranges(B) + 1) * 4);
     n += align_up((size_t)((rows + 31) / 32) * 4);
+    n += align_up((size_t)(plan_max_chunks(B) / HOT_CHUNKS + 1) * 4);
     return n;
 }
 
@@ -174,7 +191,8 @@ inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
     p.chunk_desc = (int32_t*)c; c += align_up((size_t)p.max_chunks * 16);
     p.seg_desc = (int32_t*)c;   c += align_up((size_t)S * 32);
     p.range_start = (int32_t*)c; c += align_up((size_t)(plan_ranges(B) + 1) * 4);
-    p.touched = (uint32_t*)c;
+    p.touched = (uint32_t*)c;    c += align_up((size_t)((rows + 31) / 32) * 4);
+    p.hot_list = (int32_t*)c;
     return p;
 }
 
@@ -454,12 +472,20 @@ struct AdamScalars {
 // the fp32 sum, and the reciprocal's argument is >= eps.
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
+#if INVPREF_FTZ_ADAM
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+#else
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+#endif
     return r;
 }
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
+#if INVPREF_FTZ_ADAM
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+#else
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+#endif
     return r;
 }
 

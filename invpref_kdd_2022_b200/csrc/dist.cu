@@ -166,6 +166,74 @@ __global__ void __launch_bounds__(256) owner_adam_p2p_kernel(float* __restrict__
     }
 }
 
+struct PeerOut { float* p[2 * P2P_MAX_WORLD]; };
+
+// Owner side of the PUSH exchange: partials from LOCAL staging (the ranks' item passes stored them there over
+// NVLink), summed in rank order, Adam in registers, and the updated row stored into every requester's row cache
+// for the next batch (posted NVLink writes).  Same per-element arithmetic and order as owner_adam_p2p_kernel.
+template <int VEC>
+__global__ void __launch_bounds__(256) owner_adam_push_kernel(float* __restrict__ th0, float* __restrict__ th1,
+                                                              float* __restrict__ m0, float* __restrict__ m1,
+                                                              float* __restrict__ v0, float* __restrict__ v1,
+                                                              int64_t n_rows, int dim, int world,
+                                                              const float* __restrict__ stage0,
+                                                              const float* __restrict__ stage1,
+                                                              const int32_t* __restrict__ spos, PeerOut caches,
+                                                              const int32_t* __restrict__ npos, AdamScalars s) {
+    const int per_row = dim / VEC;
+    const int64_t per_table = n_rows * per_row, total = 2 * per_table;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int t = q >= per_table ? 1 : 0;
+        const int64_t rem = q - t * per_table;
+        const int64_t j = rem / per_row;
+        const int c = (int)(rem - j * per_row) * VEC;
+        const float* __restrict__ stage = t ? stage1 : stage0;
+        int sl[P2P_MAX_WORLD];
+        float part[P2P_MAX_WORLD][VEC];
+#pragma unroll
+        for (int p = 0; p < P2P_MAX_WORLD; ++p) sl[p] = (p < world) ? spos[(int64_t)p * n_rows + j] : -1;
+#pragma unroll
+        for (int p = 0; p < P2P_MAX_WORLD; ++p) {
+            if (sl[p] >= 0) {
+                ldv_sys<VEC>(stage + (int64_t)sl[p] * dim + c, part[p]);   // written by a peer: never from this SM's L1
+            } else {
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) part[p][x] = 0.f;
+            }
+        }
+        float g[VEC];
+#pragma unroll
+        for (int x = 0; x < VEC; ++x) g[x] = 0.f;
+#pragma unroll
+        for (int p = 0; p < P2P_MAX_WORLD; ++p)
+            if (sl[p] >= 0) {
+#pragma unroll
+                for (int x = 0; x < VEC; ++x) g[x] += part[p][x];
+            }
+        float* th = (t ? th1 : th0) + j * dim + c;
+        float* mm = (t ? m1 : m0) + j * dim + c;
+        float* vv = (t ? v1 : v0) + j * dim + c;
+        float pr[VEC], mr[VEC], vr[VEC];
+        ldv_stream<VEC>(th, pr);
+        ldv_stream<VEC>(mm, mr);
+        ldv_stream<VEC>(vv, vr);
+#pragma unroll
+        for (int x = 0; x < VEC; ++x) adam_update(pr[x], mr[x], vr[x], g[x], s);
+        stv<VEC>(th, pr);
+        stv_stream<VEC>(mm, mr);
+        stv_stream<VEC>(vv, vr);
+        if (npos != nullptr) {
+#pragma unroll
+            for (int p = 0; p < P2P_MAX_WORLD; ++p) {
+                if (p < world) {
+                    const int slot = npos[(int64_t)p * n_rows + j];
+                    if (slot >= 0) stv<VEC>(caches.p[t * world + p] + (int64_t)slot * dim + c, pr);
+                }
+            }
+        }
+    }
+}
+
 inline int grid_1d(int64_t work, int max_blocks = 148 * 16) {
     int64_t need = (work + 255) / 256;
     if (need < 1) need = 1;
@@ -221,6 +289,23 @@ int launch_owner_adam_p2p(float* th0, float* th1, float* m0, float* m1, float* v
     for (int i = 0; i < 2 * world; ++i) { pp.p[i] = grads_host[i]; v4 = v4 && ((uintptr_t)grads_host[i] % 16 == 0); }
     if (v4) owner_adam_p2p_kernel<4><<<grid_1d(2 * n_rows * (dim / 4)), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, pp, pos, s);
     else owner_adam_p2p_kernel<1><<<grid_1d(2 * n_rows * dim), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, pp, pos, s);
+    count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
+                           int world, const float* stage0, const float* stage1, const int32_t* spos,
+                           float* const* caches_host, const int32_t* npos, const AdamScalars& s, cudaStream_t stream) {
+    if (world < 1 || world > P2P_MAX_WORLD) return INVPREF_ERR_BAD_ARG;
+    PeerOut pp = {};
+    bool v4 = dim % 4 == 0 && ((uintptr_t)stage0 % 16 == 0) && ((uintptr_t)stage1 % 16 == 0);
+    for (float* q : {th0, th1, m0, m1, v0, v1}) v4 = v4 && ((uintptr_t)q % 16 == 0);
+    for (int i = 0; caches_host && i < 2 * world; ++i) {
+        pp.p[i] = caches_host[i];
+        v4 = v4 && ((uintptr_t)caches_host[i] % 16 == 0);
+    }
+    if (v4) owner_adam_push_kernel<4><<<grid_1d(2 * n_rows * (dim / 4)), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s);
+    else owner_adam_push_kernel<1><<<grid_1d(2 * n_rows * dim), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

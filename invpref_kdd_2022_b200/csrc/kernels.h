@@ -62,6 +62,12 @@ struct BwdSideArgs {
                                               // item pass: partner rows are read from here via plan.pseg
     const invpref_dyn* dyn;                   // optional device record overriding adam.step_size / inv_bc2_sqrt, step
                                               // (and UserPassArgs.neg_alpha): CUDA-graph replay
+    // EPI_EXPORT to peer memory (invpref_push): row r of the partial gradient goes to
+    // push_base[t * push_world + push_owner[r]] + push_index[r] * D instead of grad_inv / grad_env
+    float* const* push_base;
+    const int32_t* push_owner;
+    const int32_t* push_index;
+    int push_world;
 };
 
 int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream);
@@ -141,12 +147,19 @@ int launch_fetch_rows_p2p(const float* const* tables_host, int world, const int3
 int launch_owner_adam_p2p(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
                           int world, const float* const* grads_host, const int32_t* pos, const AdamScalars& s,
                           cudaStream_t stream);
+int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
+                           int world, const float* stage0, const float* stage1, const int32_t* spos,
+                           float* const* caches_host, const int32_t* npos, const AdamScalars& s, cudaStream_t stream);
 
 // ---- eval.cu ---------------------------------------------------------------------------------
 int launch_mask_scores(float* rating, int64_t b, int64_t n_items, const int64_t* users, const int64_t* off,
                        const int64_t* items, float value, int add, cudaStream_t stream);
 int launch_hits_from_csr(const int64_t* top, int64_t b, int k, const int64_t* users, const int64_t* off,
                          const int64_t* items, uint8_t* hits, int64_t* n_list, cudaStream_t stream);
+int launch_eval_topk(const float* Uinv, const float* Iinv, int64_t n_items, int D, int implicit, const int64_t* users,
+                     int64_t b, const int64_t* mask_off, const int64_t* mask_items, const int64_t* pool_off,
+                     const int64_t* pool_items, const int64_t* gt_off, const int64_t* gt_items, int k,
+                     int64_t* top_items, float* top_scores, uint8_t* hits, int64_t* n_gt, cudaStream_t stream);
 
 // ---- plan.cu ---------------------------------------------------------------------------------
 int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, PlanSide p, char* tmp,

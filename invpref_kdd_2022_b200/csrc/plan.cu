@@ -109,6 +109,7 @@ __global__ void write_chunks_kernel(PlanSide p, int chunk, int has_partner) {
                          (two && has_partner) ? p.partner[beg + 1] : 0, 0);
     }
     if (c1 == c0) return;
+    if (c1 - c0 > HOT_CHUNKS) p.hot_list[atomicAdd(&p.counters[4], 1)] = (int32_t)s;   // order is irrelevant
     for (int32_t c = c0; c < c1; ++c) {
         int32_t b = beg + (c - c0) * chunk;
         int32_t e = b + chunk < end ? b + chunk : end;

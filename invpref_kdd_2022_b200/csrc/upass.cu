@@ -107,23 +107,35 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
         if (LAZY && lane == 11) cp_async<4>(smem_addr(meta + UM_SEGS + stg * 4 + 3), a.side.last_step + row);
     };
 
+    // Segment of this group's ordinal o: round o of the segments, taken in SNAKE order (group g takes g in even
+    // rounds and ng-1-g in odd ones).  Segments are sorted by row id and the ids by popularity (the hot users of a
+    // batch come first), so with plain strides group 0 would collect the longest segment of every round: on the
+    // dataset-scale configs, a few segments per group, the slowest group set the kernel time (18 % of the warp
+    // samples sat at the final barrier).  Only the last round can be incomplete, so the first missing segment ends
+    // a group's walk.
+#ifdef INVPREF_AB_NOSNAKE
+    auto seg_at = [&](int o) { return o * ng + s0; };
+#else
+    auto seg_at = [&](int o) { return o * ng + ((o & 1) ? ng - 1 - s0 : s0); };
+#endif
+
     // prologue: descriptors of the first two segments (the only exposed latency), then group A_0
-    request_desc(0, s0);
-    request_desc(1, s0 + ng);
+    request_desc(0, seg_at(0));
+    request_desc(1, seg_at(1));
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp(gmask);
     if (s0 < n_seg) request_segment(0, meta + UM_DESC);
-    request_desc(2, s0 + 2 * ng);
+    request_desc(2, seg_at(2));
     cp_async_commit();
 
     int ord = 0;
-    for (int sgm = s0; sgm < n_seg; sgm += ng, ++ord) {
+    for (int sgm = s0; sgm < n_seg; sgm = seg_at(++ord)) {
         const int stg = ord & 1;
         cp_async_wait<0>();      // A_ord: this segment's rows and scalars, the next segment's descriptor
         __syncwarp(gmask);
-        if (sgm + ng < n_seg) request_segment(stg ^ 1, meta + UM_DESC + ((ord + 1) & 3) * 8);
-        request_desc(ord + 3, sgm + 3 * ng);     // its slot held this group's previous segment
+        if (seg_at(ord + 1) < n_seg) request_segment(stg ^ 1, meta + UM_DESC + ((ord + 1) & 3) * 8);
+        request_desc(ord + 3, seg_at(ord + 3));     // its slot held this group's previous segment
         cp_async_commit();       // A_{ord+1}
 
         const int4 dA = *reinterpret_cast<const int4*>(meta + UM_DESC + (ord & 3) * 8);       // row, begin, end, n0

@@ -3,101 +3,176 @@
 Fixed global workload (strong scaling): the same global batches as the 1-GPU run are split over the ranks.
 Timed region: K steps between a barrier + synchronize on both sides, CUDA events on every rank, MAX over
 ranks; value = K * global_batch / that time.
+
+Legs of the one JSON line rank 0 prints:
+  headline        C5 (10 M x 1 M, D 64, B 2^22), users + items row-sharded, item exchange over peer memory
+                  (INVPREF_EXCHANGE = push (default) | pull | nccl);
+  parity_vs_1gpu  a reduced shape trained for a few steps by the N ranks (same exchange) AND by rank 0 alone: losses
+                  and every gathered table compared (tolerance: the summation order of the item partials differs), plus
+                  bit-equality of the peer-memory exchange with the NCCL all-to-all exchange on the real ranks;
+  configs.c4      MIND-shaped config (BASELINE.json configs[3]: "data-parallel at 1/2/4/8 B200") on the same ranks.
 """
 from __future__ import annotations
 
 import json
 import os
+import time
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 
-def run(args, w):
-    from invpref_kdd_2022_b200 import _lib
-    from invpref_kdd_2022_b200.parallel import DistDriver, ReplicatedTrainer, ShardedTrainer
-    import bench as B
+def _exchange_mode():
+    m = os.environ.get("INVPREF_EXCHANGE", "").lower()
+    if m in ("push", "pull", "nccl"):
+        return m
+    return "nccl" if os.environ.get("INVPREF_P2P", "1") == "0" else "push"
 
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-    local = int(os.environ.get("LOCAL_RANK", rank))
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
-    # stdout carries exactly one JSON line: NCCL's version banner / debug log (NCCL_DEBUG from the environment or
-    # nccl.conf) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    dist.init_process_group("nccl", device_id=dev)
-    drv = DistDriver()
+
+def make_sharded(w, U, I, Bg, rank, world, dev, mode, init=None, lazy=True):
+    """A ShardedTrainer wired for `mode`; falls back (all ranks together) to the NCCL exchange if symmetric memory
+    is unavailable.  Returns (trainer, note)."""
+    from invpref_kdd_2022_b200.parallel import ShardedTrainer, SymmetricItemStorage
     K, D = w["K"], w["D"]
-    nb = max(1, min(args.nbatch, args.steps + args.warmup))
+    cache_rows = min(I, Bg // world * 2 + 1024)
+    stage_rows = min(2 * cache_rows, (I + world - 1) // world * world) if mode == "push" else 0
+    store, why = None, "disabled (INVPREF_EXCHANGE=nccl)"
+    if mode != "nccl":
+        try:
+            store = SymmetricItemStorage(I, D, world, cache_rows, dev, dist.group.WORLD, stage_rows=stage_rows)
+            why = ""
+        except Exception as ex:      # noqa: BLE001 -- any failure means "use NCCL"
+            store, why = None, f"{type(ex).__name__}: {ex}"[:200]
+    ok = torch.tensor([1 if (store is not None or mode == "nccl") else 0], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        store, mode = None, "nccl"
+    tr = ShardedTrainer(U, I, K, D, w["implicit"], w["roe"], w["ree"], w["lr"], rank, world, dev,
+                        cache_rows=cache_rows, alloc=store.alloc if store is not None else None, init=init, lazy=lazy,
+                        stage_rows=stage_rows if store is not None else 0)
+    if store is not None:
+        tr.enable_p2p(store.ptrs("Iinv"), store.ptrs("Ienv"), store.ptrs("gcache0"), store.ptrs("gcache1"))
+        note = "peer memory (torch symmetric memory), NVLink pulls"
+        if mode == "push":
+            tr.enable_push([[store.ptrs(f"stage{par}{t}") for t in range(2)] for par in range(2)],
+                           [store.ptrs(f"cache{t}") for t in range(2)])
+            note = "peer memory (torch symmetric memory): item pass pushes partial gradients into the owners' " \
+                   "staging, owners push updated rows into the requesters' next-batch caches (posted NVLink writes)"
+        tr._store = store
+    else:
+        note = "NCCL all-to-all (" + (why or "a peer could not map symmetric memory") + ")"
+    torch.cuda.synchronize()
+    dist.barrier()                       # every shard initialised before anyone touches a peer's memory
+    return tr, note, mode
+
+
+def prepare_all(tr, drv, batches, dev):
+    t = lambda a: torch.from_numpy(a).to(dev)
+    prepared = []
+    for (u, i, y, e) in batches:
+        sb = drv.run(tr.prepare_gen(t(u), t(i), t(y)))
+        le = t(e)[sb.sel].contiguous()
+        sw = tr.hot.stat_envs(le, tr.hot.env_hist(le))[1] if le.numel() else torch.zeros(0, device=dev)
+        prepared.append((sb, le, sw))
+    return prepared
+
+
+def parity_check(rank, world, dev, mode, drv):
+    """A few steps of a reduced shape on the REAL ranks vs the same batches on rank 0 alone (1-GPU engine), and the
+    peer-memory exchange vs the NCCL exchange bit for bit.  Returns a dict on rank 0."""
+    import bench as B
+    from invpref_kdd_2022_b200.engine import HotPath
+    w = dict(B.WORKLOADS["c5"], U=400_000, I=60_000, B=1 << 18)
+    steps = 4
+    U, I, Bg, batches = B.synth_batches(w, steps, seed=77)
+    kw = dict(alpha=1.0, use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
+    init = B.make_tables(w, dev, U=U, I=I, seed=123)                 # same seed on every rank: identical tables
+    res = {}
+    for m in dict.fromkeys((mode, "nccl")):
+        tr, _, got = make_sharded(w, U, I, Bg, rank, world, dev, m, init=init)
+        prep = prepare_all(tr, drv, batches, dev)
+        losses = []
+        for s in range(steps):
+            sb, le, sw = prep[s]
+            nxt = prep[s + 1][0] if s + 1 < steps else None
+            losses.append(drv.run(tr.step_gen(sb, le, sw, next_sb=nxt, **kw)).clone())
+        tr.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        res[m] = (torch.stack(losses), {k: v.clone() for k, v in tr.local_tables().items()}, got)
+        del tr, prep
+        torch.cuda.empty_cache()
+    # (1) exchange paths bit-identical on every rank
+    same = 1
+    if mode != "nccl" and res[mode][2] == mode:
+        a, b = res[mode], res["nccl"]
+        same = int(torch.equal(a[0], b[0]) and all(torch.equal(a[1][k], b[1][k]) for k in a[1]))
+    flag = torch.tensor([same], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    # (2) against one GPU: gather the shards on rank 0
+    losses, loc, _ = res[mode]
+    out = None
+    gathered = {}
+    for k in ("Uinv", "Uenv", "Iinv", "Ienv"):
+        rows = (U if k[0] == "U" else I)
+        per = (rows + world - 1) // world
+        pad = torch.zeros((per, w["D"]), device=dev)
+        pad[:loc[k].shape[0]] = loc[k]
+        bufs = [torch.zeros_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, bufs, dst=0)
+        if rank == 0:
+            full = torch.zeros((per * world, w["D"]), device=dev)
+            for r in range(world):
+                full[r::world] = bufs[r]
+            gathered[k] = full[:rows]
+    if rank == 0:
+        hp = HotPath({k: v.clone() for k, v in init.items()}, w["implicit"], w["roe"], w["ree"], lr=w["lr"], lazy=True)
+        ref_losses = []
+        for (u, i, y, e) in batches:
+            u, i, y, e = (torch.from_numpy(a).to(dev) for a in (u, i, y, e))
+            sw = hp.stat_envs(e, hp.env_hist(e))[1]
+            ref_losses.append(hp.train_step(u, i, y, e, sw, **kw).clone())
+        hp.flush()
+        ref_losses = torch.stack(ref_losses)
+        nerr = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        terr = {k: nerr(gathered[k], hp.params[k]) for k in gathered}
+        terr.update({k: nerr(loc[k], hp.params[k]) for k in ("E", "W", "b")})
+        lerr = float(((losses - ref_losses).abs() / ref_losses.abs()).max())
+        out = {"shape": f"U={U} I={I} D={w['D']} K={w['K']} B={Bg}, {steps} steps, exchange={res[mode][2]}",
+               "max_rel_loss_err": lerr, "max_table_err": max(terr.values()), "table_err": terr,
+               "tolerance": {"loss": 1e-5, "tables": 2e-4,
+                             "why": "the item partials of a row are summed per rank, then across ranks in rank order: "
+                                    "a different (fixed) order than the single-GPU sorted order"},
+               "pass": bool(lerr <= 1e-5 and max(terr.values()) <= 2e-4),
+               "peer_memory_bitwise_equals_nccl": bool(int(flag.item()))}
+        del hp
+    del res, gathered
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return out
+
+
+def timed_sharded(args, w, rank, world, dev, mode, drv, nb, steps, warmup, want_e2e=True):
+    """Times `steps` sharded steps of workload `w`; returns the pieces of the JSON line (rank 0) or None."""
+    import bench as B
+    from invpref_kdd_2022_b200 import _lib
+    K, D = w["K"], w["D"]
     U, I, Bg, batches = B.synth_batches(w, nb)
     P = 2 * (U + I) * D + 2 * K * D + K
-    sharded = P * 4 > 2.5e8                       # dataset-scale tables are replicated (SURVEY.md §8e)
     kw = dict(alpha=1.0, use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
-    t = lambda a: torch.from_numpy(a).to(dev)
+    tr, note, mode = make_sharded(w, U, I, Bg, rank, world, dev, mode)
+    prepared = prepare_all(tr, drv, batches, dev)
 
-    p2p_note = "off"
-    if sharded:
-        cache_rows = min(I, Bg // world * 2 + 1024)
-        # item exchange over peer memory (NVLink loads from torch symmetric memory) unless unavailable or
-        # INVPREF_P2P=0; every rank must take the same path, so the outcome is agreed on with an all-reduce
-        store, why = None, "disabled (INVPREF_P2P=0)"
-        if os.environ.get("INVPREF_P2P", "1") != "0":
-            try:
-                from invpref_kdd_2022_b200.parallel import SymmetricItemStorage
-                store = SymmetricItemStorage(I, D, world, cache_rows, dev, dist.group.WORLD)
-                why = ""
-            except Exception as ex:      # noqa: BLE001 -- any failure means "use NCCL"
-                store, why = None, f"{type(ex).__name__}: {ex}"[:200]
-        ok = torch.tensor([1 if store is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            store = None
-        tr = ShardedTrainer(U, I, K, D, w["implicit"], w["roe"], w["ree"], w["lr"], rank, world, dev,
-                            cache_rows=cache_rows, alloc=store.alloc if store is not None else None)
-        if store is not None:
-            tr.enable_p2p(store.ptrs("Iinv"), store.ptrs("Ienv"), store.ptrs("gcache0"), store.ptrs("gcache1"))
-            p2p_note = "peer memory (torch symmetric memory, NVLink loads)"
-        else:
-            p2p_note = "NCCL all-to-all (" + (why or "a peer could not map symmetric memory") + ")"
-        torch.cuda.synchronize()
-        dist.barrier()                   # every shard initialised before anyone reads a peer's rows
-        prepared = []
-        for (u, i, y, e) in batches:
-            sb = drv.run(tr.prepare_gen(t(u), t(i), t(y)))
-            le = t(e)[sb.sel].contiguous()
-            cw, sw = tr.hot.stat_envs(le, tr.hot.env_hist(le)) if le.numel() else (None, torch.zeros(0, device=dev))
-            prepared.append((sb, le, sw))
+    def step(s):
+        sb, le, sw = prepared[s % nb]
+        return drv.run(tr.step_gen(sb, le, sw, next_sb=prepared[(s + 1) % nb][0], **kw))
 
-        def step(s):
-            sb, le, sw = prepared[s % nb]
-            return drv.run(tr.step_gen(sb, le, sw, next_sb=prepared[(s + 1) % nb][0], **kw))
-        mode = f"users+items row-sharded (mod {world}), interactions routed to the user's owner, " \
-               f"item rows/grads exchanged over {p2p_note}, E/W/b all-reduce"
-    else:
-        g = torch.Generator(device=dev).manual_seed(17373331)
-        tr = ReplicatedTrainer(B.make_tables(w, dev), w["implicit"], w["roe"], w["ree"], w["lr"], rank, world)
-        prepared = []
-        for (u, i, y, e) in batches:
-            a, b = tr.chunk(0, Bg)
-            le = t(e[a:b])
-            cw, sw = tr.hot.stat_envs(le, tr.hot.env_hist(le)) if le.numel() else (None, torch.zeros(0, device=dev))
-            lu, li = t(u[a:b]), t(i[a:b])
-            plan = tr.hot.new_plan(lu, li) if lu.numel() else None
-            prepared.append((lu, li, t(y[a:b]), le, sw, plan))
-
-        def step(s):
-            lu, li, ly, le, sw, plan = prepared[s % nb]
-            return drv.run(tr.step_gen(lu, li, ly, le, sw, Bg, plan=plan, **kw))
-        mode = f"tables replicated, batch chunked over {world} ranks, flat gradient all-reduce"
-
-    for s in range(args.warmup):
+    for s in range(warmup):
         step(s)
-    if sharded:
-        tr.flush()
+    tr.flush()
     torch.cuda.synchronize()
-    if sharded:
-        tr.phase_events = []
+    tr.phase_events = []
     clocks = B.ClockSampler(dev.index)
     if rank == 0:
         clocks.start()
@@ -106,87 +181,156 @@ def run(args, w):
     dist.barrier()
     torch.cuda.synchronize()
     ev0.record()
-    for s in range(args.warmup, args.warmup + args.steps):
+    for s in range(warmup, warmup + steps):
         loss = step(s)
-    if sharded:
-        tr.flush()        # lazy Adam: every local user row brought up to date inside the timed region
+    tr.flush()            # lazy Adam: every local user row brought up to date inside the timed region
     ev1.record()
     torch.cuda.synchronize()
     dist.barrier()
     launches = _lib.launch_count() - l0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item()) / args.steps
+    ms = float(ms.item()) / steps
     assert torch.isfinite(loss).all()
     clk = clocks.stop() if rank == 0 else None
     phases = {}
-    if sharded and tr.phase_events:
-        evs = tr.phase_events
-        for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
-            if n1 != "start":
-                phases[n1] = phases.get(n1, 0.0) + e0.elapsed_time(e1) / args.steps
-        info = [sb.route.n_cache for sb, _, _ in prepared], [int(sb.users.numel()) for sb, _, _ in prepared]
-        phases["cache_rows"], phases["local_batch"] = info[0][0], info[1][0]
-    # ---- e2e at N GPUs: the per-step mutable inputs of this rank's share (scores, envs, sample weights) come
-    # from pinned host memory every step, the six losses go back to the host, host-synchronised per step.
-    # (ids and their routing / sort-segment plans are static per batch and stay resident, as in the trainer.)
-    if sharded:
-        tr.phase_events = None
-        host = [(sb.scores.cpu().pin_memory(), le.cpu().pin_memory(), sw.cpu().pin_memory()) for sb, le, sw in prepared]
-    else:
-        host = [(p[2].cpu().pin_memory(), p[3].cpu().pin_memory(), p[4].cpu().pin_memory()) for p in prepared]
-    h_loss = torch.empty(6).pin_memory()
-    e2e_steps = max(3, min(args.steps, 10))
+    evs = tr.phase_events
+    for (n0, e0), (n1, e1) in zip(evs[:-1], evs[1:]):
+        if n1 != "start":
+            phases[n1] = phases.get(n1, 0.0) + e0.elapsed_time(e1) / steps
+    tr.phase_events = None
+    phases["cache_rows"], phases["local_batch"] = prepared[0][0].route.n_cache, int(prepared[0][0].users.numel())
+    # bytes one rank moves over NVLink per step (either direction): partial gradients out + updated rows in/out
+    xrows = float(np.mean([sb.route.n_cache - sb.route.recv_splits[rank] for sb, _, _ in prepared]))
+    nvl = {"rows_per_rank_per_direction": xrows, "bytes_per_rank_per_direction": xrows * D * 4 * 2}
+    ex_ms = phases.get("item_adam", 0.0) + phases.get("prefetch_next", 0.0) + phases.get("grad_a2a", 0.0) + \
+        phases.get("small", 0.0)
+    nvl["exchange_ms_rank0"] = ex_ms
+    if ex_ms > 0:
+        nvl["achieved_GBs_per_direction"] = 2 * nvl["bytes_per_rank_per_direction"] / (ex_ms * 1e-3) / 1e9
+        nvl["frac_of_900"] = nvl["achieved_GBs_per_direction"] / 900.0
+        nvl["note"] = "gradients out + rows in, over the time of everything after the local step (barriers included); " \
+                      "in push mode most gradient bytes move DURING the item pass and are not on this clock"
+    e2e = None
+    if want_e2e:
+        # e2e at N GPUs: per step every rank copies its share's ids (local user rows, item cache slots), scores, envs
+        # and sample weights from pinned host memory and rebuilds the sort-segment plan of its share on a loader
+        # stream (as the 1-GPU e2e leg does); the item ROUTE (which rows come from which owner) is static per batch
+        # and stays resident.  The six losses go back to the host every step, host-synchronised.
+        host = [tuple(x.cpu().pin_memory() for x in (sb.users, sb.route.slots, sb.scores, le, sw))
+                for sb, le, sw in prepared[:min(nb, 4)]]
+        nh = len(host)
+        loader = torch.cuda.Stream(device=dev)
+        plan_bufs = [torch.empty(tr.hot.plan_bytes(max(int(sb.users.numel()) for sb, _, _ in prepared) + 1),
+                                 dtype=torch.uint8, device=dev) for _ in range(2)]
+        h_loss = torch.empty(6).pin_memory()
+        e2e_steps = max(3, min(steps, 10))
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step(s):
-        j = s % nb
-        hy, he, hw = host[j]
-        if sharded:
+        def issue(s):
+            j = s % nh
             sb, le, sw = prepared[j]
-            sb.scores.copy_(hy, non_blocking=True); le.copy_(he, non_blocking=True); sw.copy_(hw, non_blocking=True)
-        else:
-            prepared[j][2].copy_(hy, non_blocking=True); prepared[j][3].copy_(he, non_blocking=True)
-            prepared[j][4].copy_(hw, non_blocking=True)
-        out = step(s)
-        h_loss.copy_(out, non_blocking=True)
-        torch.cuda.synchronize()
+            with torch.cuda.stream(loader):
+                for dst, src in zip((sb.users, sb.route.slots, sb.scores, le, sw), host[j]):
+                    dst.copy_(src, non_blocking=True)
+                if sb.users.numel():
+                    sb.plan = tr.hot.new_plan(sb.users, sb.route.slots, out=plan_bufs[s % 2])
+                ready[s % 2].record(loader)
 
-    e2e_step(0)
-    dist.barrier()
-    torch.cuda.synchronize()
-    import time
-    t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        e2e_step(s)
-    if sharded:
+        def e2e_step(s, last):
+            if not last:
+                issue(s + 1)
+            torch.cuda.current_stream().wait_event(ready[s % 2])
+            sb, le, sw = prepared[s % nh]
+            out = drv.run(tr.step_gen(sb, le, sw, next_sb=prepared[(s + 1) % nh][0], **kw))
+            loader.wait_stream(torch.cuda.current_stream())
+            h_loss.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+
+        issue(0)
+        e2e_step(0, False)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for s in range(1, e2e_steps + 1):
+            e2e_step(s, s == e2e_steps)
         tr.flush()
         torch.cuda.synchronize()
-    dist.barrier()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) / e2e_steps * 1e3], device=dev)
-    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms.item())
-    h2d = torch.tensor([sum(t_.numel() * t_.element_size() for t_ in host[0])], device=dev, dtype=torch.float64)
-    dist.all_reduce(h2d)
+        dist.barrier()
+        e2e_ms = torch.tensor([(time.perf_counter() - t0) / e2e_steps * 1e3], device=dev)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([sum(t_.numel() * t_.element_size() for t_ in host[0])], device=dev, dtype=torch.float64)
+        dist.all_reduce(h2d)
+        e2e = {"value": Bg / (float(e2e_ms.item()) * 1e-3), "unit": "interactions/s", "ms_per_step": float(e2e_ms.item()),
+               "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 24 * world, "steps": e2e_steps,
+               "note": "per step every rank copies its share (local user rows, item cache slots, scores, envs, sample "
+                       "weights) from pinned host memory and rebuilds its sort-segment plan on a loader stream under "
+                       "the previous step, runs the step, reads the six losses back, host-synchronised.  Unlike the "
+                       "1-GPU leg the interactions arrive already routed to their user's owner and the item route "
+                       "(which rows from which owner) is resident: building it needs a collective per batch"}
+    del tr, prepared
+    torch.cuda.empty_cache()
+    return dict(ms=ms, Bg=Bg, P=P, D=D, K=K, note=note, mode=mode, launches=launches, clk=clk, phases=phases, nvl=nvl,
+                e2e=e2e, loss=float(loss[5]))
+
+
+def run(args, w):
+    from invpref_kdd_2022_b200.parallel import DistDriver
+    import bench as B
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    # stdout carries exactly one JSON line: NCCL's version banner / debug log goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
+    drv = DistDriver()
+    mode = _exchange_mode()
+    nb = max(1, min(args.nbatch or 8, args.steps + args.warmup))
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(rank, world, dev, mode, drv)
+        except Exception as ex:      # noqa: BLE001 -- reported, never fatal for the timing line
+            parity = {"pass": False, "error": f"{type(ex).__name__}: {ex}"[:300]}
+    r = timed_sharded(args, w, rank, world, dev, mode, drv, nb, args.steps, args.warmup)
+    legs = {}
+    if not args.no_config_legs and args.workload == "c5":
+        w4 = B.WORKLOADS["c4"]
+        try:
+            r4 = timed_sharded(args, w4, rank, world, dev, mode, drv, 16, max(args.steps, 32), args.warmup,
+                               want_e2e=False)
+            legs["c4"] = {"workload": w4["name"], "value": r4["Bg"] / (r4["ms"] * 1e-3), "unit": "interactions/s",
+                          "ms_per_step": r4["ms"], "global_batch": r4["Bg"], "distinct_batches": 16,
+                          "parallelism": f"row-sharded over {world} ranks, {r4['note']}",
+                          "launches_per_step": r4["launches"] / max(args.steps, 32), "rank0_phase_ms": r4["phases"],
+                          "final_loss": r4["loss"]}
+        except Exception as ex:      # noqa: BLE001
+            legs["c4"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     peak, peak_src = B.measured_peaks()
-    sbytes = B.step_bytes(Bg, D, K, P)
     if rank == 0:
+        Bg, P, D, K, ms = r["Bg"], r["P"], r["D"], r["K"], r["ms"]
+        sbytes = B.step_bytes(Bg, D, K, P)
+        mode_s = f"users+items row-sharded (mod {world}), interactions routed to the user's owner, item rows/grads " \
+                 f"exchanged over {r['note']}, E/W/b all-reduce"
         line = {"metric": "train interactions/sec (fwd+bwd+Adam)", "value": Bg / (ms * 1e-3),
                 "unit": "interactions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["name"], "global_batch": Bg, "params": P, "distinct_batches": nb,
-                           "l2": "inputs larger than L2" if sharded else "tables fit in L2 (no flush)",
-                           "parallelism": mode},
-                "roofline": {"bound": "hbm", "kernel": "fused train step (all kernels, all ranks)",
+                           "l2": "inputs larger than L2" if P * 4 > 2.5e8 else "tables fit in L2 (no flush)",
+                           "parallelism": mode_s, "exchange": r["mode"]},
+                "roofline": {"bound": "hbm", "kernel": "fused train step (all kernels, all ranks), SURVEY.md 8d bytes",
                              "achieved": sbytes / (ms * 1e-3) / 1e9, "peak": peak * world,
                              "peak_source": peak_src + f" x {world} GPUs", "unit": "GB/s",
-                             "frac": sbytes / (ms * 1e-3) / 1e9 / (peak * world), "traffic": None},
-                "e2e": {"value": Bg / (e2e_ms * 1e-3), "unit": "interactions/s", "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 24 * world, "steps": e2e_steps,
-                        "note": "per step every rank copies its share's scores / envs / sample weights from pinned "
-                                "host memory, runs the step, reads the six losses back, host-synchronised; ids, "
-                                "routing and sort-segment plans are static per batch and stay resident"},
-                "gpu_launches": int(launches), "clocks": clk, "final_loss": float(loss[5]),
-                "rank0_phase_ms": phases}
+                             "frac": None, "traffic": None,
+                             "note": "8d convention bytes / time; with lazy Adam the step moves fewer bytes than the "
+                                     "convention, so no fraction is claimed here (see the 1-GPU line)"},
+                "nvlink": r["nvl"], "e2e": r["e2e"], "gpu_launches": int(r["launches"]), "clocks": r["clk"],
+                "final_loss": r["loss"], "rank0_phase_ms": r["phases"], "parity_vs_1gpu": parity}
+        if legs:
+            line["configs"] = legs
         print(json.dumps(line), flush=True)
+    dist.barrier()
     dist.destroy_process_group()

@@ -214,11 +214,12 @@ class HotPath:
     def train_step(self, users, items, scores, envs, weights, *, c_inv, c_ea, c_env, c_L2, c_L1, alpha,
                    use_class_rw, use_rec_rw, plan: Optional[torch.Tensor] = None,
                    loss_out: Optional[torch.Tensor] = None, grads_out: Optional[Dict[str, torch.Tensor]] = None,
-                   global_batch: int = 0, flags: int = 0, dyn: Optional[int] = None):
+                   global_batch: int = 0, flags: int = 0, dyn: Optional[int] = None, push=None):
         """train.py:771-844 in one library call.  Returns the device tensor holding the six losses.
 
         ``dyn``: device address of an ``invpref_dyn`` record; the kernels then read Adam's bias corrections,
         alpha and the step number from it instead of from the launch arguments (CUDA-graph replay).
+        ``push``: an ``_lib.Push`` (``invpref_push``): exported item gradients go to peer memory.
 
         ``flags`` / ``global_batch``: data-parallel use, see ``invpref_hyper`` in the header; tables of an
         exported group are neither updated nor swapped."""
@@ -231,7 +232,8 @@ class HotPath:
         self.step += 1
         hyper = _lib.Hyper(float(c_inv), float(c_ea), float(c_env), float(c_L2), float(c_L1), float(alpha), self.lr,
                            self.betas[0], self.betas[1], self.eps, self.step, int(bool(use_class_rw)),
-                           int(bool(use_rec_rw)), int(global_batch), int(flags), 0, dyn)
+                           int(bool(use_rec_rw)), int(global_batch), int(flags), 0, dyn,
+                           C.cast(C.pointer(push), C.c_void_p) if push is not None else None)
         p_in = _lib.make_params(self.params)
         out = dict(self.params)
         swap = [k for k in TABLES if not (flags & (_lib.EXPORT_USER_GRADS if k[0] == "U" else _lib.EXPORT_ITEM_GRADS))

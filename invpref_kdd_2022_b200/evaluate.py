@@ -38,11 +38,45 @@ class ExplicitTestManager:
 class ImplicitTestManager:
     """reference evaluate.py:59-175; result = {'ndcg': {k: v}, 'recall': {k: v}, 'precision': {k: v}}."""
 
-    def __init__(self, model, data_loader, test_batch_size: int, top_k_list: list, use_item_pool: bool = False):
+    def __init__(self, model, data_loader, test_batch_size: int, top_k_list: list, use_item_pool: bool = False,
+                 fused: bool = True):
+        """``fused``: on an InvPref model that lives on the GPU the whole batch -- scores, masking, pool highlight,
+        top-k, hit look-up -- is ONE library kernel (``invpref_eval_topk``) and the [b, item_num] rating matrix is
+        never materialised; ``fused=False`` keeps the step-by-step device path (``model.predict`` -> mask kernels ->
+        ``torch.topk`` -> hit kernel)."""
         self.model, self.data_loader = model, data_loader
         self.batch_size = test_batch_size
         self.top_k_list = sorted(top_k_list)
         self.use_item_pool = use_item_pool
+        self.fused = fused
+
+    def _hits_fused(self, users_t, kmax):
+        """One kernel per batch: ``invpref_eval_topk``.  Returns (hits [b, kmax] float64, n_gt [b] float64, top)."""
+        import ctypes as C
+        from . import _lib
+        hp = self.model.hot_path()
+        hp.flush()
+        dev = hp.device
+        users_t = users_t.to(dev).contiguous()
+        hp.check_ids(users_t, None, None)
+        b = users_t.numel()
+        m_off, m_items = self._csr_on("mask", dev)
+        g_off, g_items = self._csr_on("gt", dev)
+        p_off = p_items = None
+        if self.use_item_pool:
+            p_off, p_items = self._csr_on("pool", dev)
+        top = torch.empty((b, kmax), dtype=torch.int64, device=dev)
+        hits = torch.zeros((b, kmax), dtype=torch.uint8, device=dev)
+        n_gt = torch.zeros(b, dtype=torch.int64, device=dev)
+        pad = lambda t: t if t.numel() else torch.zeros(1, dtype=torch.int64, device=dev)   # empty lists: valid pointer
+        p = _lib.make_params(hp.params)
+        _lib.check(hp.lib.invpref_eval_topk(
+            C.byref(hp.desc), C.byref(p), _lib.ptr(users_t, torch.int64), b, _lib.ptr(m_off, torch.int64),
+            _lib.ptr(pad(m_items), torch.int64), _lib.ptr(p_off, torch.int64) if p_off is not None else None,
+            _lib.ptr(pad(p_items), torch.int64) if p_items is not None else None, _lib.ptr(g_off, torch.int64),
+            _lib.ptr(pad(g_items), torch.int64), int(kmax), _lib.ptr(top), None, _lib.ptr(hits), _lib.ptr(n_gt),
+            _lib.stream_ptr()), "eval_topk")
+        return hits.double(), n_gt.double(), top
 
     def _dense(self, off, items, users: np.ndarray, n_items: int, device) -> torch.Tensor:
         lens = off[users + 1] - off[users]
@@ -109,14 +143,20 @@ class ImplicitTestManager:
     def evaluate_batch(self, batch_users_tensor: torch.Tensor, batch_users_list: list, batch_users_ground_truth=None,
                        force_host: bool = False):
         users = np.asarray(batch_users_list, dtype=np.int64)
-        with torch.no_grad():
-            rating = self.model.predict(batch_users_tensor).clone()
-        dev = rating.device
         kmax = max(self.top_k_list)
-        if rating.is_cuda and not force_host:
-            hits, n_gt = self._hits_device(rating.contiguous(), batch_users_tensor.to(dev), kmax)
+        use_fused = self.fused and not force_host and hasattr(self.model, "hot_path") and kmax <= 256 \
+            and next(self.model.parameters()).is_cuda
+        if use_fused:
+            hits, n_gt, _ = self._hits_fused(batch_users_tensor, kmax)
+            dev = hits.device
         else:
-            hits, n_gt = self._hits_host(rating, users, kmax)                                   # [b, kmax] 0/1
+            with torch.no_grad():
+                rating = self.model.predict(batch_users_tensor).clone()
+            dev = rating.device
+            if rating.is_cuda and not force_host:
+                hits, n_gt = self._hits_device(rating.contiguous(), batch_users_tensor.to(dev), kmax)
+            else:
+                hits, n_gt = self._hits_host(rating, users, kmax)                               # [b, kmax] 0/1
         disc = 1.0 / torch.log2(torch.arange(2, kmax + 2, device=dev, dtype=torch.float64))
         pre, rec, ndcg = [], [], []
         for k in self.top_k_list:

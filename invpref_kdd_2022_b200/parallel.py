@@ -83,6 +83,25 @@ class DistDriver:
                 o += sp[self.rank]
 
 
+class LocalDriver:
+    """world = 1: every collective is the identity (all_reduce) or a local copy (all_to_all).  Lets the sharded
+    trainers run in a single process without a process group."""
+    world, rank = 1, 0
+
+    def run(self, gen):
+        try:
+            req = next(gen)
+            while True:
+                if req[0] == "all_to_all":
+                    _, out, inp, _, _ = req
+                    out.copy_(inp)
+                elif req[0] != "all_reduce":
+                    raise ValueError(req[0])
+                req = gen.send(None)
+        except StopIteration as stop:
+            return stop.value
+
+
 class SimDriver:
     """Runs the generators of G simulated ranks in lockstep inside one process (tests / debugging)."""
 
@@ -195,7 +214,14 @@ class ItemRoute:
         self.slot_owner = None     # int32 [n_cache] owner rank of every cache slot
         self.want_rows = None      # int64 [n_cache] owner-local row of every cache slot
         self.peer_first = None     # list[G]     first slot, in requester p's cache, of the rows it wants from me
-        self.pos = None            # int32 [G, I_loc] slot of my row j in rank p's gradient cache, or -1
+        self.pos = None            # int32 [G, I_loc] slot of my row j in rank p's (gradient / row) cache, or -1
+        # push exchange (ShardedTrainer.enable_push): owners keep a staging buffer laid out like send_rows (grouped
+        # by requester); a requester stores the partial gradient of cache slot c into owner slot_owner[c]'s staging
+        # at push_index[c]
+        self.peer_off = None       # list[G]     first staging row, at owner o, of the block of rows I want from o
+        self.push_index = None     # int32 [n_cache] row in the owner's staging buffer of every cache slot
+        self.spos = None           # int32 [G, I_loc] row in MY staging buffer of rank p's partial for my row j, or -1
+        self.n_stage = 0           # rows of my staging buffer in use (= len(send_rows))
 
 
 def build_route_gen(items_global: torch.Tensor, world: int, route: ItemRoute):
@@ -223,6 +249,15 @@ def build_route_gen(items_global: torch.Tensor, world: int, route: ItemRoute):
     peer_first = torch.zeros(world, dtype=torch.int64, device=dev)
     yield ("all_to_all", peer_first, first.to(torch.int64).contiguous(), [1] * world, [1] * world)
     route.peer_first = [int(c) for c in peer_first.tolist()]
+    # push exchange: where, in every OWNER's staging buffer (laid out like its send_rows), my block starts
+    send_off = torch.cumsum(send_counts, 0) - send_counts        # my staging: first row of each requester's block
+    peer_off = torch.zeros(world, dtype=torch.int64, device=dev)
+    yield ("all_to_all", peer_off, send_off.to(torch.int64).contiguous(), [1] * world, [1] * world)
+    route.peer_off = [int(c) for c in peer_off.tolist()]
+    slot = torch.arange(route.n_cache, device=dev)
+    own = route.slot_owner.to(torch.int64)
+    route.push_index = (peer_off[own] + slot - first[own]).to(torch.int32).contiguous()
+    route.n_stage = int(route.send_rows.numel())
     return route
 
 
@@ -239,17 +274,34 @@ def build_pos_table(route: ItemRoute, world: int, n_local_rows: int) -> torch.Te
     return pos
 
 
+def build_spos_table(route: ItemRoute, world: int, n_local_rows: int) -> torch.Tensor:
+    """spos[p, j] = row, in MY staging buffer, where rank p's item pass stores its partial gradient of my item row
+    j (-1: rank p has none).  The staging buffer is laid out like send_rows: grouped by requester, in its order."""
+    dev = route.send_rows.device
+    spos = torch.full((world, max(n_local_rows, 1)), -1, dtype=torch.int32, device=dev)
+    o = 0
+    for p in range(world):
+        n = route.send_splits[p]
+        if n:
+            spos[p, route.send_rows[o:o + n]] = (o + torch.arange(n, device=dev)).to(torch.int32)
+        o += n
+    return spos
+
+
 class SymmetricItemStorage:
     """Peer-visible storage of one rank's item shard and partial-gradient caches: ONE torch symmetric-memory
     buffer [Iinv | Ienv | gcache0 | gcache1] with the same layout on every rank, so that a peer's table is
     `buffer_ptrs[rank] + offset`.  Raises if symmetric memory is unavailable (callers fall back to NCCL)."""
 
-    def __init__(self, n_items, dim, world, cache_rows, device, group):
+    def __init__(self, n_items, dim, world, cache_rows, device, group, stage_rows=0):
         import torch.distributed._symmetric_memory as symm
         rows_max = (n_items + world - 1) // world
         pad = lambda n: (n + 63) // 64 * 64                      # 256-byte aligned sections
         sizes = [("Iinv", pad(rows_max * dim)), ("Ienv", pad(rows_max * dim)),
                  ("gcache0", pad(cache_rows * dim)), ("gcache1", pad(cache_rows * dim))]
+        if stage_rows:      # push exchange: peer-written row caches and double-buffered gradient staging
+            sizes += [("cache0", pad(cache_rows * dim)), ("cache1", pad(cache_rows * dim))]
+            sizes += [(f"stage{par}{t}", pad(stage_rows * dim)) for par in range(2) for t in range(2)]
         self.offsets, o = {}, 0
         for k, n in sizes:
             self.offsets[k] = o
@@ -288,7 +340,7 @@ class ShardedTrainer:
     """User and item tables mod-sharded by row over `world` ranks (row r of rank g holds id r*world + g)."""
 
     def __init__(self, n_users, n_items, n_envs, dim, implicit, reg_only_embed, reg_env_embed, lr, rank, world,
-                 device, cache_rows, init=None, seed=17373331, lazy=True, alloc=None):
+                 device, cache_rows, init=None, seed=17373331, lazy=True, alloc=None, stage_rows=0):
         """``alloc(name, shape) -> fp32 tensor``: storage for the buffers other ranks read in peer-memory mode
         (``Iinv``, ``Ienv``, ``gcache0``, ``gcache1``), e.g. views of a torch symmetric-memory buffer; default:
         ordinary device tensors (NCCL exchange, or simulated ranks in one process)."""
@@ -330,11 +382,21 @@ class ShardedTrainer:
                            "b": t[2 * KD:2 * KD + n_envs]}
         self.loss = self.gsmall[2 * KD + n_envs:]
         # per-batch item cache (what the local kernels see as "the item tables") and its gradient
-        self.cache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
+        self.stage_rows = int(stage_rows)
+        if alloc is not None and self.stage_rows:
+            self.cache = [alloc(f"cache{t}", (self.cache_rows, dim)).zero_() for t in range(2)]
+        else:
+            self.cache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
         if alloc is not None:
             self.gcache = [alloc(f"gcache{t}", (self.cache_rows, dim)).zero_() for t in range(2)]
         else:
             self.gcache = [torch.zeros((self.cache_rows, dim), **f32) for _ in range(2)]
+        # push exchange: double-buffered staging of the ranks' partial item gradients, [parity][table]
+        self.stage = None
+        if self.stage_rows:
+            mk = (lambda n: alloc(n, (self.stage_rows, dim)).zero_()) if alloc is not None else \
+                (lambda n: torch.zeros((self.stage_rows, dim), **f32))
+            self.stage = [[mk(f"stage{par}{t}") for t in range(2)] for par in range(2)]
         params = {"Uinv": uinv, "Uenv": uenv, "Iinv": self.cache[0], "Ienv": self.cache[1]}
         params.update(views(self.small))
         # lazy: the local user shard uses lazy dense Adam (bit-identical, see HotPath), so there is no dense
@@ -356,6 +418,7 @@ class ShardedTrainer:
         self.side = torch.cuda.Stream(device=device)
         self.phase_events = None                  # set to [] to record (name, event) marks per step (bench)
         self.p2p = None                           # (tables ptr array, grads ptr array) once enable_p2p() ran
+        self.push = None                          # push exchange state once enable_push() ran
         self.bar = torch.zeros(1, **f32)          # payload of the barrier all-reduce (peer-memory mode)
 
     def enable_p2p(self, item_inv_ptrs, item_env_ptrs, gcache0_ptrs, gcache1_ptrs):
@@ -367,6 +430,22 @@ class ShardedTrainer:
         tables = (C.c_void_p * (2 * G))(*([int(x) for x in item_inv_ptrs] + [int(x) for x in item_env_ptrs]))
         grads = (C.c_void_p * (2 * G))(*([int(x) for x in gcache0_ptrs] + [int(x) for x in gcache1_ptrs]))
         self.p2p = (tables, grads)
+
+    def enable_push(self, stage_ptrs, cache_ptrs):
+        """Push exchange on top of enable_p2p (which stays in use for the first fetch and for cluster_gen):
+        ``stage_ptrs[parity][t][rank]`` / ``cache_ptrs[t][rank]`` = device address IN THIS PROCESS of rank `rank`'s
+        staging buffer / row cache of item table t (own rank included).  The item pass then stores its partial
+        gradients straight into the owners' staging buffers and the owners, after Adam, store the updated rows
+        into the requesters' caches for the next batch: no pull kernel is left on the critical path."""
+        G = self.world
+        assert self.stage is not None and self.p2p is not None
+        base = []
+        for par in range(2):
+            flat = [int(x) for t in range(2) for x in stage_ptrs[par][t]]
+            assert len(flat) == 2 * G
+            base.append(torch.tensor(flat, dtype=torch.int64, device=self.dev))
+        caches = (C.c_void_p * (2 * G))(*[int(x) for t in range(2) for x in cache_ptrs[t]])
+        self.push = {"base": base, "caches": caches, "step": 0}
 
     def _mark(self, name):
         if self.phase_events is not None:
@@ -385,6 +464,8 @@ class ShardedTrainer:
         yield from build_route_gen(items_g[sb.sel], self.world, sb.route)
         if sb.route.n_cache > self.cache_rows:
             raise RuntimeError(f"item cache too small: {sb.route.n_cache} > {self.cache_rows}")
+        if self.stage_rows and sb.route.n_stage > self.stage_rows:
+            raise RuntimeError(f"gradient staging too small: {sb.route.n_stage} > {self.stage_rows}")
         sb.plan = self.hot.new_plan(sb.users, sb.route.slots)      # also for an empty share (sweep needs it)
         return sb
 
@@ -439,10 +520,17 @@ class ShardedTrainer:
         self._mark("fetch")
         self.gsmall.zero_()
         main = torch.cuda.current_stream()
+        push, par = None, 0
+        if self.push is not None:
+            par = self.push["step"] & 1
+            if r.n_cache:
+                push = _lib.Push(_lib.ptr(self.push["base"][par], torch.int64), _lib.ptr(r.slot_owner, torch.int32),
+                                 _lib.ptr(r.push_index, torch.int32), self.world, 0)
         if self.lazy:
             if sb.users.numel() > 0:
                 self.hot.train_step(sb.users, r.slots, sb.scores, envs, weights, plan=sb.plan, loss_out=self.loss,
-                                    grads_out=self.grads, global_batch=sb.global_batch, flags=self.flags, **kw)
+                                    grads_out=self.grads, global_batch=sb.global_batch, flags=self.flags, push=push,
+                                    **kw)
             else:   # no interaction routed here: the local rows just fall one more step behind
                 self.hot._ensure_state(())
                 self.hot._ensure_lazy()
@@ -455,7 +543,7 @@ class ShardedTrainer:
             if sb.users.numel() > 0:
                 self.hot.train_step(sb.users, r.slots, sb.scores, envs, weights, plan=sb.plan, loss_out=self.loss,
                                     grads_out=self.grads, global_batch=sb.global_batch,
-                                    flags=self.flags | _lib.DEFER_USER_SWEEP, **kw)
+                                    flags=self.flags | _lib.DEFER_USER_SWEEP, push=push, **kw)
             else:       # no interaction routed here: every local user row still moves by momentum
                 self.hot.step += 1
                 for k in ("Uinv", "Uenv"):
@@ -464,6 +552,45 @@ class ShardedTrainer:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
                 self.hot.user_sweep(sb.plan, sb.users.numel())
+        if self.push is not None:
+            # PUSH exchange.  The item pass above already stored this rank's partial item gradients into the owners'
+            # staging buffers (parity `par`).  Barrier 1 = the all-reduce of the replicated tensors' gradients: when
+            # it returns every rank's item pass -- and with it every posted NVLink write -- has completed.  Then ONE
+            # kernel per rank reduces its rows from LOCAL memory in rank order, applies Adam and stores the updated
+            # rows into the requesters' caches for the next batch.
+            yield ("all_reduce", self.gsmall)
+            self._mark("grad_a2a")
+            if r.spos is None:
+                r.spos = build_spos_table(r, self.world, self.I_loc)
+            npos = None
+            if next_sb is not None:
+                if next_sb.route.pos is None:
+                    next_sb.route.pos = build_pos_table(next_sb.route, self.world, self.I_loc)
+                npos = next_sb.route.pos
+            hyper = _lib.Hyper(0, 0, 0, 0, 0, 0, self.hot.lr, self.hot.betas[0], self.hot.betas[1], self.hot.eps,
+                               int(self.hot.step), 0, 0, 0, 0, 0)
+            _lib.check(self.hot.lib.invpref_owner_adam_push(
+                _lib.ptr(self.Iinv), _lib.ptr(self.Ienv), _lib.ptr(self.mI[0]), _lib.ptr(self.mI[1]),
+                _lib.ptr(self.vI[0]), _lib.ptr(self.vI[1]), self.I_loc, self.D, self.world,
+                _lib.ptr(self.stage[par][0]), _lib.ptr(self.stage[par][1]), _lib.ptr(r.spos, torch.int32),
+                self.push["caches"] if npos is not None else None,
+                _lib.ptr(npos, torch.int32) if npos is not None else None, C.byref(hyper), _lib.stream_ptr()),
+                "owner_adam_push")
+            self._mark("item_adam")
+            n_small = self.small.numel()
+            self.hot.adam_dense(self.small, self.msmall, self.vsmall, self.gsmall[:n_small])
+            # Barrier 2: every owner's pushes have landed before anyone's next local step reads its cache.  (The
+            # staging buffers need no barrier of their own: they alternate, and barrier 1 of the NEXT step already
+            # orders this step's owner kernels before the item pass of the step after it.)
+            yield ("all_reduce", self.bar)
+            self._mark("small")
+            if next_sb is not None:
+                self._fetched = next_sb
+            self._mark("prefetch_next")
+            main.wait_stream(self.side)
+            self._mark("sweep_wait")
+            self.push["step"] += 1
+            return self.loss
         if self.p2p is not None:
             # Peer-memory exchange.  Barrier 1 = the all-reduce of the replicated tensors' gradients: when it
             # returns, every rank's item pass has written its partial-gradient cache.  Then ONE kernel per rank

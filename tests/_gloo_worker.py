@@ -9,7 +9,8 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from invpref_kdd_2022_b200.parallel import DistDriver, ItemRoute, build_pos_table, build_route_gen  # noqa: E402
+from invpref_kdd_2022_b200.parallel import (DistDriver, ItemRoute, build_pos_table, build_route_gen,  # noqa: E402
+                                            build_spos_table)
 
 
 def main():
@@ -89,8 +90,35 @@ def main():
         want[route.send_rows[o:o + n]] += recv2[o:o + n]
         o += n
     ok_pull_p2p = bool(torch.equal(pulled, want))
+
+    # ---- the PUSH exchange's tables.  Every requester "stores" (rank + 1) * 1000 + slot for cache slot c into owner
+    # slot_owner[c]'s staging row push_index[c] (emulated: gather every rank's (owner, index, value) triples); the
+    # owner then reads its staging through spos[p, j] and must find, for each requester p, that requester's value
+    # for row j -- and the staging rows written by different requesters never collide.
+    vals = (rank + 1) * 1000.0 + torch.arange(route.n_cache, dtype=torch.float32)
+    trip = torch.stack([route.slot_owner.float(), route.push_index.float(), vals], dim=1) if route.n_cache \
+        else torch.zeros((0, 3))
+    trips = gather_padded(torch.cat([trip, torch.full((1, 3), -1.0)]), n_items + 1)       # -1 row = terminator
+    staging = torch.full((max(route.n_stage, 1),), float("nan"))
+    writes = 0
+    for p in range(world):
+        tp = trips[p]
+        tp = tp[: int((tp[:, 0] < 0).nonzero()[0])]
+        mine = tp[tp[:, 0] == rank]
+        idx = mine[:, 1].long()
+        assert bool(torch.isnan(staging[idx]).all())                  # no two writers share a staging row
+        staging[idx] = mine[:, 2]
+        writes += int(idx.numel())
+    ok_push = writes == route.n_stage and not bool(torch.isnan(staging[:route.n_stage]).any())
+    spos = build_spos_table(route, world, shard.shape[0])
+    # requester p's slot of my row j = pos[p, j]  =>  the staged value must be (p + 1) * 1000 + pos[p, j]
+    for p in range(world):
+        has = spos[p] >= 0
+        ok_push = ok_push and bool(torch.equal(has, pos[p] >= 0))
+        got = staging[spos[p][has].long()]
+        ok_push = ok_push and bool(torch.equal(got, (p + 1) * 1000.0 + pos[p][has].float()))
     print(json.dumps({"rank": rank, "fetch": ok_fetch, "back": ok_back, "fetch_p2p": ok_fetch_p2p,
-                      "pull_p2p": ok_pull_p2p, "n_cache": route.n_cache,
+                      "pull_p2p": ok_pull_p2p, "push": ok_push, "n_cache": route.n_cache,
                       "recv": route.recv_splits, "send": route.send_splits}), flush=True)
     dist.destroy_process_group()
 

@@ -80,9 +80,21 @@ def main():
     out["alpha0"] = np.float64(alpha0)
     sl = slice(0, B)
     md, tmd = build(double=True)
-    tmd.train_a_batch(tmd.users_tensor[sl], tmd.items_tensor[sl], tmd.scores_tensor[sl].double(), tmd.envs[sl],
-                      tmd.sample_weights[sl].double(), alpha0)
+    ld64 = tmd.train_a_batch(tmd.users_tensor[sl], tmd.items_tensor[sl], tmd.scores_tensor[sl].double(), tmd.envs[sl],
+                             tmd.sample_weights[sl].double(), alpha0)
     g64 = {k: p.grad.numpy().copy() for k, p in md.named_parameters()}
+    # the fp64 twin's losses: the reference's own fp32 L2 / L1 values carry ~2e-4 of summation noise at this size
+    # (norm() over 5.2 M gathered elements accumulated in fp32 on the CPU), so losses are judged by the same rule as
+    # the gradients: err(ours, fp64) <= max(tol, 2 err(reference fp32, fp64))
+    out["loss0_f64"] = np.asarray([ld64[k] for k in on.LOSS_KEYS], dtype=np.float64)
+    md2, tmd2 = build(double=True)
+    tmd2.scores_tensor = tmd2.scores_tensor.double()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mean64 = tmd2.train_a_epoch()
+    out["epoch_mean_loss_f64"] = np.asarray([mean64[k] for k in on.LOSS_KEYS], dtype=np.float64)
+    for k, v in md2.state_dict().items():
+        out["epoch1_f64/" + k] = sample(k, v.detach().numpy())
 
     losses = []
     orig = tm.train_a_batch

@@ -36,7 +36,8 @@ def test_struct_layouts():
     assert C.sizeof(_lib.Params) == 56
     assert C.sizeof(_lib.Adam) == 136
     assert C.sizeof(_lib.Batch) == 48
-    assert C.sizeof(_lib.Hyper) == 120
+    assert C.sizeof(_lib.Hyper) == 128
+    assert C.sizeof(_lib.Push) == 32
     assert C.sizeof(_lib.Dyn) == 16
 
 

@@ -38,6 +38,7 @@ def test_routing_over_gloo(world):
     for o in outs:
         assert o["fetch"] and o["back"], o
         assert o["fetch_p2p"] and o["pull_p2p"], o      # routing tables of the peer-memory exchange
+        assert o["push"], o                             # ... and of its push variant (staging rows, spos)
         assert sum(o["recv"]) == o["n_cache"]
     # what rank a receives from b is what b sends to a
     by = {o["rank"]: o for o in outs}

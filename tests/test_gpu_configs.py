@@ -232,9 +232,12 @@ def test_yahoo_explicit_real_file_epoch_and_cluster_match_the_live_reference():
                            tm.sample_weights[:B], c_inv=tc["invariant_coe"], c_ea=tc["env_aware_coe"],
                            c_env=tc["env_coe"], c_L2=tc["L2_coe"], c_L1=tc["L1_coe"], alpha=float(z["alpha0"]),
                            use_class_rw=False, use_rec_rw=False, grads_out=grads).cpu().numpy()
-    ref_losses = z["epoch_losses"]
+    # losses by the same rule as the gradients: at this size the reference's own fp32 L2 / L1 values are ~2e-4 off its
+    # fp64 twin (norm() over 5.2 M gathered elements accumulated in fp32 on the CPU)
+    ref_losses, l64 = z["epoch_losses"], z["loss0_f64"]
     for j, k in enumerate(on.LOSS_KEYS):
-        assert abs(loss0[j] - ref_losses[0][j]) <= 1e-5 * abs(ref_losses[0][j]), k
+        err_ours, err_ref = abs(loss0[j] - l64[j]) / abs(l64[j]), abs(ref_losses[0][j] - l64[j]) / abs(l64[j])
+        assert err_ours <= max(1e-5, 2 * err_ref), (k, loss0[j], ref_losses[0][j], l64[j])
     ref_err = dict(zip(z["grad0_ref_err_keys"].tolist(), z["grad0_ref_err"].tolist()))
     for k, sk in on.STATE_KEYS.items():
         g = grads[k].cpu().numpy().astype(np.float64)
@@ -246,14 +249,19 @@ def test_yahoo_explicit_real_file_epoch_and_cluster_match_the_live_reference():
 
     # the full epoch through the trainer (3 steps, alpha schedule, cached plans, CUDA-graph replay allowed)
     mean_ld = tm.train_a_epoch()
+    m64 = z["epoch_mean_loss_f64"]
     for j, k in enumerate(on.LOSS_KEYS):
-        assert abs(mean_ld[k] - z["epoch_mean_loss"][j]) <= 1e-4 * abs(z["epoch_mean_loss"][j]), k
+        err_ours = abs(mean_ld[k] - m64[j]) / abs(m64[j])
+        err_ref = abs(z["epoch_mean_loss"][j] - m64[j]) / abs(m64[j])
+        assert err_ours <= max(1e-4, 2 * err_ref), (k, mean_ld[k], z["epoch_mean_loss"][j], m64[j])
     sd = {k: v.cpu().numpy() for k, v in model.state_dict().items()}
     for k in sd:
         ours = sd[k][::stride] if k.startswith("embed_user") else sd[k]
-        want = z["epoch1/" + k]
-        den = np.abs(want).max()
-        assert float(np.abs(ours.astype(np.float64) - want).max() / den) <= 5e-4, k
+        want, w64 = z["epoch1/" + k], z["epoch1_f64/" + k]
+        den = np.abs(w64).max()
+        err_ours = float(np.abs(ours.astype(np.float64) - w64).max() / den)
+        err_ref = float(np.abs(want.astype(np.float64) - w64).max() / den)
+        assert err_ours <= max(5e-4, 2 * err_ref), (k, err_ours, err_ref)
 
     # cluster(): same host-drawn tie-break stream; assignments equal except fp32 near-ties (bounded by the count
     # the reference's own distances have)

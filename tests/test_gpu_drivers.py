@@ -121,3 +121,84 @@ def test_implicit_evaluator_device_path_equals_host_path_with_item_pool():
         b = ev.evaluate_batch(users_t, users_l, force_host=True)
         for m in ("ndcg", "recall", "precision"):
             assert np.allclose(a[m], b[m], rtol=0, atol=1e-9), (use_pool, m, a[m], b[m])
+
+
+@pytest.mark.parametrize("n_items,dim", [(211, 24), (3706, 40), (60000, 40), (997, 30)])
+@pytest.mark.parametrize("use_pool", [False, True])
+def test_fused_evaluator_kernel_matches_the_step_by_step_path(n_items, dim, use_pool):
+    """invpref_eval_topk (scores + mask + pool + exact top-k + hits in one kernel, no rating matrix) against
+    model.predict -> mask kernels -> torch.topk -> hit kernel, which test_ref_loaders_evaluators.py pins to the live
+    reference.  Item sets that fit the shared-memory score cache (211, 997, 3706) and one that does not (60000:
+    bitmap + recompute path); D = 30 takes the scalar dot product.  The selected ITEMS must be the same wherever the
+    k-th and (k+1)-th ratings are distinguishable (the fused kernel sums the dot product in a different order than
+    the GEMM: ratings within 1e-6 may swap ranks), and the metric dictionaries must agree."""
+    from invpref_kdd_2022_b200.dataloader import YahooImplicitBCELossDataLoader, synthetic_interactions
+    from invpref_kdd_2022_b200.dataloader import synthetic_item_pool
+    from invpref_kdd_2022_b200.evaluate import ImplicitTestManager
+    from invpref_kdd_2022_b200.models import InvPrefImplicit
+    dev = torch.device("cuda:0")
+    U = 300
+    tr = synthetic_interactions(U, n_items, 9000, True, seed=5)
+    te = synthetic_interactions(U, n_items, 1500, True, seed=6)
+    te = te[te[:, 2] > 0]
+    loader = YahooImplicitBCELossDataLoader("", dev, train=tr, test=te)
+    if use_pool:
+        loader.set_item_pool(synthetic_item_pool(te, U, n_items, extra=min(50, n_items // 3)))
+    torch.manual_seed(1)
+    model = InvPrefImplicit(loader.user_num, loader.item_num, 2, dim).to(dev)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(30.0)
+    ks = [40, 3, 5]
+    users_t, users_l = loader.all_test_users_by_sorted_tensor, loader.all_test_users_by_sorted_list
+    ev_f = ImplicitTestManager(model, loader, test_batch_size=64, top_k_list=ks, use_item_pool=use_pool, fused=True)
+    ev_s = ImplicitTestManager(model, loader, test_batch_size=64, top_k_list=ks, use_item_pool=use_pool, fused=False)
+    hits, n_gt, top = ev_f._hits_fused(users_t, 40)
+    # the step-by-step ratings, adjusted the same way
+    rating = model.predict(users_t).clone().contiguous()
+    h2, n2 = ev_s._hits_device(rating, users_t.to(dev), 40)          # masks `rating` in place, then top-k + hits
+    vals, top_ref = torch.topk(rating, k=40)
+    got_vals = torch.gather(rating, 1, top)
+    assert torch.equal(n_gt, n2)
+    assert float((got_vals - vals).abs().max()) <= 2e-6               # same rating at every rank ...
+    same = (top == top_ref)
+    gap_ok = (vals[:, :-1] - vals[:, 1:]).abs() > 4e-6                # ... and the same item wherever ranks are distinct
+    clear = torch.ones_like(same)
+    clear[:, :-1] &= gap_ok
+    clear[:, 1:] &= gap_ok
+    kth = torch.topk(rating, k=41).values[:, 40:41] if n_items > 40 else None
+    if kth is not None:
+        clear[:, -1:] &= (vals[:, -1:] - kth).abs() > 4e-6
+    assert bool(same[clear].all())
+    assert float(clear.double().mean()) > 0.5
+    # descending order with ties broken by the lower item id
+    assert bool((got_vals[:, :-1] >= got_vals[:, 1:]).all())
+    a, b = ev_f.evaluate(), ev_s.evaluate()
+    for m in ("ndcg", "recall", "precision"):
+        for k in ks:
+            assert abs(a[m][k] - b[m][k]) <= 2e-3, (m, k, a[m][k], b[m][k])
+
+
+def test_fused_evaluator_ties_go_to_the_lowest_item_id():
+    """All-equal ratings (zero tables): torch.topk leaves the order of ties unspecified, the fused kernel takes the
+    lowest ids in ascending order; masked items drop out, pool items come first."""
+    from invpref_kdd_2022_b200.dataloader import YahooImplicitBCELossDataLoader
+    from invpref_kdd_2022_b200.evaluate import ImplicitTestManager
+    from invpref_kdd_2022_b200.models import InvPrefImplicit
+    dev = torch.device("cuda:0")
+    tr = np.array([[0, 0, 1], [0, 2, 1], [1, 1, 1], [2, 699, 0]], dtype=np.int64)
+    te = np.array([[0, 5, 1], [1, 0, 1], [2, 3, 1]], dtype=np.int64)
+    loader = YahooImplicitBCELossDataLoader("", dev, train=tr, test=te)
+    loader.set_item_pool(np.array([[0, 650], [0, 9], [1, 1]], dtype=np.int64))
+    model = InvPrefImplicit(loader.user_num, loader.item_num, 2, 16).to(dev)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.zero_()
+    ev = ImplicitTestManager(model, loader, test_batch_size=8, top_k_list=[6], use_item_pool=True)
+    hits, n_gt, top = ev._hits_fused(loader.all_test_users_by_sorted_tensor, 6)
+    top = top.cpu().tolist()
+    assert top[0] == [9, 650, 1, 3, 4, 5]          # pool first (ascending), then the unmasked ids 1, 3, 4, 5 (0, 2 masked)
+    assert top[1] == [0, 2, 3, 4, 5, 6]            # item 1 is masked AND in the pool: -1024 + 1024 = 0 < 0.5
+    assert top[2] == [0, 1, 2, 3, 4, 5]
+    assert hits.cpu().tolist() == [[0, 0, 0, 0, 0, 1], [1, 0, 0, 0, 0, 0], [0, 0, 0, 1, 0, 0]]
+    assert n_gt.cpu().tolist() == [1, 1, 1]

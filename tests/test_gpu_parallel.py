@@ -128,39 +128,112 @@ def test_replicated_matches_single_gpu(world):
             assert nerr(rk.params[k].cpu().numpy(), ref.params[k].cpu().numpy()) <= 2e-4, k
 
 
-def test_sharded_peer_memory_is_bitwise_the_collective_path():
-    """The peer-memory exchange (invpref_fetch_rows_p2p + invpref_owner_adam_p2p) sums the partial item
-    gradients in the same rank order with the same arithmetic as all-to-all + scatter-add + adam_dense."""
+def _wire(ranks, mode):
+    """Peer pointers of simulated ranks = the other ranks' tensors on the same device."""
+    if mode in ("p2p", "push"):
+        for rk in ranks:
+            rk.enable_p2p([x.Iinv.data_ptr() for x in ranks], [x.Ienv.data_ptr() for x in ranks],
+                          [x.gcache[0].data_ptr() for x in ranks], [x.gcache[1].data_ptr() for x in ranks])
+    if mode == "push":
+        for rk in ranks:
+            rk.enable_push([[[x.stage[par][t].data_ptr() for x in ranks] for t in range(2)] for par in range(2)],
+                           [[x.cache[t].data_ptr() for x in ranks] for t in range(2)])
+
+
+@pytest.mark.parametrize("lazy", [True, False])
+def test_sharded_peer_memory_paths_are_bitwise_the_collective_path(lazy):
+    """Three exchanges of the item rows / partial item gradients, same arithmetic in the same (rank) order:
+      collective  gather_rows -> all-to-all -> cache; gradients all-to-all back -> scatter_add per rank -> adam_dense
+      p2p         invpref_fetch_rows_p2p + invpref_owner_adam_p2p (NVLink pulls)
+      push        the item pass stores its partials into the owners' staging buffers (invpref_push), the owner
+                  reduces from local memory and stores the updated rows into the requesters' next-batch caches
+                  (invpref_owner_adam_push): no pull kernel at all
+    must give bit-identical losses, tables and moments over several steps (double-buffered staging: 5 steps)."""
     from invpref_kdd_2022_b200.parallel import ShardedTrainer, SimDriver
     dev = torch.device("cuda:0")
-    world, U, I, K, D, B = 3, 700, 151, 4, 64, 12000
-    u, i, y, e, w, p = synth(U, I, 3 * B, K, D, False, 11)
+    world, U, I, K, D, B, S = 3, 700, 151, 4, 64, 12000, 5
+    u, i, y, e, w, p = synth(U, I, S * B, K, D, False, 11)
     init = {k: torch.tensor(v, device=dev) for k, v in p.items()}
     t = lambda a: torch.tensor(a, device=dev)
     out = []
-    for p2p in (False, True):
-        ranks = [ShardedTrainer(U, I, K, D, False, True, False, 1e-2, r, world, dev, cache_rows=I, init=init)
-                 for r in range(world)]
-        if p2p:
-            for rk in ranks:
-                rk.enable_p2p([x.Iinv.data_ptr() for x in ranks], [x.Ienv.data_ptr() for x in ranks],
-                              [x.gcache[0].data_ptr() for x in ranks], [x.gcache[1].data_ptr() for x in ranks])
+    for mode in ("collective", "p2p", "push"):
+        ranks = [ShardedTrainer(U, I, K, D, False, True, False, 1e-2, r, world, dev, cache_rows=I, init=init,
+                                lazy=lazy, stage_rows=(2 * I if mode == "push" else 0)) for r in range(world)]
+        _wire(ranks, mode)
         sim = SimDriver(world)
         losses = []
         sbs_all = []
-        for s in range(3):
+        for s in range(S):
             sl = slice(s * B, (s + 1) * B)
             sbs_all.append(sim.run_all([rk.prepare_gen(t(u[sl]), t(i[sl]), t(y[sl])) for rk in ranks]))
-        for s in range(3):
+        for s in range(S):
             sl = slice(s * B, (s + 1) * B)
             sbs = sbs_all[s]
-            nxt = sbs_all[s + 1] if s + 1 < 3 else [None] * world
+            nxt = sbs_all[s + 1] if s + 1 < S else [None] * world
             res = sim.run_all([rk.step_gen(sb, t(e[sl])[sb.sel].contiguous(), t(w[sl])[sb.sel].contiguous(),
                                            next_sb=nx, **KW) for rk, sb, nx in zip(ranks, sbs, nxt)])
             losses.append(res[0].clone())
-        out.append((losses, [{k: v.clone() for k, v in rk.local_tables().items()} for rk in ranks]))
-    for a, b in zip(out[0][0], out[1][0]):
-        assert torch.equal(a, b)
-    for ta, tb in zip(out[0][1], out[1][1]):
-        for k in ta:
-            assert torch.equal(ta[k], tb[k]), k
+        # a re-assignment after training reads the item rows through a fresh (pull) fetch
+        eps = torch.tensor(on.init_eps(K), device=dev)
+        sl = slice(0, B)
+        cl = sim.run_all([rk.cluster_gen(sb, None, None, t(e[sl])[sb.sel].contiguous())
+                          for rk, sb in zip(ranks, sbs_all[0])])
+        out.append((losses, [{k: v.clone() for k, v in rk.local_tables().items()} for rk in ranks],
+                    [c[0].clone() for c in cl]))
+    for other in out[1:]:
+        for a, b in zip(out[0][0], other[0]):
+            assert torch.equal(a, b)
+        for ta, tb in zip(out[0][1], other[1]):
+            for k in ta:
+                assert torch.equal(ta[k], tb[k]), k
+        for a, b in zip(out[0][2], other[2]):
+            assert torch.equal(a, b)
+
+
+def _managers(g, world, rank, driver, epochs=2, **kw):
+    """A single-GPU ExplicitTrainManager/ImplicitTrainManager and the sharded manager, same seeds, same init."""
+    from invpref_kdd_2022_b200.dist_train import ShardedExplicitTrainManager, ShardedImplicitTrainManager
+    from invpref_kdd_2022_b200.models import InvPrefExplicit, InvPrefImplicit
+    dev = torch.device("cuda:0")
+    torch.manual_seed(g.seed)
+    M = InvPrefImplicit if g.implicit else InvPrefExplicit
+    model = M(g.U, g.I, g.K, g.D, g.roe, g.ree).to(dev)
+    init = {k: p.data.clone() for k, p in model.named_hot_params().items()}
+    np.random.seed(g.seed)
+    T = ShardedImplicitTrainManager if g.implicit else ShardedExplicitTrainManager
+    return T(g.U, g.I, g.K, g.D, torch.LongTensor(g.data), dev, batch_size=g.B, epochs=epochs, cluster_interval=1,
+             evaluate_interval=1, lr=g.lr, invariant_coe=g.coef["c_inv"], env_aware_coe=g.coef["c_ea"],
+             env_coe=g.coef["c_env"], L2_coe=g.coef["c_L2"], L1_coe=g.coef["c_L1"], alpha=g.alpha,
+             use_class_re_weight=g.crw, use_recommend_re_weight=g.rrw, reg_only_embed=g.roe, reg_env_embed=g.ree,
+             init=init, driver=driver, rank=rank, world=world, **kw)
+
+
+@pytest.mark.parametrize("case", ["coat_explicit", "implicit_k6"])
+def test_sharded_train_manager_world1_follows_the_golden_epoch(case):
+    """The distributed trainer behind the reference API (dist_train.py), degenerate world = 1: one epoch, cluster(),
+    stat_envs() against what the LIVE reference produced (tests/golden): same initial envs (numpy stream), same
+    epoch losses, same env counts bookkeeping."""
+    from _golden import Golden
+    g = Golden(case)
+    tm = _managers(g, 1, 0, None)
+    assert np.array_equal(tm.envs.cpu().numpy(), g["envs0"])
+    cnt = tm.stat_envs()
+    assert sum(cnt.values()) == g.N
+    assert np.array_equal(tm.sample_weights.cpu().numpy(), g["sample_weights0"])
+    assert np.array_equal(tm.class_weights.cpu().numpy(), g["class_weights0"])
+    mean_ld = tm.train_a_epoch()
+    for j, k in enumerate(on.LOSS_KEYS):
+        assert abs(mean_ld[k] - g["epoch_mean_loss"][j]) <= 1e-4 * abs(g["epoch_mean_loss"][j]), k
+    loc = tm.trainer.local_tables()
+    ep = g.group("epoch1")
+    for k, sk in on.STATE_KEYS.items():
+        assert nerr(loc[k].cpu().numpy(), ep[sk]) <= 5e-4, k
+    np.random.seed(g.seed + 1)
+    diff = tm.cluster()
+    new = tm.envs.cpu().numpy()
+    assert diff == int((new != g["envs0"]).sum())
+    cnt = tm.stat_envs()
+    assert [cnt[k] for k in range(g.K)] == np.bincount(new, minlength=g.K).tolist()
+    assert np.array_equal(tm.sample_weights.cpu().numpy(), on.stat_envs(new, g.K, g.N)[2])
+    (losses, ep_idx), _, (diffs, cnts, cl_ep) = tm.train(silent=True, auto=True)
+    assert ep_idx == [2] and cl_ep == [2] and sum(cnts[0].values()) == g.N
