@@ -439,17 +439,19 @@ def run_ours_single(args, w):
     for _ in range(2):
         hp.cluster(cu, ci, cy, pidx, eps, ce)
     torch.cuda.synchronize()
-    reps = 5
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(reps):
-        new_e, hist, diff = hp.cluster(cu, ci, cy, pidx, eps, ce)
+    reps = 7
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    evs[0].record()
+    for r_ in range(reps):
+        new_e, hist, diff = hp.cluster(cu, ci, cy, pidx, eps, ce, trusted=True)
         hp.stat_envs(new_e, hist)
-    ev1.record()
+        evs[r_ + 1].record()
     torch.cuda.synchronize()
-    cms = ev0.elapsed_time(ev1) / reps
+    per_rep = [evs[r_].elapsed_time(evs[r_ + 1]) for r_ in range(reps)]
+    cms = statistics.median(per_rep)          # per-call CUDA-event times; the median is robust against a stray stall
     cb = cluster_bytes_per_sample(D) * Nc
     cluster = {"value": Nc / (cms * 1e-3), "unit": "samples/s", "samples": Nc, "ms": cms,
+               "ms_min_max": [min(per_rep), max(per_rep)], "reps": reps,
                "roofline": {"bound": "hbm", "kernel": "cluster_kernel (+ stat_envs)", "achieved": cb / (cms * 1e-3) / 1e9,
                             "peak": peak, "unit": "GB/s", "frac": cb / (cms * 1e-3) / 1e9 / peak,
                             "bytes_per_launch": cb, "traffic": None}}

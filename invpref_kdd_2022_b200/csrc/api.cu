@@ -506,7 +506,7 @@ int invpref_adam_dense(float* theta, float* m, float* v, const float* grad, int6
                        void* stream) {
     if (!theta || !m || !v || !grad || !hyper || n < 0 || hyper->step < 1) return INVPREF_ERR_BAD_ARG;
     if (n == 0) return INVPREF_OK;
-    return launch_adam_dense(theta, m, v, grad, n, make_adam(hyper), (cudaStream_t)stream);
+    return launch_adam_dense(theta, m, v, grad, n, make_adam(hyper), hyper->dyn, (cudaStream_t)stream);
 }
 
 int invpref_gather_rows(const float* table, const int64_t* rows, int64_t n, int32_t dim, float* out, void* stream) {
@@ -571,7 +571,7 @@ int invpref_owner_adam_p2p(float* theta_inv, float* theta_env, float* m_inv, flo
         if (!grads[i]) return INVPREF_ERR_BAD_ARG;
     if (n_rows == 0) return INVPREF_OK;
     return launch_owner_adam_p2p(theta_inv, theta_env, m_inv, m_env, v_inv, v_env, n_rows, dim, world, grads, pos,
-                                 make_adam(hyper), (cudaStream_t)stream);
+                                 make_adam(hyper), hyper->dyn, (cudaStream_t)stream);
 }
 
 int invpref_owner_adam_push(float* theta_inv, float* theta_env, float* m_inv, float* m_env, float* v_inv, float* v_env,
@@ -587,7 +587,7 @@ int invpref_owner_adam_push(float* theta_inv, float* theta_env, float* m_inv, fl
         if (!caches[i]) return INVPREF_ERR_BAD_ARG;
     if (n_rows == 0) return INVPREF_OK;
     return launch_owner_adam_push(theta_inv, theta_env, m_inv, m_env, v_inv, v_env, n_rows, dim, world, stage_inv,
-                                  stage_env, spos, caches, npos, make_adam(hyper), (cudaStream_t)stream);
+                                  stage_env, spos, caches, npos, make_adam(hyper), hyper->dyn, (cudaStream_t)stream);
 }
 
 int invpref_backward(const invpref_desc* desc, const invpref_params* params, const invpref_batch* batch, double alpha,

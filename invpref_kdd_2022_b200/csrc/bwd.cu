@@ -260,12 +260,12 @@ __device__ __forceinline__ void ring_consume(const float* __restrict__ gslot, co
 // a few hundred sequential interactions each: the critical path of the item pass).
 template <int VEC, int NV, bool STASH, int KX>
 __global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_ring_kernel(BwdSideArgs a) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int D = KX ? GROUP * VEC * NV : a.D, K = KX ? KX : a.K, GS = KX ? (KX <= 5 ? 8 : 12) : a.GS, KD = K * D;
     float* sE = smem;
     float* sW = smem + KD;
     float* sG = smem + ((2 * KD + 3) & ~3);
-    float* ring = sG + GROUPS_PER_BLOCK * (RING + 1) * 12;
+    float* ring = smem + ring_align_up(((2 * KD + 3) & ~3) + GROUPS_PER_BLOCK * (RING + 1) * 12);
     stage_EW(a, sE, sW);
     const int lane = threadIdx.x & (GROUP - 1);
     const unsigned gmask = group_mask();
@@ -345,12 +345,12 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_ring_kernel(BwdSideArgs a
 // shifts); KX = 0: any D, K.
 template <int VEC, int NV, int EPI, bool STASH, int KX>
 __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, int long_len) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int D = KX ? GROUP * VEC * NV : a.D, K = KX ? KX : a.K, GS = KX ? (KX <= 5 ? 8 : 12) : a.GS, KD = K * D;
     float* sE = smem;
     float* sW = smem + KD;
     float* sG = smem + ((2 * KD + 3) & ~3);                    // [groups][RING + 1][12] g-packs
-    float* ring = sG + GROUPS_PER_BLOCK * (RING + 1) * 12;     // [RING][2 rows][NV][BLOCK][VEC]
+    float* ring = smem + ring_align_up(((2 * KD + 3) & ~3) + GROUPS_PER_BLOCK * (RING + 1) * 12);   // [RING][2 rows][NV][BLOCK][VEC]
     stage_EW(a, sE, sW);
     const int lane = threadIdx.x & (GROUP - 1);
     const unsigned gmask = group_mask();
@@ -774,7 +774,7 @@ static bool ring_enabled() {
 }
 
 static size_t ring_smem(const Geometry& g) {
-    return ((size_t)((2 * g.K * g.D + 3) & ~3) + (size_t)GROUPS_PER_BLOCK * (RING + 1) * 12 +
+    return ((size_t)ring_align_up(((2 * g.K * g.D + 3) & ~3) + GROUPS_PER_BLOCK * (RING + 1) * 12) +
             (size_t)RING * 2 * g.NV * g.VEC * BLOCK) * sizeof(float);
 }
 

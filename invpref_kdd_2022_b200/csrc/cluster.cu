@@ -29,13 +29,13 @@ template <int VEC, int NV> struct ClStages { static constexpr int value = (VEC *
 template <int VEC, int NV, int KT, bool EXACT>
 __global__ void __launch_bounds__(BLOCK, (VEC * NV <= 4 && KT <= 4) ? 4 : 1) cluster_kernel(ClusterArgs a,
                                                                                             int eps_rows_smem) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     constexpr int RV = VEC * NV, ST = ClStages<VEC, NV>::value;
     constexpr bool E_REG = KT * RV <= 32;      // this lane's slice of E lives in registers for the whole kernel
     const int D = EXACT ? GROUP * VEC * NV : a.D, K = EXACT ? KT : a.K, KD = K * D;
     float* sE = smem;                                        // [K*D]
     float* sEps = smem + ((KD + 3) & ~3);                    // [eps_rows_smem * K]
-    float* ring = sEps + ((eps_rows_smem * K + 3) & ~3);     // [ST][4 rows][NV][BLOCK][VEC]
+    float* ring = smem + ring_align_up(((KD + 3) & ~3) + ((eps_rows_smem * K + 3) & ~3));   // [ST][4 rows][NV][BLOCK][VEC]
     __shared__ unsigned long long sHist[INVPREF_MAX_ENVS + 1];   // [K] histogram, [8] diff
     const int tid = threadIdx.x, lane = tid & (GROUP - 1);
     const unsigned gmask = group_mask();
@@ -231,7 +231,7 @@ int launch_cluster(const Geometry& g, const ClusterArgs& a, cudaStream_t stream)
         for (int j = 2; j <= g.K; ++j) eps_rows *= j;
     }
     const int stages = (g.VEC * g.NV <= 8) ? 3 : 2;
-    const size_t smem = ((size_t)((g.K * g.D + 3) & ~3) + (size_t)((eps_rows * g.K + 3) & ~3) +
+    const size_t smem = ((size_t)ring_align_up(((g.K * g.D + 3) & ~3) + ((eps_rows * g.K + 3) & ~3)) +
                          (size_t)stages * 4 * g.NV * g.VEC * BLOCK) * sizeof(float);
     int64_t need = (a.B + GROUPS_PER_BLOCK - 1) / GROUPS_PER_BLOCK;
     int grid = (int)(need < 1 ? 1 : (need < 148 * 16 ? need : 148 * 16));

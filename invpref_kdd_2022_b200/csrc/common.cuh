@@ -369,6 +369,13 @@ template <int PENDING> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory");
 }
 
+// The staging rings start on a 128-byte boundary of shared memory (RING_ALIGN floats).  A warp-wide 16-byte cp.async
+// writes 512 contiguous bytes; when that span straddles 128-byte lines unevenly the LSU splits the instruction and
+// re-requests sectors from L2: ncu on the round-2 user pass whose ring had slipped from offset 32 to 48 (mod 128)
+// showed TWICE the L2 -> L1 sectors for LDGSTS (7.5 -> 14.7 GB per launch) and an 11 % longer kernel.
+constexpr int RING_ALIGN = 32;
+__host__ __device__ inline int ring_align_up(int floats) { return (floats + RING_ALIGN - 1) & ~(RING_ALIGN - 1); }
+
 // Per-thread slot of a staged row slice: [slot][j][thread][VEC] floats (consecutive threads -> consecutive
 // VEC*4 bytes: conflict-free for the 128-bit shared loads).
 template <int VEC, int NV>

@@ -23,7 +23,9 @@ namespace {
 
 __global__ void __launch_bounds__(256) adam_dense_kernel(float* __restrict__ theta, float* __restrict__ m,
                                                          float* __restrict__ v, const float* __restrict__ grad,
-                                                         int64_t n, AdamScalars s, int vec_ok) {
+                                                         int64_t n, AdamScalars s0, int vec_ok,
+                                                         const invpref_dyn* dyn) {
+    const AdamScalars s = with_dyn(s0, dyn);
     const int64_t n4 = vec_ok ? (n >> 2) : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -120,7 +122,9 @@ __global__ void __launch_bounds__(256) owner_adam_p2p_kernel(float* __restrict__
                                                              float* __restrict__ m0, float* __restrict__ m1,
                                                              float* __restrict__ v0, float* __restrict__ v1,
                                                              int64_t n_rows, int dim, int world, PeerPtrs grads,
-                                                             const int32_t* __restrict__ pos, AdamScalars s) {
+                                                             const int32_t* __restrict__ pos, AdamScalars s0,
+                                                             const invpref_dyn* dyn) {
+    const AdamScalars s = with_dyn(s0, dyn);
     const int per_row = dim / VEC;
     const int64_t per_table = n_rows * per_row, total = 2 * per_table;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
@@ -179,7 +183,9 @@ __global__ void __launch_bounds__(256) owner_adam_push_kernel(float* __restrict_
                                                               const float* __restrict__ stage0,
                                                               const float* __restrict__ stage1,
                                                               const int32_t* __restrict__ spos, PeerOut caches,
-                                                              const int32_t* __restrict__ npos, AdamScalars s) {
+                                                              const int32_t* __restrict__ npos, AdamScalars s0,
+                                                              const invpref_dyn* dyn) {
+    const AdamScalars s = with_dyn(s0, dyn);
     const int per_row = dim / VEC;
     const int64_t per_table = n_rows * per_row, total = 2 * per_table;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
@@ -243,9 +249,9 @@ inline int grid_1d(int64_t work, int max_blocks = 148 * 16) {
 }  // namespace
 
 int launch_adam_dense(float* theta, float* m, float* v, const float* grad, int64_t n, const AdamScalars& s,
-                      cudaStream_t stream) {
+                      const invpref_dyn* dyn, cudaStream_t stream) {
     const int vec_ok = (((uintptr_t)theta | (uintptr_t)m | (uintptr_t)v | (uintptr_t)grad) % 16) == 0;
-    adam_dense_kernel<<<grid_1d(vec_ok ? n / 4 + 4 : n), 256, 0, stream>>>(theta, m, v, grad, n, s, vec_ok);
+    adam_dense_kernel<<<grid_1d(vec_ok ? n / 4 + 4 : n), 256, 0, stream>>>(theta, m, v, grad, n, s, vec_ok, dyn);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
@@ -281,21 +287,22 @@ int launch_fetch_rows_p2p(const float* const* tables_host, int world, const int3
 
 int launch_owner_adam_p2p(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
                           int world, const float* const* grads_host, const int32_t* pos, const AdamScalars& s,
-                          cudaStream_t stream) {
+                          const invpref_dyn* dyn, cudaStream_t stream) {
     if (world < 1 || world > P2P_MAX_WORLD) return INVPREF_ERR_BAD_ARG;
     PeerPtrs pp = {};
     bool v4 = dim % 4 == 0;
     for (float* q : {th0, th1, m0, m1, v0, v1}) v4 = v4 && ((uintptr_t)q % 16 == 0);
     for (int i = 0; i < 2 * world; ++i) { pp.p[i] = grads_host[i]; v4 = v4 && ((uintptr_t)grads_host[i] % 16 == 0); }
-    if (v4) owner_adam_p2p_kernel<4><<<grid_1d(2 * n_rows * (dim / 4)), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, pp, pos, s);
-    else owner_adam_p2p_kernel<1><<<grid_1d(2 * n_rows * dim), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, pp, pos, s);
+    if (v4) owner_adam_p2p_kernel<4><<<grid_1d(2 * n_rows * (dim / 4)), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, pp, pos, s, dyn);
+    else owner_adam_p2p_kernel<1><<<grid_1d(2 * n_rows * dim), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, pp, pos, s, dyn);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 
 int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
                            int world, const float* stage0, const float* stage1, const int32_t* spos,
-                           float* const* caches_host, const int32_t* npos, const AdamScalars& s, cudaStream_t stream) {
+                           float* const* caches_host, const int32_t* npos, const AdamScalars& s,
+                           const invpref_dyn* dyn, cudaStream_t stream) {
     if (world < 1 || world > P2P_MAX_WORLD) return INVPREF_ERR_BAD_ARG;
     PeerOut pp = {};
     bool v4 = dim % 4 == 0 && ((uintptr_t)stage0 % 16 == 0) && ((uintptr_t)stage1 % 16 == 0);
@@ -304,8 +311,8 @@ int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* 
         pp.p[i] = caches_host[i];
         v4 = v4 && ((uintptr_t)caches_host[i] % 16 == 0);
     }
-    if (v4) owner_adam_push_kernel<4><<<grid_1d(2 * n_rows * (dim / 4)), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s);
-    else owner_adam_push_kernel<1><<<grid_1d(2 * n_rows * dim), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s);
+    if (v4) owner_adam_push_kernel<4><<<grid_1d(2 * n_rows * (dim / 4)), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s, dyn);
+    else owner_adam_push_kernel<1><<<grid_1d(2 * n_rows * dim), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s, dyn);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

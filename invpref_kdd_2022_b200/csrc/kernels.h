@@ -136,7 +136,7 @@ int launch_stat_envs(const int64_t* envs, int64_t N, int K, const int64_t* hist,
 
 // ---- dist.cu ---------------------------------------------------------------------------------
 int launch_adam_dense(float* theta, float* m, float* v, const float* grad, int64_t n, const AdamScalars& s,
-                      cudaStream_t stream);
+                      const invpref_dyn* dyn, cudaStream_t stream);
 int launch_gather_rows(const float* table, const int64_t* rows, int64_t n, int dim, float* out, cudaStream_t stream);
 int launch_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, int dim, float* table,
                             cudaStream_t stream);
@@ -146,10 +146,11 @@ int launch_fetch_rows_p2p(const float* const* tables_host, int world, const int3
                           int64_t n, int dim, float* out0, float* out1, cudaStream_t stream);
 int launch_owner_adam_p2p(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
                           int world, const float* const* grads_host, const int32_t* pos, const AdamScalars& s,
-                          cudaStream_t stream);
+                          const invpref_dyn* dyn, cudaStream_t stream);
 int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
                            int world, const float* stage0, const float* stage1, const int32_t* spos,
-                           float* const* caches_host, const int32_t* npos, const AdamScalars& s, cudaStream_t stream);
+                           float* const* caches_host, const int32_t* npos, const AdamScalars& s,
+                           const invpref_dyn* dyn, cudaStream_t stream);
 
 // ---- eval.cu ---------------------------------------------------------------------------------
 int launch_mask_scores(float* rating, int64_t b, int64_t n_items, const int64_t* users, const int64_t* off,

@@ -55,10 +55,10 @@ constexpr int UM_WORDS = 56;
 // EXACT: D = 16 * VEC * NV and K = KT are compile-time constants (bounds guards fold away, row offsets are shifts).
 template <int VEC, int NV, int KT, int EPI, bool LAZY, bool EXACT>
 __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArgs a, int long_len) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int D = EXACT ? GROUP * VEC * NV : a.side.D, K = EXACT ? KT : a.side.K, KD = K * D;
     const Smem s = carve_smem(smem, KD);
-    float* ring = smem + (((4 + 2 * GROUPS_PER_BLOCK) * KD + SB_WORDS + 3) & ~3);   // [2][8][NV][BLOCK][VEC]
+    float* ring = smem + ring_align_up((4 + 2 * GROUPS_PER_BLOCK) * KD + SB_WORDS);   // [2][8][NV][BLOCK][VEC]
     int32_t* meta = reinterpret_cast<int32_t*>(ring + (size_t)2 * UP_SLOTS * NV * VEC * BLOCK) +
                     (threadIdx.x >> 4) * UM_WORDS;                                          // this group's words
     Running st;
@@ -266,6 +266,9 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
 inline size_t upass_ring_bytes(const Geometry& g) {   // staged rows + per-group metadata
     return (size_t)2 * UP_SLOTS * g.NV * g.VEC * BLOCK * sizeof(float) + (size_t)GROUPS_PER_BLOCK * UM_WORDS * 4;
 }
+inline size_t upass_ring_offset(const Geometry& g) {   // bytes before the ring: the carve of upass_smem, 128-byte aligned
+    return (size_t)ring_align_up((4 + 2 * GROUPS_PER_BLOCK) * g.K * g.D + SB_WORDS) * sizeof(float);
+}
 inline bool upass_staged(const Geometry& g) {
     static const bool enabled = [] {
         const char* e = getenv("INVPREF_STAGED");   // INVPREF_STAGED=0: register-only rows kernel (A/B runs)
@@ -279,7 +282,7 @@ inline bool upass_staged(const Geometry& g) {
 bool upass_supported(const Geometry& g) { return upass_smem(g) <= 96 * 1024; }
 
 static bool use_staged(const Geometry& g) {
-    return upass_staged(g) && ((upass_smem(g) + 15) & ~(size_t)15) + upass_ring_bytes(g) <= 227 * 1024;
+    return upass_staged(g) && upass_ring_offset(g) + upass_ring_bytes(g) <= 227 * 1024;
 }
 
 int upass_rows_grid(const Geometry& g, int64_t max_seg) {
@@ -297,7 +300,7 @@ int launch_upass_rows(const Geometry& g, const UserPassArgs& a, int epi, int gri
     const bool lazy = a.side.last_step != nullptr;
     if (lazy && epi != EPI_ADAM) return INVPREF_ERR_BAD_ARG;
     if (use_staged(g)) {
-        const size_t smem = ((upass_smem(g) + 15) & ~(size_t)15) + upass_ring_bytes(g);
+        const size_t smem = upass_ring_offset(g) + upass_ring_bytes(g);
         const int long_len = 2 * chunk_for(a.side.plan.B);   // plan.cu: segments longer than this are chunked
 #define LAUNCH(KERNEL)                                                                                           \
     do {                                                                                                         \

@@ -33,7 +33,7 @@ class _InvPrefTrainManager:
             alpha: float = None, use_class_re_weight: bool = False, test_begin_epoch: int = 0,
             begin_cluster_epoch: int = None, stop_cluster_epoch: int = None, cluster_use_random_sort: bool = True,
             use_recommend_re_weight: bool = True, cache_plans: bool = True, lazy_adam: bool = True,
-            use_graph: bool = True
+            use_graph: bool = True, plan_cache_bytes: int = 16 << 30
     ):
         self.model = model
         self.evaluator = evaluator
@@ -78,6 +78,15 @@ class _InvPrefTrainManager:
         self.optimizer = self.engine           # exposes .m / .v / .step (exp_avg, exp_avg_sq, step)
         self.cache_plans = cache_plans
         self._plans = {}
+        # Plans are cached while they fit `plan_cache_bytes` (a plan is ~80 bytes per interaction: the 239 batches of a
+        # 10^9-interaction epoch would take 79 GB).  Batches beyond the budget get their plan rebuilt every epoch into
+        # one of two rotating buffers on a loader stream, one step ahead of the step that consumes it (a plan build is
+        # a 2 x 32-bit radix sort of the batch: ~1 ms for 4 M interactions, hidden under the 4.6 ms step).
+        self.plan_cache_bytes = int(plan_cache_bytes)
+        self._plan_bytes_used = 0
+        self._ring = None
+        self._consumed_slot = None
+        self._scratch_busy_on_main = False      # a plan was built on the main stream since the loader last synced
         self._loss_rows = None
         # CUDA-graph replay of the epoch (train.py:881-910 issues 3-31 steps per epoch on the dataset configs, every
         # one of them a fixed sequence of launches on fixed buffers): from the second epoch on, one graph launch per
@@ -100,10 +109,60 @@ class _InvPrefTrainManager:
             return None
         plan = self._plans.get(key)
         if plan is None:
+            nbytes = self.engine.plan_bytes(users.numel())
+            if self._plan_bytes_used + nbytes > self.plan_cache_bytes:
+                return self._streamed_plan(key)
             plan = self.engine.new_plan(users, items)
+            self._scratch_busy_on_main = True
             self.engine.plan_status(plan, users.numel())       # IndexError on an out-of-range id (once per batch)
             self._plans[key] = plan
+            self._plan_bytes_used += nbytes
         return plan
+
+    # ---- plans that do not fit the cache: built one step ahead on a loader stream, two rotating buffers ----
+    def _ring_state(self):
+        if self._ring is None:
+            nbytes = self.engine.plan_bytes(self.batch_size)
+            self._ring = {"buf": [torch.empty(nbytes, dtype=torch.uint8, device=self.device) for _ in range(2)],
+                          "ready": [torch.cuda.Event(), torch.cuda.Event()],
+                          "consumed": [torch.cuda.Event(), torch.cuda.Event()],
+                          "stream": torch.cuda.Stream(device=self.device), "holds": [None, None], "turn": 0}
+            self.engine.workspace(self.batch_size)             # allocated before two streams share it
+            self._scratch_busy_on_main = True
+            for ev in self._ring["consumed"]:
+                ev.record()
+        return self._ring
+
+    def _prefetch_plan(self, key):
+        """Starts building the plan of batch `key` (if it is a streamed one) on the loader stream."""
+        if not self.cache_plans or key >= self.batch_num or key in self._plans:
+            return
+        if self._plan_bytes_used + self.engine.plan_bytes(self.batch_size) <= self.plan_cache_bytes:
+            return                                             # will be cached when its step comes
+        r = self._ring_state()
+        if key in r["holds"]:
+            return
+        slot = r["turn"]
+        r["turn"] ^= 1
+        lo = key * self.batch_size
+        u, i = self.users_tensor[lo:lo + self.batch_size], self.items_tensor[lo:lo + self.batch_size]
+        if self._scratch_busy_on_main:                         # the sort scratch was last used on the main stream
+            r["stream"].wait_stream(torch.cuda.current_stream())
+            self._scratch_busy_on_main = False
+        with torch.cuda.stream(r["stream"]):
+            r["stream"].wait_event(r["consumed"][slot])        # the step that last read this buffer is done
+            self.engine.new_plan(u, i, out=r["buf"][slot])
+            r["ready"][slot].record(r["stream"])
+        r["holds"][slot] = key
+
+    def _streamed_plan(self, key):
+        r = self._ring_state()
+        if key not in r["holds"]:
+            self._prefetch_plan(key)
+        slot = r["holds"].index(key)
+        torch.cuda.current_stream().wait_event(r["ready"][slot])
+        self._consumed_slot = slot
+        return r["buf"][slot]
 
     def _step(self, users, items, scores, envs, weights, alpha, loss_out=None, plan_key=None):
         users, items, envs = users.contiguous(), items.contiguous(), envs.contiguous()
@@ -196,8 +255,13 @@ class _InvPrefTrainManager:
         for batch_index, (u, i, y, e, w) in enumerate(mini_batch(
                 self.batch_size, self.users_tensor, self.items_tensor, self.scores_tensor, self.envs,
                 self.sample_weights)):
+            self._consumed_slot = None
             self._step(u, i, y, e, w, self._alpha_at(batch_index), loss_out=self._loss_rows[batch_index],
                        plan_key=batch_index)
+            if self._consumed_slot is not None:                 # a streamed plan: its buffer is free after this step
+                self._ring["consumed"][self._consumed_slot].record()
+                self._ring["holds"][self._consumed_slot] = None
+            self._prefetch_plan(batch_index + 1)
         self.epoch_cnt += 1
         self.engine.flush()
         rows = self._loss_rows.cpu().tolist()

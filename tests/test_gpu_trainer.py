@@ -192,3 +192,29 @@ def test_model_forward_backward_with_torch_autograd(implicit):
     # cluster_predict == env-aware score
     with torch.no_grad():
         assert nerr(model.cluster_predict(u, i, e).cpu().numpy(), s_env.detach().cpu().numpy()) <= 1e-5
+
+
+def test_bounded_plan_cache_streams_the_remaining_plans():
+    """plan_cache_bytes: batches whose plan does not fit the cache get it rebuilt every epoch on a loader stream, one
+    step ahead (two rotating buffers).  Same epochs, bit for bit, as with every plan cached -- and as with none."""
+    g = Golden("explicit_d64_k4")          # 7000 interactions, B = 3000 -> 3 batches
+    out = {}
+    for name, kw in (("all", {}), ("one", {"plan_cache_bytes": None}), ("none", {"plan_cache_bytes": 0}),
+                     ("nocache", {"cache_plans": False})):
+        if name == "one":
+            model, tm = build(g, epochs=3)
+            kw = {"plan_cache_bytes": tm.engine.plan_bytes(g.B) + 1}      # room for exactly one plan
+        model, tm = build(g, epochs=3, use_graph=False, **kw)
+        tm.stat_envs()
+        lds = [tm.train_a_epoch() for _ in range(3)]
+        if name == "one":
+            assert len(tm._plans) == 1 and tm._ring is not None
+        if name == "none":
+            assert len(tm._plans) == 0 and tm._ring is not None
+        if name == "all":
+            assert len(tm._plans) == 3 and tm._ring is None
+        out[name] = (lds, {k: v.clone() for k, v in model.state_dict().items()})
+    for name in ("one", "none", "nocache"):
+        assert out[name][0] == out["all"][0], name
+        for k in out["all"][1]:
+            assert torch.equal(out[name][1][k], out["all"][1][k]), (name, k)

@@ -27,7 +27,7 @@ def ref():
 def test_explicit_loader_matches_reference(ref, name):
     from invpref_kdd_2022_b200.dataloader import ExplicitDataLoader
     cpu = torch.device("cpu")
-    ours = ExplicitDataLoader(os.path.join(DATA, name), cpu)
+    ours = ExplicitDataLoader(os.path.join(DATA, name), cpu, cache=False)
     theirs = ref.dataloader.ExplicitDataLoader(os.path.join(DATA, name), cpu)
     assert (ours.user_num, ours.item_num) == (theirs.user_num, theirs.item_num)
     assert (ours.train_data_len, ours.test_data_len) == (theirs.train_data_len, theirs.test_data_len)
@@ -41,7 +41,7 @@ def test_explicit_loader_matches_reference(ref, name):
 def test_implicit_loader_matches_reference(ref, name, pool):
     from invpref_kdd_2022_b200.dataloader import YahooImplicitBCELossDataLoader
     cpu = torch.device("cpu")
-    ours = YahooImplicitBCELossDataLoader(os.path.join(DATA, name), cpu, has_item_pool_file=pool)
+    ours = YahooImplicitBCELossDataLoader(os.path.join(DATA, name), cpu, has_item_pool_file=pool, cache=False)
     theirs = ref.dataloader.YahooImplicitBCELossDataLoader(os.path.join(DATA, name), cpu, has_item_pool_file=pool)
     assert (ours.user_num, ours.item_num) == (theirs.user_num, theirs.item_num)
     assert np.array_equal(ours.train_data_np, theirs.train_data_np)
@@ -86,7 +86,7 @@ def test_implicit_evaluator_matches_reference(ref, use_pool):
     from invpref_kdd_2022_b200.evaluate import ImplicitTestManager
     cpu = torch.device("cpu")
     path = os.path.join(DATA, "Coat_all_data")
-    ours_dl = YahooImplicitBCELossDataLoader(path, cpu, has_item_pool_file=True)
+    ours_dl = YahooImplicitBCELossDataLoader(path, cpu, has_item_pool_file=True, cache=False)
     ref_dl = ref.dataloader.YahooImplicitBCELossDataLoader(path, cpu, has_item_pool_file=True)
     model = _StubImplicit(ours_dl.user_num, ours_dl.item_num)
     ks = [3, 5, 7]
@@ -106,7 +106,7 @@ def test_explicit_evaluator_matches_reference(ref):
     from invpref_kdd_2022_b200.evaluate import ExplicitTestManager
     cpu = torch.device("cpu")
     path = os.path.join(DATA, "Coat_explicit_all_data")
-    ours_dl = ExplicitDataLoader(path, cpu)
+    ours_dl = ExplicitDataLoader(path, cpu, cache=False)
     ref_dl = ref.dataloader.ExplicitDataLoader(path, cpu)
     model = _StubExplicit(ours_dl.user_num, ours_dl.item_num)
     got = ExplicitTestManager(model, ours_dl).evaluate()

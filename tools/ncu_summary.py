@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Summarise ncu output into profiles/: tools/ncu_summary.py <report.ncu-rep>[,<report2>...] <launches.csv> <out.md> [title]
 
-  <report.ncu-rep>  from `ncu --set full --clock-control none --import-source on ...` (read with ncu -i, no GPU)
+  <report.ncu-rep>  from `ncu --set full --clock-control none --import-source on ...` (read with ncu -i, no GPU);
+                    or the `ncu -i <rep> --page raw --csv` export of one (round 2: the .ncu-rep files are exported to
+                    CSV on the GPU box, they are too big to bring back); "-" = no launch list
   <launches.csv>    from `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...`
 """
 import csv
@@ -38,7 +40,10 @@ def main():
     lines = [f"# {title}", "", "## Kernels captured with `ncu --set full --clock-control none` (one launch each)", ""]
     captured = []
     for one in rep.split(","):
-        raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if one.endswith(".csv"):
+            raw = open(one).read()
+        else:
+            raw = subprocess.run(["ncu", "-i", one, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
         captured += [(rows[0], rows[1], r, one) for r in rows[2:]]
     for hdr, units, r, one in captured:
@@ -64,6 +69,10 @@ def main():
     # launch list: share of each kernel in the step
     agg = OrderedDict()
     total = 0.0
+    if launches == "-":
+        open(out, "w").write("\n".join(lines))
+        print("wrote", out)
+        return
     with open(launches) as f:
         rd = [r for r in csv.reader(l for l in f if not l.startswith("==")) if r]
     h = rd[0]
