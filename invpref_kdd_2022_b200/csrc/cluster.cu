@@ -104,6 +104,15 @@ __global__ void __launch_bounds__(BLOCK, (VEC * NV <= 4 && KT <= 4) ? 4 : 1) clu
         cp_async_commit();
         uq = uq2; iq = iq2;
         if (n + (ST + 1) * stride < a.B) { uq2 = users_lo[2 * (n + (ST + 1) * stride)]; iq2 = items_lo[2 * (n + (ST + 1) * stride)]; }
+#if INVPREF_CLUSTER_L2_PREFETCH
+        // the rows that will be requested NEXT iteration (ids already in uq / iq): into L2 now, one line per lane
+        if (n + ST * stride < a.B && lane < 8) {
+            const int t = lane >> 1, half = lane & 1;
+            const float* tab = (t == 0) ? a.Uinv : ((t == 1) ? a.Iinv : ((t == 2) ? a.Uenv : a.Ienv));
+            const int64_t rr = (t & 1) ? iq : uq;
+            if (half * 32 < D) prefetch_l2(tab + rr * D + half * 32);
+        }
+#endif
         const float y = __int_as_float(__shfl_sync(gmask, sc, gbase));
         const int pidx = __shfl_sync(gmask, sc, gbase + 1);
         const int old = __shfl_sync(gmask, sc, gbase + 2);

@@ -13,6 +13,15 @@
 #ifndef INVPREF_DIST_SOFTMAX
 #define INVPREF_DIST_SOFTMAX 1
 #endif
+// An extra step of look-ahead with prefetch.global.L2 (no third shared-memory stage needed) was measured and LOSES:
+// user pass 2.91 -> 2.99 ms, re-assignment 3.69 -> 4.66 ms on 25 M samples (round 2, B200): the kernels are bound by
+// DRAM throughput, not by exposed latency, and the prefetches only add request traffic.  Kept as A/B switches.
+#ifndef INVPREF_UPASS_L2_PREFETCH
+#define INVPREF_UPASS_L2_PREFETCH 0
+#endif
+#ifndef INVPREF_CLUSTER_L2_PREFETCH
+#define INVPREF_CLUSTER_L2_PREFETCH 0
+#endif
 
 namespace invpref {
 

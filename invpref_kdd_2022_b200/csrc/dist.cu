@@ -175,7 +175,9 @@ struct PeerOut { float* p[2 * P2P_MAX_WORLD]; };
 // Owner side of the PUSH exchange: partials from LOCAL staging (the ranks' item passes stored them there over
 // NVLink), summed in rank order, Adam in registers, and the updated row stored into every requester's row cache
 // for the next batch (posted NVLink writes).  Same per-element arithmetic and order as owner_adam_p2p_kernel.
-template <int VEC>
+// WMAX: compile-time bound of the rank loops (2, 4, 8, 16): the position loads, the staging loads and the pushes are
+// fully unrolled and all in flight together.
+template <int VEC, int WMAX>
 __global__ void __launch_bounds__(256) owner_adam_push_kernel(float* __restrict__ th0, float* __restrict__ th1,
                                                               float* __restrict__ m0, float* __restrict__ m1,
                                                               float* __restrict__ v0, float* __restrict__ v1,
@@ -194,12 +196,12 @@ __global__ void __launch_bounds__(256) owner_adam_push_kernel(float* __restrict_
         const int64_t j = rem / per_row;
         const int c = (int)(rem - j * per_row) * VEC;
         const float* __restrict__ stage = t ? stage1 : stage0;
-        int sl[P2P_MAX_WORLD];
-        float part[P2P_MAX_WORLD][VEC];
+        int sl[WMAX];
+        float part[WMAX][VEC];
 #pragma unroll
-        for (int p = 0; p < P2P_MAX_WORLD; ++p) sl[p] = (p < world) ? spos[(int64_t)p * n_rows + j] : -1;
+        for (int p = 0; p < WMAX; ++p) sl[p] = (p < world) ? spos[(int64_t)p * n_rows + j] : -1;
 #pragma unroll
-        for (int p = 0; p < P2P_MAX_WORLD; ++p) {
+        for (int p = 0; p < WMAX; ++p) {
             if (sl[p] >= 0) {
                 ldv_sys<VEC>(stage + (int64_t)sl[p] * dim + c, part[p]);   // written by a peer: never from this SM's L1
             } else {
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(256) owner_adam_push_kernel(float* __restrict_
 #pragma unroll
         for (int x = 0; x < VEC; ++x) g[x] = 0.f;
 #pragma unroll
-        for (int p = 0; p < P2P_MAX_WORLD; ++p)
+        for (int p = 0; p < WMAX; ++p)
             if (sl[p] >= 0) {
 #pragma unroll
                 for (int x = 0; x < VEC; ++x) g[x] += part[p][x];
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(256) owner_adam_push_kernel(float* __restrict_
         stv_stream<VEC>(vv, vr);
         if (npos != nullptr) {
 #pragma unroll
-            for (int p = 0; p < P2P_MAX_WORLD; ++p) {
+            for (int p = 0; p < WMAX; ++p) {
                 if (p < world) {
                     const int slot = npos[(int64_t)p * n_rows + j];
                     if (slot >= 0) stv<VEC>(caches.p[t * world + p] + (int64_t)slot * dim + c, pr);
@@ -311,8 +313,20 @@ int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* 
         pp.p[i] = caches_host[i];
         v4 = v4 && ((uintptr_t)caches_host[i] % 16 == 0);
     }
-    if (v4) owner_adam_push_kernel<4><<<grid_1d(2 * n_rows * (dim / 4)), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s, dyn);
-    else owner_adam_push_kernel<1><<<grid_1d(2 * n_rows * dim), 256, 0, stream>>>(th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s, dyn);
+#define PUSH_CALL(V, W)                                                                                          \
+    owner_adam_push_kernel<V, W><<<grid_1d(2 * n_rows * (dim / V)), 256, 0, stream>>>(                           \
+        th0, th1, m0, m1, v0, v1, n_rows, dim, world, stage0, stage1, spos, pp, npos, s, dyn)
+#define PUSH_W(V)                                                                                                \
+    do {                                                                                                         \
+        if (world <= 2) PUSH_CALL(V, 2);                                                                         \
+        else if (world <= 4) PUSH_CALL(V, 4);                                                                    \
+        else if (world <= 8) PUSH_CALL(V, 8);                                                                    \
+        else PUSH_CALL(V, 16);                                                                                   \
+    } while (0)
+    if (v4) PUSH_W(4);
+    else PUSH_W(1);
+#undef PUSH_W
+#undef PUSH_CALL
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }

@@ -137,6 +137,26 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
         if (seg_at(ord + 1) < n_seg) request_segment(stg ^ 1, meta + UM_DESC + ((ord + 1) & 3) * 8);
         request_desc(ord + 3, seg_at(ord + 3));     // its slot held this group's previous segment
         cp_async_commit();       // A_{ord+1}
+#if INVPREF_UPASS_L2_PREFETCH
+        // One more segment of look-ahead without a third shared-memory stage: the eight rows of segment ord+2 (its
+        // descriptor is already here) are pulled into L2 now, one 128-byte line per lane, so that the cp.async of
+        // group A_{ord+2}, issued one segment from now, pays L2 instead of DRAM latency.
+        if (seg_at(ord + 2) < n_seg) {
+            const int32_t* d2 = meta + UM_DESC + ((ord + 2) & 3) * 8;
+            const int t = lane >> 1, half = lane & 1;
+            const float* tab = a.side.own_inv_in;
+            tab = (t == 1) ? a.side.own_env_in : tab;
+            tab = (t == 2) ? a.side.m_inv : tab;
+            tab = (t == 3) ? a.side.m_env : tab;
+            tab = (t == 4) ? a.side.v_inv : tab;
+            tab = (t == 5) ? a.side.v_env : tab;
+            tab = (t == 6) ? a.side.partner_inv : tab;
+            tab = (t == 7) ? a.side.partner_env : tab;
+            const int64_t r2 = (t >= 6) ? d2[4] : d2[0];
+            if ((EPI == EPI_ADAM || t < 2 || t >= 6) && half * 32 < D)
+                prefetch_l2(tab + r2 * D + half * 32);
+        }
+#endif
 
         const int4 dA = *reinterpret_cast<const int4*>(meta + UM_DESC + (ord & 3) * 8);       // row, begin, end, n0
         const int4 dB = *reinterpret_cast<const int4*>(meta + UM_DESC + (ord & 3) * 8 + 4);   // p0, n1, p1, -

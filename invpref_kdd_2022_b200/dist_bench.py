@@ -83,11 +83,17 @@ def parity_check(rank, world, dev, mode, drv):
     peer-memory exchange vs the NCCL exchange bit for bit.  Returns a dict on rank 0."""
     import bench as B
     from invpref_kdd_2022_b200.engine import HotPath
-    w = dict(B.WORKLOADS["c5"], U=400_000, I=60_000, B=1 << 18)
+    # Shape of C5 scaled down; coefficients and table scales of the simulated-rank tests (tests/test_gpu_parallel.py):
+    # at the N(0, 0.01) init and the Yahoo coefficients the user-invariant gradients are ~1e-8 = Adam's eps, where
+    # g / (|g| + eps) turns summation-order noise into +-lr steps (BASELINE.md) and no two orders agree to 2e-4.
+    w = dict(B.WORKLOADS["c5"], U=400_000, I=60_000, B=1 << 18,
+             coef=dict(c_inv=0.8, c_ea=1.7, c_env=1.1, c_L2=0.6, c_L1=0.03))
     steps = 4
     U, I, Bg, batches = B.synth_batches(w, steps, seed=77)
-    kw = dict(alpha=1.0, use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
+    kw = dict(alpha=1.3, use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
     init = B.make_tables(w, dev, U=U, I=I, seed=123)                 # same seed on every rank: identical tables
+    for k, sc in (("Uinv", 10.0), ("Iinv", 10.0), ("Uenv", 30.0), ("Ienv", 30.0), ("E", 50.0), ("W", 3.0)):
+        init[k] *= sc
     res = {}
     for m in dict.fromkeys((mode, "nccl")):
         tr, _, got = make_sharded(w, U, I, Bg, rank, world, dev, m, init=init)

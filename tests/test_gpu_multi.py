@@ -1,8 +1,8 @@
 """GPU, two or more devices (self-skips otherwise; run by the builder with `gpurun --gpus 2`): the REAL multi-rank
 paths -- NCCL, torch symmetric memory, system-scope loads and posted NVLink stores between processes -- that the
 simulated-rank tests of test_gpu_parallel.py cannot reach.  One torchrun-style launch per case: the distributed
-trainer (dist_train.py) trains 3 epochs with a cluster() in between on N ranks, rank 0 trains the same thing with the
-single-GPU trainer and compares losses, every gathered table and the environment assignments."""
+trainer (dist_train.py) trains 3 epochs on N ranks and then re-assigns the environments once; rank 0 does the same with
+the single-GPU trainer and compares losses, every gathered table and the environment assignments."""
 import json
 import os
 import socket
@@ -23,7 +23,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("exchange", ["push", "pull", "nccl"])
-@pytest.mark.parametrize("case", ["explicit_d64_k4", "implicit_k6"])
+@pytest.mark.parametrize("case", ["explicit", "implicit"])
 def test_distributed_trainer_matches_single_gpu_on_real_ranks(case, exchange):
     n = torch.cuda.device_count()
     if n < 2:
@@ -44,5 +44,7 @@ def test_distributed_trainer_matches_single_gpu_on_real_ranks(case, exchange):
     r0 = [o for o in outs if o["rank"] == 0][0]
     assert r0["ok"], r0
     assert r0["exchange"] == exchange
-    # environments: fp32 near-ties may flip with the different summation order of the item gradients
-    assert r0["env_mismatch"] <= 0.05 * r0["N"], r0
+    # environments after one re-assignment on the trained tables: only fp32 near-ties may differ (the tables of the
+    # two runs differ by ~1e-5: a different, fixed summation order of the item partials)
+    assert r0["env_mismatch"] <= 0.01 * r0["N"], r0
+    assert abs(r0["diff"] - r0["ref_diff"]) <= r0["env_mismatch"]
