@@ -202,7 +202,10 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_kernel(BwdSideArgs a) {
     }
 }
 
-constexpr int RING = 4;   // interactions in flight per group (ring kernels)
+#ifndef INVPREF_RING_DEPTH
+#define INVPREF_RING_DEPTH 4
+#endif
+constexpr int RING = INVPREF_RING_DEPTH;   // interactions in flight per group (ring kernels)
 
 // One interaction of the ring kernels: its g-pack (shared by the group) and the two partner-row slices this
 // lane staged, accumulated exactly as accumulate_range does.

@@ -38,9 +38,13 @@ constexpr int GROUPS_PER_BLOCK = BLOCK / GROUP;
 // serially by one group, so the chunk bounds the critical path: small batches (B = 64K..256K with a few
 // hot rows) need small chunks to spread the hot rows over the machine, large ones amortise better with
 // big chunks.  chunk is a function of the batch size only.
+// Round 2: on the dataset-scale batches (<= 2^18 interactions, everything L2-resident) a group spends ~4-5 us per
+// interaction of serial latency, so the longest UNCHUNKED segment (2 * chunk) is the critical path of the rows kernels
+// (MIND shape, chunk 32: 64 interactions = 0.30 ms of a 0.55 ms step): chunks of 8 there.
 inline int chunk_for(int64_t B) {
-    int64_t c = 16;
-    while (c < 256 && c * 8192 < B) c *= 2;
+    if (B >= ((int64_t)1 << 22)) return 256;
+    int64_t c = 8;
+    while (c < 128 && c * 32768 < B) c *= 2;
     return (int)c;
 }
 
@@ -161,7 +165,7 @@ inline int64_t plan_ranges(int64_t B) { int64_t r = B / 64; return r < 1 ? 1 : (
 // Upper bound on the chunk count of a batch of AT MOST B interactions (monotonic in B, so a workspace sized
 // for the largest batch also fits every shorter one): chunks <= 1.5 * B' / chunk_for(B') for any B' <= B.
 inline int64_t plan_max_chunks(int64_t B) {
-    int64_t small = B / 16 < 16384 ? B / 16 : 16384;
+    int64_t small = B / 8 < 32768 ? B / 8 : 32768;     // B' / chunk_for(B') <= 32768 for every B' < 2^22
     int64_t big = B / 256;
     return 3 * (small > big ? small : big) / 2 + 4;
 }
@@ -206,7 +210,7 @@ inline PlanSide carve_plan_side(char* base, int64_t B, int64_t rows) {
 }
 
 // ---- workspace layout ------------------------------------------------------------------------
-constexpr int FWD_MAX_BLOCKS = 148 * 4 + 74;   // upper bound on CTAs that write a partial-sum vector
+constexpr int FWD_MAX_BLOCKS = 148 * 4 + 148;   // upper bound on CTAs that write a partial-sum vector
 
 struct Workspace {
     float* stash;        // [min(B, n_users) * 2 * D]  lazy mode: caught-up user rows of the batch

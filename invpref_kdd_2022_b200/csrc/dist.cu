@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) fetch_rows_p2p_kernel(PeerPtrs tables, in
             if (q < total) {
                 const int t = q >= per_table ? 1 : 0;
                 const int64_t rem = q - t * per_table;
-                const int64_t j = rem / per_row;
+                const int64_t j = (int64_t)((uint32_t)rem / (uint32_t)per_row);   // per_table < 2^31 (checked at launch)
                 const int c = (int)(rem - j * per_row) * VEC;
                 const float* src = tables.p[t * world + owner[j]] + rows[j] * dim + c;
                 ldv_sys<VEC>(src, r[u]);
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) owner_adam_p2p_kernel(float* __restrict__
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
         const int t = q >= per_table ? 1 : 0;
         const int64_t rem = q - t * per_table;
-        const int64_t j = rem / per_row;
+        const int64_t j = (int64_t)((uint32_t)rem / (uint32_t)per_row);   // per_table < 2^31 (checked at launch)
         const int c = (int)(rem - j * per_row) * VEC;
         // all slots first, then all (independent) remote loads, then the sum in rank order
         int sl[P2P_MAX_WORLD];
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) owner_adam_push_kernel(float* __restrict_
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
         const int t = q >= per_table ? 1 : 0;
         const int64_t rem = q - t * per_table;
-        const int64_t j = rem / per_row;
+        const int64_t j = (int64_t)((uint32_t)rem / (uint32_t)per_row);   // per_table < 2^31 (checked at launch)
         const int c = (int)(rem - j * per_row) * VEC;
         const float* __restrict__ stage = t ? stage1 : stage0;
         int sl[WMAX];
@@ -277,7 +277,7 @@ int launch_scatter_add_rows(const float* src, const int64_t* rows, int64_t n, in
 
 int launch_fetch_rows_p2p(const float* const* tables_host, int world, const int32_t* owner, const int64_t* rows,
                           int64_t n, int dim, float* out0, float* out1, cudaStream_t stream) {
-    if (world < 1 || world > P2P_MAX_WORLD) return INVPREF_ERR_BAD_ARG;
+    if (world < 1 || world > P2P_MAX_WORLD || n * (int64_t)dim >= 0x7fffffffLL) return INVPREF_ERR_BAD_ARG;
     PeerPtrs pp = {};
     bool v4 = dim % 4 == 0 && ((uintptr_t)out0 % 16 == 0) && ((uintptr_t)out1 % 16 == 0);
     for (int i = 0; i < 2 * world; ++i) { pp.p[i] = tables_host[i]; v4 = v4 && ((uintptr_t)tables_host[i] % 16 == 0); }
@@ -290,7 +290,7 @@ int launch_fetch_rows_p2p(const float* const* tables_host, int world, const int3
 int launch_owner_adam_p2p(float* th0, float* th1, float* m0, float* m1, float* v0, float* v1, int64_t n_rows, int dim,
                           int world, const float* const* grads_host, const int32_t* pos, const AdamScalars& s,
                           const invpref_dyn* dyn, cudaStream_t stream) {
-    if (world < 1 || world > P2P_MAX_WORLD) return INVPREF_ERR_BAD_ARG;
+    if (world < 1 || world > P2P_MAX_WORLD || n_rows * (int64_t)dim >= 0x7fffffffLL) return INVPREF_ERR_BAD_ARG;
     PeerPtrs pp = {};
     bool v4 = dim % 4 == 0;
     for (float* q : {th0, th1, m0, m1, v0, v1}) v4 = v4 && ((uintptr_t)q % 16 == 0);
@@ -305,7 +305,7 @@ int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* 
                            int world, const float* stage0, const float* stage1, const int32_t* spos,
                            float* const* caches_host, const int32_t* npos, const AdamScalars& s,
                            const invpref_dyn* dyn, cudaStream_t stream) {
-    if (world < 1 || world > P2P_MAX_WORLD) return INVPREF_ERR_BAD_ARG;
+    if (world < 1 || world > P2P_MAX_WORLD || n_rows * (int64_t)dim >= 0x7fffffffLL) return INVPREF_ERR_BAD_ARG;
     PeerOut pp = {};
     bool v4 = dim % 4 == 0 && ((uintptr_t)stage0 % 16 == 0) && ((uintptr_t)stage1 % 16 == 0);
     for (float* q : {th0, th1, m0, m1, v0, v1}) v4 = v4 && ((uintptr_t)q % 16 == 0);

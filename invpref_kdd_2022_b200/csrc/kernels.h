@@ -77,7 +77,7 @@ int launch_flush(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream); 
 int launch_sched_write(float2* sched, int step, const AdamScalars& s, const invpref_dyn* dyn, cudaStream_t stream);
 
 // ---- upass.cu: fused forward + user-side backward + Adam ---------------------------------------------
-constexpr int UPASS_CHUNK_CTAS = 74;   // CTAs of the (usually idle) long-user-segment kernel
+constexpr int UPASS_CHUNK_CTAS = 148;  // CTAs of the long-user-segment kernel (idle on C5, busy on the dataset configs)
 
 struct UserPassArgs {
     BwdSideArgs side;        // own = user tables, partner = item tables, plan = user side

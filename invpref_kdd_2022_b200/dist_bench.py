@@ -72,9 +72,9 @@ def prepare_all(tr, drv, batches, dev):
     prepared = []
     for (u, i, y, e) in batches:
         sb = drv.run(tr.prepare_gen(t(u), t(i), t(y)))
-        le = t(e)[sb.sel].contiguous()
-        sw = tr.hot.stat_envs(le, tr.hot.env_hist(le))[1] if le.numel() else torch.zeros(0, device=dev)
-        prepared.append((sb, le, sw))
+        ge = t(e)
+        gw = tr.hot.stat_envs(ge, tr.hot.env_hist(ge))[1]          # sample weights of the GLOBAL batch (train.py:945-957)
+        prepared.append((sb, ge[sb.sel].contiguous(), gw[sb.sel].contiguous()))
     return prepared
 
 
