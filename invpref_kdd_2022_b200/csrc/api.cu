@@ -663,7 +663,30 @@ int invpref_cluster(const invpref_desc* desc, const invpref_params* params, cons
     a.users = users; a.items = items; a.scores = scores; a.perm_idx = perm_idx; a.eps_table = eps_table;
     a.old_envs = old_envs; a.B = B; a.D = g.D; a.K = g.K; a.implicit = desc->implicit;
     a.new_envs = new_envs; a.hist = (unsigned long long*)hist; a.diff = (unsigned long long*)diff;
+    a.perm = nullptr; a.users32 = nullptr; a.items32 = nullptr;
     return launch_cluster(g, a, (cudaStream_t)stream);
+}
+
+int invpref_cluster_sorted(const invpref_desc* desc, const invpref_params* params, const int32_t* perm,
+                           const int32_t* users_sorted, const int32_t* items_sorted, const float* scores_sorted,
+                           const int64_t* perm_idx, const float* eps_table, const int64_t* old_envs, int64_t N,
+                           int64_t* new_envs, int64_t* hist, int64_t* diff, void* stream) {
+    Geometry g;
+    int rc = make_geometry(desc, &g);
+    if (rc != INVPREF_OK) return rc;
+    if ((rc = check_tables(g, params)) != INVPREF_OK) return rc;
+    if (N < 0 || N > 0x7fffffffLL || (N > 0 && (!perm || !users_sorted || !items_sorted || !scores_sorted || !new_envs)))
+        return INVPREF_ERR_BAD_ARG;
+    if (perm_idx && !eps_table) return INVPREF_ERR_BAD_ARG;
+    if (diff && !old_envs) return INVPREF_ERR_BAD_ARG;
+    if (N == 0) return INVPREF_OK;
+    ClusterArgs a;
+    a.Uinv = params->Uinv; a.Iinv = params->Iinv; a.Uenv = params->Uenv; a.Ienv = params->Ienv; a.E = params->E;
+    a.users = nullptr; a.items = nullptr; a.scores = scores_sorted; a.perm_idx = perm_idx; a.eps_table = eps_table;
+    a.old_envs = old_envs; a.B = N; a.D = g.D; a.K = g.K; a.implicit = desc->implicit;
+    a.new_envs = new_envs; a.hist = (unsigned long long*)hist; a.diff = (unsigned long long*)diff;
+    a.perm = perm; a.users32 = users_sorted; a.items32 = items_sorted;
+    return launch_cluster_sorted(g, a, (cudaStream_t)stream);
 }
 
 int invpref_stat_envs(const int64_t* envs, int64_t N, int32_t n_envs, const int64_t* hist, float* class_weights,

@@ -344,13 +344,14 @@ class HotPath:
                                              C.byref(g), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()), "backward")
 
     # ---- EM re-assignment -------------------------------------------------------------------------
-    def cluster(self, users, items, scores, perm_idx, eps_table, old_envs, trusted=False):
-        """train.py:846-879 over a whole slice.  Returns (new_envs int64[B], hist int64[K], diff int64[1])."""
+    def cluster(self, users, items, scores, perm_idx, eps_table, old_envs, trusted=False, out=None):
+        """train.py:846-879 over a whole slice.  Returns (new_envs int64[B], hist int64[K], diff int64[1]).
+        ``out``: optional int64 [B] tensor to write the new environments into (no allocation in the call)."""
         if not trusted and users.numel():
             self.check_ids(users, items, None)
         self.flush()
         B = users.numel()
-        new_envs = torch.empty(B, dtype=torch.int64, device=self.device)
+        new_envs = out if out is not None else torch.empty(B, dtype=torch.int64, device=self.device)
         hist = torch.zeros(self.n_envs, dtype=torch.int64, device=self.device)
         diff = torch.zeros(1, dtype=torch.int64, device=self.device)
         p = _lib.make_params(self.params)
@@ -364,17 +365,44 @@ class HotPath:
                    "cluster")
         return new_envs, hist, diff
 
+    def sorted_view(self, users, items, scores):
+        """User-sorted view of a dataset for ``cluster_sorted``: (perm int32, users int32, items int32, scores fp32).
+        Built once per dataset (ids never change): a stable sort by user id."""
+        perm = torch.sort(users, stable=True).indices
+        return (perm.to(torch.int32).contiguous(), users[perm].to(torch.int32).contiguous(),
+                items[perm].to(torch.int32).contiguous(), scores[perm].contiguous())
+
+    def cluster_sorted(self, view, perm_idx, eps_table, old_envs, out=None):
+        """``invpref_cluster_sorted``: the re-assignment of ``cluster`` over the user-sorted ``view`` of the dataset
+        (``sorted_view``); identical results, the user rows of consecutive samples come out of L2."""
+        self.flush()
+        perm, us, its, ys = view
+        N = perm.numel()
+        new_envs = out if out is not None else torch.empty(N, dtype=torch.int64, device=self.device)
+        hist = torch.zeros(self.n_envs, dtype=torch.int64, device=self.device)
+        diff = torch.zeros(1, dtype=torch.int64, device=self.device)
+        p = _lib.make_params(self.params)
+        _lib.check(self.lib.invpref_cluster_sorted(
+            C.byref(self.desc), C.byref(p), _lib.ptr(perm, torch.int32), _lib.ptr(us, torch.int32),
+            _lib.ptr(its, torch.int32), _lib.ptr(ys, torch.float32),
+            _lib.ptr(perm_idx, torch.int64) if perm_idx is not None else None,
+            _lib.ptr(eps_table, torch.float32) if eps_table is not None else None,
+            _lib.ptr(old_envs, torch.int64) if old_envs is not None else None, N, _lib.ptr(new_envs), _lib.ptr(hist),
+            _lib.ptr(diff) if old_envs is not None else None, _lib.stream_ptr()), "cluster_sorted")
+        return new_envs, hist, diff
+
     def env_hist(self, envs):
         hist = torch.zeros(self.n_envs, dtype=torch.int64, device=self.device)
         _lib.check(self.lib.invpref_env_hist(_lib.ptr(envs, torch.int64), envs.numel(), self.n_envs, _lib.ptr(hist),
                                              _lib.stream_ptr()), "env_hist")
         return hist
 
-    def stat_envs(self, envs, hist):
-        """train.py:945-957 -> (class_weights fp32[K], sample_weights fp32[N])."""
+    def stat_envs(self, envs, hist, out=None):
+        """train.py:945-957 -> (class_weights fp32[K], sample_weights fp32[N]).  ``out``: optional fp32 [N] tensor
+        for the sample weights."""
         N = envs.numel()
         cw = torch.empty(self.n_envs, dtype=torch.float32, device=self.device)
-        sw = torch.empty(N, dtype=torch.float32, device=self.device)
+        sw = out if out is not None else torch.empty(N, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.invpref_stat_envs(_lib.ptr(envs, torch.int64), N, self.n_envs, _lib.ptr(hist, torch.int64),
                                               _lib.ptr(cw), _lib.ptr(sw), _lib.stream_ptr()), "stat_envs")
         return cw, sw

@@ -33,7 +33,7 @@ class _InvPrefTrainManager:
             alpha: float = None, use_class_re_weight: bool = False, test_begin_epoch: int = 0,
             begin_cluster_epoch: int = None, stop_cluster_epoch: int = None, cluster_use_random_sort: bool = True,
             use_recommend_re_weight: bool = True, cache_plans: bool = True, lazy_adam: bool = True,
-            use_graph: bool = True, plan_cache_bytes: int = 16 << 30
+            use_graph: bool = True, plan_cache_bytes: int = 16 << 30, sorted_cluster: bool = True
     ):
         self.model = model
         self.evaluator = evaluator
@@ -86,6 +86,10 @@ class _InvPrefTrainManager:
         self._plan_bytes_used = 0
         self._ring = None
         self._consumed_slot = None
+        # cluster() walks the whole dataset: over a user-sorted view (built once: ids never change) the two user rows
+        # of consecutive samples come out of L2 instead of HBM (invpref_cluster_sorted; identical results)
+        self.sorted_cluster = bool(sorted_cluster)
+        self._cl_view = None
         self._scratch_busy_on_main = False      # a plan was built on the main stream since the loader last synced
         self._loss_rows = None
         # CUDA-graph replay of the epoch (train.py:881-910 issues 3-31 steps per epoch on the dataset configs, every
@@ -289,9 +293,14 @@ class _InvPrefTrainManager:
             draws = [np.random.randint(0, self.eps_random_tensor.shape[0], min(self.batch_size, n - lo))
                      for lo in range(0, n, self.batch_size)]
             perm = torch.from_numpy(np.concatenate(draws).astype(np.int64)).to(self.device)
-        new_envs, hist, diff = self.engine.cluster(self.users_tensor, self.items_tensor, self.scores_tensor, perm,
-                                                   self.eps_random_tensor if perm is not None else None, self.envs,
-                                                   trusted=True)
+        eps = self.eps_random_tensor if perm is not None else None
+        if self.sorted_cluster:
+            if self._cl_view is None:
+                self._cl_view = self.engine.sorted_view(self.users_tensor, self.items_tensor, self.scores_tensor)
+            new_envs, hist, diff = self.engine.cluster_sorted(self._cl_view, perm, eps, self.envs)
+        else:
+            new_envs, hist, diff = self.engine.cluster(self.users_tensor, self.items_tensor, self.scores_tensor, perm,
+                                                       eps, self.envs, trusted=True)
         self.envs = new_envs
         self._hist = hist
         return int(diff.item())

@@ -352,3 +352,33 @@ def test_error_paths():
         hp.train_step(t(u), t(i), t(y), t(e), None, c_inv=1, c_ea=1, c_env=1, c_L2=0, c_L1=0, alpha=1,
                       use_class_rw=True, use_rec_rw=False)
     assert hp.step == 0
+
+
+@pytest.mark.parametrize("shape", [(1000, 203, 4, 64, 30000, False), (300, 120, 6, 40, 9000, True),
+                                   (50, 30, 2, 30, 7, False), (4000, 11, 5, 16, 20001, True)])
+@pytest.mark.parametrize("with_eps", [True, False])
+def test_cluster_over_the_user_sorted_view_is_identical(shape, with_eps):
+    """invpref_cluster_sorted walks the dataset in stable user order (contiguous run per 16-lane group: the user rows of
+    consecutive samples come out of L2): new environments (written through perm to the original positions), histogram
+    and diff count must be bit-identical to invpref_cluster."""
+    import itertools
+    from invpref_kdd_2022_b200.engine import HotPath
+    U, I, K, D, N, implicit = shape
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(U + N)
+    u = torch.tensor(np.floor(U * rng.random(N) ** 1.5).astype(np.int64), device=dev)
+    i = torch.tensor(np.floor(I * rng.random(N) ** 3).astype(np.int64), device=dev)
+    y = torch.tensor((rng.integers(0, 2, N) if implicit else rng.integers(1, 6, N)).astype(np.float32), device=dev)
+    e = torch.tensor(rng.integers(0, K, N).astype(np.int64), device=dev)
+    shp = {"Uinv": (U, D), "Iinv": (I, D), "Uenv": (U, D), "Ienv": (I, D), "E": (K, D), "W": (K, D), "b": (K,)}
+    p = {k: torch.tensor(rng.normal(0, 0.3, s).astype(np.float32), device=dev) for k, s in shp.items()}
+    hp = HotPath(p, implicit, True, False)
+    base = torch.Tensor([1e-10 * (1e-1 ** k) for k in range(K)])
+    eps = torch.Tensor(list(itertools.permutations(base))).to(dev) if with_eps else None
+    pidx = torch.tensor(rng.integers(0, eps.shape[0], N), device=dev) if with_eps else None
+    a_new, a_hist, a_diff = hp.cluster(u, i, y, pidx, eps, e)
+    view = hp.sorted_view(u, i, y)
+    assert bool((view[1][1:] >= view[1][:-1]).all())
+    b_new, b_hist, b_diff = hp.cluster_sorted(view, pidx, eps, e)
+    assert torch.equal(a_new, b_new) and torch.equal(a_hist, b_hist) and torch.equal(a_diff, b_diff)
+    assert int(a_hist.sum()) == N
