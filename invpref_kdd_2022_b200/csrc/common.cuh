@@ -22,6 +22,10 @@
 #ifndef INVPREF_CLUSTER_L2_PREFETCH
 #define INVPREF_CLUSTER_L2_PREFETCH 0
 #endif
+// Row staging of the re-assignment kernel with cp.async.bulk + mbarrier (UBLKCP / SYNCS) instead of per-lane cp.async
+#ifndef INVPREF_CLUSTER_BULK
+#define INVPREF_CLUSTER_BULK 0
+#endif
 
 namespace invpref {
 

@@ -131,6 +131,34 @@ class HotPath:
                                                 _lib.stream_ptr()), "flush_users")
         self._dirty = False
 
+    # ---- the slice of the torch.optim.Optimizer surface callers of `trainer.optimizer` use (train.py:718) -------
+    def zero_grad(self, set_to_none: bool = True):
+        """No-op: gradients are never materialised (the segment reductions feed Adam in registers)."""
+
+    def state_dict(self):
+        """torch.optim.Adam-shaped: per-parameter step / exp_avg / exp_avg_sq in model.parameters() order."""
+        self.flush()
+        self._ensure_state(())
+        state = {i: {"step": torch.tensor(float(self.step)), "exp_avg": self.m[k], "exp_avg_sq": self.v[k]}
+                 for i, k in enumerate(PARAM_FIELDS)}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "params": list(range(len(PARAM_FIELDS)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        self.flush()
+        self._ensure_state(())
+        for i, k in enumerate(PARAM_FIELDS):
+            st = sd["state"][i]
+            self.m[k].copy_(st["exp_avg"])
+            self.v[k].copy_(st["exp_avg_sq"])
+            self.step = int(st["step"])
+        g = sd["param_groups"][0]
+        self.lr, self.betas, self.eps = float(g["lr"]), (float(g["betas"][0]), float(g["betas"][1])), float(g["eps"])
+        if self.lazy and self.last_step is not None:
+            self.last_step.fill_(self.step)            # every row is current at the loaded step
+        self.generation += 1
+
     # ---- buffers -------------------------------------------------------------------------
     def _ensure_state(self, shadow_for=TABLES):
         if self.m is None:

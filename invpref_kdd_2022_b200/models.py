@@ -148,8 +148,16 @@ class _InvPref(nn.Module):
         return super().state_dict(*a, **kw)
 
     def _apply(self, fn, *a, **kw):
-        self._hot = None            # .to(device) / .float() re-allocate the storages
-        return super()._apply(fn, *a, **kw)
+        """``.to(device)`` / ``.float()`` / ``.cuda()``: lazily updated user rows are brought up to date first; the
+        engine (which holds the Adam state) is dropped only if a storage was actually re-allocated -- a no-op call
+        keeps it.  A trainer built before a re-allocation refuses to step afterwards (train.py)."""
+        if self._hot is not None:
+            self._hot.flush()
+        before = {k: p.data.data_ptr() for k, p in self.named_hot_params().items()}
+        out = super()._apply(fn, *a, **kw)
+        if any(p.data.data_ptr() != before[k] for k, p in self.named_hot_params().items()):
+            self._hot = None
+        return out
 
     # ---- reference API -----------------------------------------------------------------------
     def forward(self, users_id, items_id, envs_id, alpha):

@@ -33,7 +33,7 @@ class _InvPrefTrainManager:
             alpha: float = None, use_class_re_weight: bool = False, test_begin_epoch: int = 0,
             begin_cluster_epoch: int = None, stop_cluster_epoch: int = None, cluster_use_random_sort: bool = True,
             use_recommend_re_weight: bool = True, cache_plans: bool = True, lazy_adam: bool = True,
-            use_graph: bool = True, plan_cache_bytes: int = 16 << 30, sorted_cluster: bool = True
+            use_graph: bool = True, plan_cache_bytes: int = 16 << 30, sorted_cluster: bool = False
     ):
         self.model = model
         self.evaluator = evaluator
@@ -86,8 +86,11 @@ class _InvPrefTrainManager:
         self._plan_bytes_used = 0
         self._ring = None
         self._consumed_slot = None
-        # cluster() walks the whole dataset: over a user-sorted view (built once: ids never change) the two user rows
-        # of consecutive samples come out of L2 instead of HBM (invpref_cluster_sorted; identical results)
+        # cluster() walks the whole dataset; optionally over a user-sorted view (built once: ids never change) in which
+        # the two user rows of consecutive samples come out of L2 instead of HBM (invpref_cluster_sorted; identical
+        # results).  Off by default: measured on the B200 it moves fewer DRAM bytes but is SLOWER (4.9 vs 5.8 G samples/s
+        # at 96 M samples) -- the scattered tie-break / old / new environment accesses through the permutation cost more
+        # than the user rows save, and the unsorted kernel already runs at 0.95 of the HBM roofline.
         self.sorted_cluster = bool(sorted_cluster)
         self._cl_view = None
         self._scratch_busy_on_main = False      # a plan was built on the main stream since the loader last synced
@@ -168,7 +171,14 @@ class _InvPrefTrainManager:
         self._consumed_slot = slot
         return r["buf"][slot]
 
+    def _check_engine(self):
+        if self.model._hot is not self.engine:
+            raise RuntimeError("the model's parameter storages were re-allocated (.to() / .float() / load into new "
+                               "tensors) after this trainer was built: its Adam state belongs to the old storages; "
+                               "move the model first, then construct the trainer")
+
     def _step(self, users, items, scores, envs, weights, alpha, loss_out=None, plan_key=None):
+        self._check_engine()
         users, items, envs = users.contiguous(), items.contiguous(), envs.contiguous()
         assert users.shape == items.shape == scores.shape == envs.shape          # train.py:789-790
         return self.engine.train_step(
@@ -248,6 +258,7 @@ class _InvPrefTrainManager:
         """train.py:881-910.  Losses stay on the device until the end of the epoch (one sync per epoch
         instead of six per batch); the returned dict is the same np.mean of per-batch floats."""
         self.model.train()
+        self._check_engine()
         if self._loss_rows is None or self._loss_rows.shape[0] != self.batch_num:
             self._loss_rows = torch.zeros((self.batch_num, 6), dtype=torch.float32, device=self.device)
             if self._graph is not None:

@@ -218,3 +218,27 @@ def test_bounded_plan_cache_streams_the_remaining_plans():
         assert out[name][0] == out["all"][0], name
         for k in out["all"][1]:
             assert torch.equal(out[name][1][k], out["all"][1][k]), (name, k)
+
+
+def test_model_move_and_optimizer_surface():
+    """A no-op .to() keeps the engine (and flushes lazily updated rows first); a real re-allocation drops it and a
+    trainer built before refuses to step; trainer.optimizer offers zero_grad / state_dict / load_state_dict."""
+    g = Golden("coat_explicit")
+    model, tm = build(g)
+    tm.stat_envs()
+    tm.train_a_epoch()
+    eng = tm.engine
+    model.to("cuda:0")                                   # no-op: same storages
+    assert model._hot is eng
+    tm.train_a_epoch()                                   # still steps
+    tm.optimizer.zero_grad()
+    sd = tm.optimizer.state_dict()
+    assert len(sd["state"]) == 7 and int(sd["state"][0]["step"]) == eng.step == 2 * tm.batch_num
+    assert torch.equal(sd["state"][1]["exp_avg"], eng.m["Iinv"])
+    m0 = {k: v.clone() for k, v in eng.m.items()}
+    tm.optimizer.load_state_dict(sd)
+    assert all(torch.equal(eng.m[k], m0[k]) for k in m0)
+    model.double()                                       # re-allocates every storage
+    assert model._hot is None
+    with pytest.raises(RuntimeError, match="re-allocated"):
+        tm.train_a_epoch()
