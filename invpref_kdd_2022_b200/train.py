@@ -91,6 +91,11 @@ class _InvPrefTrainManager:
         # results).  Off by default: measured on the B200 it moves fewer DRAM bytes but is SLOWER (4.9 vs 5.8 G samples/s
         # at 96 M samples) -- the scattered tie-break / old / new environment accesses through the permutation cost more
         # than the user rows save, and the unsorted kernel already runs at 0.95 of the HBM roofline.
+        # train_a_batch (the reference's public per-batch call) leaves every parameter current, as torch.optim.Adam does:
+        # with lazy Adam that is a sweep over the user rows that are behind.  Callers that drive their own batch loop
+        # and read the tables only through this package (forward / predict / cluster / state_dict flush on demand) can
+        # set this to False and keep the lazy saving.
+        self.flush_after_batch = True
         self.sorted_cluster = bool(sorted_cluster)
         self._cl_view = None
         self._scratch_busy_on_main = False      # a plan was built on the main stream since the loader last synced
@@ -194,7 +199,8 @@ class _InvPrefTrainManager:
                               batch_envs_tensor.contiguous(), sync=False)
         out = self._step(batch_users_tensor, batch_items_tensor, batch_scores_tensor, batch_envs_tensor,
                          batch_sample_weights, alpha)
-        self.engine.flush()
+        if self.flush_after_batch:
+            self.engine.flush()
         vals = out.cpu().tolist()
         self.engine.raise_if_bad_ids()
         return dict(zip(LOSS_KEYS, vals))
