@@ -261,10 +261,10 @@ __device__ __forceinline__ void ring_consume(const float* __restrict__ gslot, co
 // Ring version of bwd_chunks_kernel: a group walks its chunks (c = g, g + G, ...) with the producer RING-1
 // interactions ahead, across chunk boundaries.  Chunks are spread over the CTAs first (a few hundred chunks of
 // a few hundred sequential interactions each: the critical path of the item pass).
-template <int VEC, int NV, bool STASH, int KX>
+template <int VEC, int NV, bool STASH, int KX, int DX = GROUP * VEC * NV>
 __global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_ring_kernel(BwdSideArgs a) {
     extern __shared__ __align__(128) float smem[];
-    const int D = KX ? GROUP * VEC * NV : a.D, K = KX ? KX : a.K, GS = KX ? (KX <= 5 ? 8 : 12) : a.GS, KD = K * D;
+    const int D = KX ? DX : a.D, K = KX ? KX : a.K, GS = KX ? (KX <= 5 ? 8 : 12) : a.GS, KD = K * D;
     float* sE = smem;
     float* sW = smem + KD;
     float* sG = smem + ((2 * KD + 3) & ~3);
@@ -344,12 +344,12 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_ring_kernel(BwdSideArgs a
 //    -- and copies the partner rows (each lane its own slice) and the g-pack of every interaction global ->
 //    shared with cp.async: no register is held while the data is in flight;
 //  * per segment the arithmetic is accumulate_range's / finish_row's, value for value and in the same order.
-// KX > 0: D = 16 * VEC * NV and K = KX are compile-time constants (every bounds guard folds away, row offsets are
-// shifts); KX = 0: any D, K.
-template <int VEC, int NV, int EPI, bool STASH, int KX>
+// KX > 0: D = DX (64, or 40 = the drivers' factor_num) and K = KX are compile-time constants (bounds guards fold away,
+// row offsets are shifts and adds); KX = 0: any D, K.
+template <int VEC, int NV, int EPI, bool STASH, int KX, int DX = GROUP * VEC * NV>
 __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, int long_len) {
     extern __shared__ __align__(128) float smem[];
-    const int D = KX ? GROUP * VEC * NV : a.D, K = KX ? KX : a.K, GS = KX ? (KX <= 5 ? 8 : 12) : a.GS, KD = K * D;
+    const int D = KX ? DX : a.D, K = KX ? KX : a.K, GS = KX ? (KX <= 5 ? 8 : 12) : a.GS, KD = K * D;
     float* sE = smem;
     float* sW = smem + KD;
     float* sG = smem + ((2 * KD + 3) & ~3);                    // [groups][RING + 1][12] g-packs
@@ -793,12 +793,16 @@ int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stre
         INVPREF_SET_SMEM_ONCE(KERNEL, smem);                                                                     \
         KERNEL<<<grid, BLOCK, smem, stream>>>(a);                                                                \
     } while (0)
-#define CALL(V, N, KX_)                                                                                          \
+#define CALL_D(V, N, KX_, DX_)                                                                                   \
     do {                                                                                                         \
-        if (stash) LAUNCH((bwd_chunks_ring_kernel<V, N, true, KX_>));                                            \
-        else LAUNCH((bwd_chunks_ring_kernel<V, N, false, KX_>));                                                 \
+        if (stash) LAUNCH((bwd_chunks_ring_kernel<V, N, true, KX_, DX_>));                                       \
+        else LAUNCH((bwd_chunks_ring_kernel<V, N, false, KX_, DX_>));                                            \
     } while (0)
-        if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 2) { CALL(4, 1, 2); }
+#define CALL(V, N, KX_) CALL_D(V, N, KX_, GROUP * V * N)
+        if (g.VEC == 4 && g.D == 40 && g.K == 2) { CALL_D(4, 1, 2, 40); }
+        else if (g.VEC == 4 && g.D == 40 && g.K == 6) { CALL_D(4, 1, 6, 40); }
+        else if (g.VEC == 4 && g.D == 40 && g.K == 5) { CALL_D(4, 1, 5, 40); }
+        else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 2) { CALL(4, 1, 2); }
         else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 4) { CALL(4, 1, 4); }
         else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 6) { CALL(4, 1, 6); }
         else if (g.VEC == 4) { CALL(4, 1, 0); }
@@ -806,6 +810,7 @@ int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stre
         else if (g.VEC == 2) { CALL(2, 2, 0); }
         else { CALL(1, 4, 0); }
 #undef CALL
+#undef CALL_D
 #undef LAUNCH
         count_launch();
         return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
@@ -840,14 +845,18 @@ int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream
         INVPREF_SET_SMEM_ONCE(KERNEL, smem);                                                                     \
         KERNEL<<<grid, BLOCK, smem, stream>>>(a, long_len);                                                      \
     } while (0)
-#define CALL(V, N, KX_)                                                                                          \
+#define CALL_D(V, N, KX_, DX_)                                                                                   \
     do {                                                                                                         \
-        if (epi == EPI_ADAM && stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, true, KX_>));                 \
-        else if (epi == EPI_ADAM) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, false, KX_>));                    \
-        else if (stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, true, KX_>));                             \
-        else LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, false, KX_>));                                       \
+        if (epi == EPI_ADAM && stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, true, KX_, DX_>));            \
+        else if (epi == EPI_ADAM) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_ADAM, false, KX_, DX_>));               \
+        else if (stash) LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, true, KX_, DX_>));                        \
+        else LAUNCH((bwd_rows_ring_kernel<V, N, EPI_EXPORT, false, KX_, DX_>));                                  \
     } while (0)
-        if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 2) { CALL(4, 1, 2); }         // exact: D = 64, K = KT
+#define CALL(V, N, KX_) CALL_D(V, N, KX_, GROUP * V * N)
+        if (g.VEC == 4 && g.D == 40 && g.K == 2) { CALL_D(4, 1, 2, 40); }          // exact: D = 40 (MovieLens / MIND)
+        else if (g.VEC == 4 && g.D == 40 && g.K == 6) { CALL_D(4, 1, 6, 40); }
+        else if (g.VEC == 4 && g.D == 40 && g.K == 5) { CALL_D(4, 1, 5, 40); }
+        else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 2) { CALL(4, 1, 2); }    // exact: D = 64, K = KT
         else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 4) { CALL(4, 1, 4); }
         else if (g.VEC == 4 && g.D == GROUP * 4 && g.K == 6) { CALL(4, 1, 6); }
         else if (g.VEC == 4) { CALL(4, 1, 0); }
@@ -855,6 +864,7 @@ int launch_bwd_rows(const Geometry& g, const BwdSideArgs& a, int epi, cudaStream
         else if (g.VEC == 2) { CALL(2, 2, 0); }
         else { CALL(1, 4, 0); }
 #undef CALL
+#undef CALL_D
 #undef LAUNCH
         count_launch();
         return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;

@@ -25,14 +25,15 @@ namespace {
 // CL_STAGES-1 iterations before they are read.
 template <int VEC, int NV> struct ClStages { static constexpr int value = (VEC * NV <= 8) ? 3 : 2; };
 
-// EXACT: D = 16 * VEC * NV and K = KT are compile-time constants (bounds guards fold away, row offsets are shifts).
-template <int VEC, int NV, int KT, bool EXACT>
+// DX > 0: D = DX (64 or 40) and K = KT are compile-time constants (bounds guards fold away, row offsets are shifts and
+// adds); DX = 0: any D, K.
+template <int VEC, int NV, int KT, int DX>
 __global__ void __launch_bounds__(BLOCK, (VEC * NV <= 4 && KT <= 4) ? 4 : 1) cluster_kernel(ClusterArgs a,
                                                                                             int eps_rows_smem) {
     extern __shared__ __align__(128) float smem[];
     constexpr int RV = VEC * NV, ST = ClStages<VEC, NV>::value;
     constexpr bool E_REG = KT * RV <= 32;      // this lane's slice of E lives in registers for the whole kernel
-    const int D = EXACT ? GROUP * VEC * NV : a.D, K = EXACT ? KT : a.K, KD = K * D;
+    const int D = DX ? DX : a.D, K = DX ? KT : a.K, KD = K * D;
     float* sE = smem;                                        // [K*D]
     float* sEps = smem + ((KD + 3) & ~3);                    // [eps_rows_smem * K]
     float* ring = smem + ring_align_up(((KD + 3) & ~3) + ((eps_rows_smem * K + 3) & ~3));   // [ST][4 rows][NV][BLOCK][VEC]
@@ -240,13 +241,13 @@ __global__ void __launch_bounds__(BLOCK, (VEC * NV <= 4 && KT <= 4) ? 4 : 1) clu
 // about 8 D + 8 D U / N + 130 (ids and scores are read sequentially from the sorted copies; the tie-break index, the
 // old environment and the new environment go through perm: three scattered sectors).  Same per-sample arithmetic as
 // cluster_kernel, value for value.
-template <int VEC, int NV, int KT, bool EXACT>
+template <int VEC, int NV, int KT, int DX>
 __global__ void __launch_bounds__(BLOCK, (VEC * NV <= 4 && KT <= 4) ? 4 : 1) cluster_sorted_kernel(ClusterArgs a,
                                                                                             int eps_rows_smem) {
     extern __shared__ __align__(128) float smem[];
     constexpr int RV = VEC * NV, ST = ClStages<VEC, NV>::value;
     constexpr bool E_REG = KT * RV <= 32;      // this lane's slice of E lives in registers for the whole kernel
-    const int D = EXACT ? GROUP * VEC * NV : a.D, K = EXACT ? KT : a.K, KD = K * D;
+    const int D = DX ? DX : a.D, K = DX ? KT : a.K, KD = K * D;
     float* sE = smem;                                        // [K*D]
     float* sEps = smem + ((KD + 3) & ~3);                    // [eps_rows_smem * K]
     float* ring = smem + ring_align_up(((KD + 3) & ~3) + ((eps_rows_smem * K + 3) & ~3));   // [ST][4 rows][NV][BLOCK][VEC]
@@ -476,15 +477,21 @@ int launch_cluster(const Geometry& g, const ClusterArgs& a, cudaStream_t stream)
         INVPREF_SET_SMEM_ONCE((cluster_kernel<V, N, KT_, X>), smem);                                             \
         cluster_kernel<V, N, KT_, X><<<grid, BLOCK, smem, stream>>>(a, eps_rows);                                \
     } while (0)
-#define CALL(V, N, KT_) CALL_X(V, N, KT_, false)
-#define CALL_EXACT(V, N, KT_) CALL_X(V, N, KT_, true)
-    if (g.VEC == 4 && g.D == GROUP * 4 && g.K == g.KT) {
+#define CALL(V, N, KT_) CALL_X(V, N, KT_, 0)
+#define CALL_EXACT(V, N, KT_) CALL_X(V, N, KT_, 64)
+#define CALL_EXACT40(V, N, KT_) CALL_X(V, N, KT_, 40)
+    if (g.VEC == 4 && g.D == 64 && g.K == g.KT) {
         INVPREF_DISPATCH_K(4, 1, g.KT, CALL_EXACT);
+    } else if (g.VEC == 4 && g.D == 40 && g.K == g.KT) {
+        INVPREF_DISPATCH_K(4, 1, g.KT, CALL_EXACT40);
+    } else if (g.VEC == 4 && g.D == 40 && g.K == 5) {
+        CALL_EXACT40(4, 1, 5);
     } else {
         INVPREF_DISPATCH_GEOM(g, CALL);
     }
 #undef CALL
 #undef CALL_EXACT
+#undef CALL_EXACT40
 #undef CALL_X
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
@@ -507,15 +514,21 @@ int launch_cluster_sorted(const Geometry& g, const ClusterArgs& a, cudaStream_t 
         INVPREF_SET_SMEM_ONCE((cluster_sorted_kernel<V, N, KT_, X>), smem);                                             \
         cluster_sorted_kernel<V, N, KT_, X><<<grid, BLOCK, smem, stream>>>(a, eps_rows);                                \
     } while (0)
-#define CALL(V, N, KT_) CALL_X(V, N, KT_, false)
-#define CALL_EXACT(V, N, KT_) CALL_X(V, N, KT_, true)
-    if (g.VEC == 4 && g.D == GROUP * 4 && g.K == g.KT) {
+#define CALL(V, N, KT_) CALL_X(V, N, KT_, 0)
+#define CALL_EXACT(V, N, KT_) CALL_X(V, N, KT_, 64)
+#define CALL_EXACT40(V, N, KT_) CALL_X(V, N, KT_, 40)
+    if (g.VEC == 4 && g.D == 64 && g.K == g.KT) {
         INVPREF_DISPATCH_K(4, 1, g.KT, CALL_EXACT);
+    } else if (g.VEC == 4 && g.D == 40 && g.K == g.KT) {
+        INVPREF_DISPATCH_K(4, 1, g.KT, CALL_EXACT40);
+    } else if (g.VEC == 4 && g.D == 40 && g.K == 5) {
+        CALL_EXACT40(4, 1, 5);
     } else {
         INVPREF_DISPATCH_GEOM(g, CALL);
     }
 #undef CALL
 #undef CALL_EXACT
+#undef CALL_EXACT40
 #undef CALL_X
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;

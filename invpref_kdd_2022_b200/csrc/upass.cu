@@ -52,11 +52,12 @@ constexpr int UM_ITS = 40;     // [2][4]  {env, score, weight, -} of interaction
 constexpr int UM_ITI = 48;     // [2][2]  {perm, partner} of interaction i, slot i & 1
 constexpr int UM_WORDS = 56;
 
-// EXACT: D = 16 * VEC * NV and K = KT are compile-time constants (bounds guards fold away, row offsets are shifts).
-template <int VEC, int NV, int KT, int EPI, bool LAZY, bool EXACT>
+// DX > 0: D = DX (64: every lane active; 40: the drivers' factor_num, lanes 0..9 active) and K = KT are compile-time
+// constants (bounds guards fold away or become one lane predicate, row offsets are shifts and adds); DX = 0: any D, K.
+template <int VEC, int NV, int KT, int EPI, bool LAZY, int DX>
 __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArgs a, int long_len) {
     extern __shared__ __align__(128) float smem[];
-    const int D = EXACT ? GROUP * VEC * NV : a.side.D, K = EXACT ? KT : a.side.K, KD = K * D;
+    const int D = DX ? DX : a.side.D, K = DX ? KT : a.side.K, KD = K * D;
     const Smem s = carve_smem(smem, KD);
     float* ring = smem + ring_align_up((4 + 2 * GROUPS_PER_BLOCK) * KD + SB_WORDS);   // [2][8][NV][BLOCK][VEC]
     int32_t* meta = reinterpret_cast<int32_t*>(ring + (size_t)2 * UP_SLOTS * NV * VEC * BLOCK) +
@@ -333,16 +334,20 @@ int launch_upass_rows(const Geometry& g, const UserPassArgs& a, int epi, int gri
         else if (epi == EPI_ADAM) LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_ADAM, false, X>));             \
         else LAUNCH((upass_rows_staged_kernel<V, N, KT_, EPI_EXPORT, false, X>));                                \
     } while (0)
-#define CALL(V, N, KT_) CALL_X(V, N, KT_, false)
-#define CALL_EXACT(V, N, KT_) CALL_X(V, N, KT_, true)
+#define CALL(V, N, KT_) CALL_X(V, N, KT_, 0)
+#define CALL_EXACT(V, N, KT_) CALL_X(V, N, KT_, 64)
+#define CALL_EXACT40(V, N, KT_) CALL_X(V, N, KT_, 40)
         const int _k = g.KT;
-        if (g.VEC == 4 && g.D == GROUP * 4 && g.K == g.KT) { INVPREF_DISPATCH_K(4, 1, _k, CALL_EXACT); }
+        if (g.VEC == 4 && g.D == 64 && g.K == g.KT) { INVPREF_DISPATCH_K(4, 1, _k, CALL_EXACT); }
+        else if (g.VEC == 4 && g.D == 40 && g.K == g.KT) { INVPREF_DISPATCH_K(4, 1, _k, CALL_EXACT40); }
+        else if (g.VEC == 4 && g.D == 40 && g.K == 5) { CALL_EXACT40(4, 1, 5); }     // Yahoo!R3 drivers: K = 5
         else if (g.VEC == 4) { INVPREF_DISPATCH_K(4, 1, _k, CALL); }
         else if (g.VEC == 2 && g.NV == 1) { INVPREF_DISPATCH_K(2, 1, _k, CALL); }
         else if (g.VEC == 2) { INVPREF_DISPATCH_K(2, 2, _k, CALL); }
         else { INVPREF_DISPATCH_K(1, 4, _k, CALL); }
 #undef CALL
 #undef CALL_EXACT
+#undef CALL_EXACT40
 #undef CALL_X
 #undef LAUNCH
         count_launch();

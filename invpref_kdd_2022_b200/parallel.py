@@ -189,6 +189,10 @@ class ReplicatedTrainer:
     def step_gen(self, users, items, scores, envs, weights, global_batch, plan=None, **kw):
         """users..weights: this rank's chunk (may be empty).  Yields collectives; returns the loss tensor."""
         self.gflat.zero_()
+        # hot.m / hot.v alias the gradient buffer: safe only while EVERY group is exported (the step then never
+        # touches per-tensor Adam state)
+        all_exported = _lib.EXPORT_USER_GRADS | _lib.EXPORT_ITEM_GRADS | _lib.EXPORT_SMALL_GRADS
+        assert self.flags & all_exported == all_exported, "ReplicatedTrainer: m/v are aliased, every group must be exported"
         if users.numel() > 0:
             self.hot.train_step(users, items, scores, envs, weights, plan=plan, loss_out=self.loss,
                                 grads_out=self.grads, global_batch=global_batch, flags=self.flags, **kw)

@@ -202,3 +202,37 @@ def test_fused_evaluator_ties_go_to_the_lowest_item_id():
     assert top[2] == [0, 1, 2, 3, 4, 5]
     assert hits.cpu().tolist() == [[0, 0, 0, 0, 0, 1], [1, 0, 0, 0, 0, 0], [0, 0, 0, 1, 0, 0]]
     assert n_gt.cpu().tolist() == [1, 1, 1]
+
+
+@pytest.mark.parametrize("name", ["MovieLens_InvPref", "MIND_InvPref", "Yahoo_InvPref_explicit"])
+def test_remaining_driver_mains_run_on_synthetic_data(name):
+    """The MovieLens / MIND / Yahoo-explicit mains (reference MovieLens_InvPref.py, MIND_InvPref.py,
+    Yahoo_InvPref_explicit.py main()) with their own MODEL / TRAIN / EVALUATE configs, on synthetic interactions of a
+    reduced shape (their train.csv files are not in the reference checkout / too large for a unit test): epochs run
+    as CUDA graphs from the second one on, cluster() + stat_envs() in between, evaluator as the driver configures it
+    (MIND: test item pool; MovieLens: all items; Yahoo explicit: MSE)."""
+    import importlib
+    from invpref_kdd_2022_b200 import dataloader as dl
+    drv = importlib.import_module("invpref_kdd_2022_b200.drivers." + name)
+    dev = torch.device("cuda:0")
+    implicit = name != "Yahoo_InvPref_explicit"
+    U, I, N = 800, 300, 40000
+    tr = dl.synthetic_interactions(U, I, N, implicit, seed=21)
+    te = dl.synthetic_interactions(U, I, 4000, implicit, seed=22)
+    if implicit:
+        te = te[te[:, 2] > 0]
+        loader = dl.YahooImplicitBCELossDataLoader("", dev, train=tr, test=te)
+        if drv.HAS_ITEM_POOL_FILE:
+            loader.set_item_pool(dl.synthetic_item_pool(te, U, I))
+    else:
+        loader = dl.ExplicitDataLoader("", dev, train=tr, test=te)
+    tc = dict(drv.TRAIN_CONFIG, epochs=6, evaluate_interval=3, cluster_interval=2, batch_size=8192)
+    best, idx, res = drv.main(dev, drv.MODEL_CONFIG, tc, drv.EVALUATE_CONFIG, loader, 17373331, silent=True, auto=True,
+                              query=False)
+    assert np.isfinite(best) and len(idx) >= 1
+    if implicit:
+        ks = drv.EVALUATE_CONFIG["top_k_list"]
+        assert set(res) == {f"{m}@{k}" for m in ("ndcg", "recall", "precision") for k in ks}
+        assert 0.0 <= best <= 1.0
+    else:
+        assert set(res) == {"mse", "rmse", "mae"}

@@ -242,3 +242,40 @@ def test_model_move_and_optimizer_surface():
     assert model._hot is None
     with pytest.raises(RuntimeError, match="re-allocated"):
         tm.train_a_epoch()
+
+
+@pytest.mark.parametrize("K,D", [(8, 256), (6, 128)])
+def test_trainer_default_lazy_falls_back_where_the_fused_pass_is_unavailable(K, D):
+    """Shapes whose per-CTA dE/dW slices do not fit (K * D > 682) have no fused user pass and hence no lazy Adam: the
+    trainer's default lazy_adam=True must fall back to plain dense Adam by itself and match the oracle."""
+    from invpref_kdd_2022_b200.models import InvPrefExplicit
+    from invpref_kdd_2022_b200.train import ExplicitTrainManager
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    U, I, N = 60, 40, 3000
+    data = np.stack([rng.integers(0, U, N), rng.integers(0, I, N), rng.integers(1, 6, N)], axis=1).astype(np.int64)
+    data[0, :2] = (U - 1, I - 1)
+    torch.manual_seed(5)
+    np.random.seed(5)
+    model = InvPrefExplicit(U, I, K, D, True, False)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.mul_(10.0)
+    model = model.to(dev)
+    p64 = {k: prm.detach().cpu().numpy().astype(np.float64) for k, prm in model.named_hot_params().items()}
+    tm = ExplicitTrainManager(model=model, evaluator=NullEvaluator(), device=dev, training_data=torch.LongTensor(data).to(dev),
+                              batch_size=N, epochs=1, cluster_interval=1, evaluate_interval=1, lr=1e-2, invariant_coe=0.8,
+                              env_aware_coe=1.7, env_coe=1.1, L2_coe=0.6, L1_coe=0.03, alpha=1.3,
+                              use_class_re_weight=True, use_recommend_re_weight=True)
+    assert tm.engine.lazy_requested and not tm.engine.lazy_supported and not tm.engine.lazy
+    tm.stat_envs()
+    envs, sw = tm.envs.cpu().numpy(), tm.sample_weights.cpu().numpy()
+    ld = tm.train_a_epoch()
+    hyp = on.Hyper(0.8, 1.7, 1.1, 0.6, 0.03, alpha=1.3, lr=1e-2, use_class_rw=True, use_rec_rw=True)
+    st = on.new_adam_state(p64, np.float64)
+    lo, _ = on.train_step(p64, st, data[:, 0], data[:, 1], data[:, 2].astype(np.float64), envs, sw.astype(np.float64), hyp,
+                          on.Flags(False, True, False), np.float64)
+    for k in on.LOSS_KEYS:
+        assert abs(ld[k] - float(lo[k])) <= 1e-5 * abs(float(lo[k])), k
+    for k, prm in model.named_hot_params().items():
+        assert nerr(prm.detach().cpu().numpy(), p64[k]) <= 1e-4, k
