@@ -11,15 +11,15 @@ PY
 }
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 for wl in c2 c3 c4; do
-  timeout 600 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu-baseline --no-config-legs --nbatch 3 > gpurun_out/r2l_$wl.json 2> gpurun_out/r2l_$wl.err; show gpurun_out/r2l_$wl.json "$wl"
+  timeout 600 python bench.py --workload $wl --steps 20 --warmup 5 --no-cpu-baseline --no-config-legs --nbatch 3 > gpurun_out/r2m1_$wl.json 2> gpurun_out/r2m1_$wl.err; show gpurun_out/r2m1_$wl.json "$wl"
 done
 echo "== pytest -m gpu"; date
-timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/r2l_pytest.log; tail -6 gpurun_out/r2l_pytest.log
+timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -60 > gpurun_out/r2m1_pytest.log; tail -6 gpurun_out/r2m1_pytest.log
 echo "== bench default"; date
-timeout 900 python bench.py > gpurun_out/r2l_bench.json 2> gpurun_out/r2l_bench.err; tail -c 400 gpurun_out/r2l_bench.err
+timeout 900 python bench.py > gpurun_out/r2m1_bench.json 2> gpurun_out/r2m1_bench.err; tail -c 400 gpurun_out/r2m1_bench.err
 python - <<'PY'
 import json
-d=json.loads(open('gpurun_out/r2l_bench.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/r2m1_bench.json').read().strip().splitlines()[-1])
 print('C5', round(d['ms_per_step'],4), 'upass frac', round(d['roofline']['frac'],3), 'item frac', round(d['roofline']['item_pass']['frac'],3), 'step frac', round(d['roofline']['step']['frac'],3), 'e2e', round(d['e2e']['ms_per_step'],3), 'cluster', round(d['cluster']['value']/1e9,3), round(d['cluster']['roofline']['frac'],3), d['cluster']['ms_min_max'])
 print(' phases', {k:round(x,4) for k,x in d['roofline']['phase_ms'].items() if x>0.015})
 print(' dense', round(d['dense_adam']['ms_per_step'],4), round(d['dense_adam']['roofline_frac'],3))
