@@ -2,19 +2,19 @@
 // long segments, touched-row bitmap.  Replaces the duplicate handling of ATen's
 // embedding_dense_backward (autograd of the reference's models.py:449-455).
 //
-// The sort itself is a library call (cub::DeviceRadixSort, LSD => stable, so `perm` is bit-equal to
-// torch.sort(ids, stable=True)); the plan depends only on the (fixed) batch slicing of
-// utils.py:12-19 and is built once per batch by the trainer, outside the per-step hot loop.
-#include <cub/cub.cuh>
-
+// The sort and the prefix sums are hand-written (sort.cuh: stable LSD radix sort over the bits a row id can have,
+// reduce-then-scan prefix sums; no library call), so `perm` is bit-equal to torch.sort(ids, stable=True).  The plan
+// depends only on the (fixed) batch slicing of utils.py:12-19 and is built once per batch by the trainer, outside the
+// per-step hot loop (the e2e path builds it on a loader stream, one step ahead).
 #include "common.cuh"
+#include "sort.cuh"
 
 namespace invpref {
 
 namespace {
 
 __global__ void prep_keys_kernel(const int64_t* __restrict__ ids, int64_t B, int64_t rows, int32_t* __restrict__ keys,
-                                 int32_t* __restrict__ vals, int32_t* __restrict__ counters) {
+                                 int32_t* __restrict__ counters) {
     int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n == 0) { counters[0] = 0; counters[1] = 0; }
     if (n >= B) return;
@@ -24,7 +24,6 @@ __global__ void prep_keys_kernel(const int64_t* __restrict__ ids, int64_t B, int
         id = id < 0 ? 0 : rows - 1;
     }
     keys[n] = (int32_t)id;
-    vals[n] = (int32_t)n;
 }
 
 // invpref_check_ids: bit 0 / 1 / 2 of *flag = some user / item / env id outside its table
@@ -42,25 +41,34 @@ __global__ void __launch_bounds__(256) check_ids_kernel(const int64_t* __restric
     if (bad != 0 && (threadIdx.x & 31) == 0) atomicOr(flag, bad);
 }
 
-__global__ void flag_heads_kernel(const int32_t* __restrict__ sorted, int64_t B, int32_t* __restrict__ flag) {
-    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= B) return;
-    flag[k] = (k == 0 || sorted[k] != sorted[k - 1]) ? 1 : 0;
-}
-
 __global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const int32_t* __restrict__ segid,
                                       const int32_t* __restrict__ perm, const int64_t* __restrict__ other_ids,
                                       int64_t other_rows, int64_t B, PlanSide p) {
-    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k >= B) return;
-    int32_t key = sorted[k];
-    int32_t s = segid[k] - 1;
-    bool head = (k == 0) || (sorted[k - 1] != key);
+    const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool in = k < B;
+    const int lane = threadIdx.x & 31;
+    const int32_t key = in ? sorted[k] : -1;
+    const int32_t s = in ? segid[k] - 1 : 0;
+    const bool head = in && ((k == 0) || (sorted[k - 1] != key));
+    // touched-row bitmap: keys are sorted, so the lanes of one 32-row word are consecutive -> OR them with a
+    // segmented shuffle reduction and issue one atomic per (warp, word) instead of one per segment head
+    {
+        const int word = in ? (key >> 5) : -1;
+        unsigned bits = head ? (1u << (key & 31)) : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned ob = __shfl_down_sync(0xffffffffu, bits, o);
+            const int ow = __shfl_down_sync(0xffffffffu, word, o);
+            if (lane + o < 32 && ow == word) bits |= ob;
+        }
+        const int pw = __shfl_up_sync(0xffffffffu, word, 1);
+        if (in && (lane == 0 || pw != word) && bits != 0u) atomicOr(&p.touched[word], bits);
+    }
+    if (!in) return;
     p.seg_of[perm[k]] = s;
     if (head) {
         p.seg_row[s] = key;
         p.seg_off[s] = (int32_t)k;
-        atomicOr(&p.touched[key >> 5], 1u << (key & 31));
     }
     if (k == B - 1) {
         p.counters[0] = s + 1;
@@ -153,31 +161,24 @@ __global__ void widen_kernel(const int32_t* __restrict__ src, int64_t* __restric
 __global__ void widen_scalar_kernel(const int32_t* src, int64_t* dst) { *dst = *src; }
 
 struct SortTmp {
-    int32_t *keys_in, *keys_out, *vals_in, *scan;
-    void* cub_tmp;
-    size_t cub_bytes;
+    int32_t *keys_in, *keys_out, *keys_tmp, *vals_tmp, *scan;
+    char *sort_scratch, *scan_scratch;
 };
 
-size_t cub_bytes_for(int64_t B, int64_t max_seg_plus1) {
-    size_t a = 0, b = 0, c = 0;
-    int n = (int)B;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr,
-                                    (int32_t*)nullptr, n, 0, 32);
-    cub::DeviceScan::InclusiveSum(nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr, n);
-    cub::DeviceScan::ExclusiveSum(nullptr, c, (const int32_t*)nullptr, (int32_t*)nullptr, (int)max_seg_plus1);
-    size_t m = a > b ? a : b;
-    return (m > c ? m : c) + 256;
+size_t sort_scratch_bytes_for(int64_t B, int64_t max_seg_plus1) {
+    return psort::rs_scratch_bytes(B) + psort::sc_scratch_bytes(B > max_seg_plus1 ? B : max_seg_plus1);
 }
 
-SortTmp carve_sort_tmp(char* base, int64_t B, size_t total) {
+SortTmp carve_sort_tmp(char* base, int64_t B) {
     SortTmp t;
     size_t arr = align_up((size_t)B * 4);
     t.keys_in = (int32_t*)base;
     t.keys_out = (int32_t*)(base + arr);
-    t.vals_in = (int32_t*)(base + 2 * arr);
-    t.scan = (int32_t*)(base + 3 * arr);
-    t.cub_tmp = base + 4 * arr;
-    t.cub_bytes = total - 4 * arr;
+    t.keys_tmp = (int32_t*)(base + 2 * arr);
+    t.vals_tmp = (int32_t*)(base + 3 * arr);
+    t.scan = (int32_t*)(base + 4 * arr);
+    t.sort_scratch = base + 5 * arr;
+    t.scan_scratch = t.sort_scratch + psort::rs_scratch_bytes(B);
     return t;
 }
 
@@ -193,7 +194,7 @@ inline unsigned grid_for(int64_t n, int block = 256) { return (unsigned)((n + bl
 
 size_t sort_tmp_bytes_for(int64_t B, int64_t max_rows) {
     int64_t S = plan_max_seg(B, max_rows);
-    return 4 * align_up((size_t)B * 4) + align_up(cub_bytes_for(B, S + 1));
+    return 5 * align_up((size_t)B * 4) + align_up(sort_scratch_bytes_for(B, S + 1));
 }
 
 // Builds one side of a plan.  All work is enqueued on `stream`; nothing is read back.
@@ -208,22 +209,21 @@ int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_
         return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
     }
     if (tmp_bytes < sort_tmp_bytes_for(B, p.rows)) return INVPREF_ERR_WORKSPACE;
-    SortTmp t = carve_sort_tmp(tmp, B, tmp_bytes);
-    prep_keys_kernel<<<grid_for(B), 256, 0, stream>>>(ids, B, p.rows, t.keys_in, t.vals_in, p.counters);
-    size_t cb = t.cub_bytes;
-    cub::DeviceRadixSort::SortPairs(t.cub_tmp, cb, t.keys_in, t.keys_out, t.vals_in, p.perm, (int)B, 0, bits_for(p.rows),
-                                    stream);
-    flag_heads_kernel<<<grid_for(B), 256, 0, stream>>>(t.keys_out, B, t.scan);
-    cb = t.cub_bytes;
-    cub::DeviceScan::InclusiveSum(t.cub_tmp, cb, t.scan, t.scan, (int)B, stream);
+    SortTmp t = carve_sort_tmp(tmp, B);
+    prep_keys_kernel<<<grid_for(B), 256, 0, stream>>>(ids, B, p.rows, t.keys_in, p.counters);
+    int n_launch = 5;
+    // perm = stable argsort of the row ids
+    n_launch += psort::radix_sort_pairs(t.keys_in, nullptr, t.keys_out, p.perm, t.keys_tmp, t.vals_tmp, B,
+                                        bits_for(p.rows), t.sort_scratch, stream);
+    // scan[k] = 1 + segment of sorted position k (inclusive sum of the head flags)
+    n_launch += psort::prefix_sum<1, true>(t.keys_out, t.scan, B, t.scan_scratch, stream);
     write_segments_kernel<<<grid_for(B), 256, 0, stream>>>(t.keys_out, t.scan, p.perm, other_ids, other_rows, B, p);
     chunk_counts_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B));
-    cb = t.cub_bytes;
-    cub::DeviceScan::ExclusiveSum(t.cub_tmp, cb, p.seg_chunk, p.seg_chunk, (int)(p.max_seg + 1), stream);
+    n_launch += psort::prefix_sum<0, false>(p.seg_chunk, p.seg_chunk, p.max_seg + 1, t.scan_scratch, stream);
     write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p, chunk_for(B),
                                                                                        other_ids != nullptr);
     write_ranges_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B) / 2, (int)plan_ranges(B));
-    count_launch(6 + 6);   // 6 of ours + CUB's (radix passes, 2 scans; approximate)
+    count_launch(n_launch);
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 

@@ -396,7 +396,7 @@ class HotPath:
     def sorted_view(self, users, items, scores):
         """User-sorted view of a dataset for ``cluster_sorted``: (perm int32, users int32, items int32, scores fp32).
         Built once per dataset (ids never change): a stable sort by user id."""
-        perm = torch.sort(users, stable=True).indices
+        perm = build_segments(users, int(self.desc.n_users))[0]            # the library's own stable radix sort
         return (perm.to(torch.int32).contiguous(), users[perm].to(torch.int32).contiguous(),
                 items[perm].to(torch.int32).contiguous(), scores[perm].contiguous())
 
