@@ -280,6 +280,52 @@ def timed_sharded(args, w, rank, world, dev, mode, drv, nb, steps, warmup, want_
                 e2e=e2e, loss=float(loss[5]))
 
 
+def timed_replicated(w, rank, world, dev, drv, nb, steps, warmup):
+    """SURVEY.md 8e "replicated tables": every rank holds all tables, takes a contiguous 1/world chunk of each global
+    batch, exports its partial dense gradients; ONE all-reduce of the flat gradient (+ loss sums) per step, then the
+    same dense Adam everywhere (parallel.ReplicatedTrainer).  Returns (ms per step, launches per step, final loss)."""
+    import bench as B
+    from invpref_kdd_2022_b200 import _lib
+    from invpref_kdd_2022_b200.parallel import ReplicatedTrainer
+    U, I, Bg, batches = B.synth_batches(w, nb)
+    kw = dict(alpha=1.0, use_class_rw=w["crw"], use_rec_rw=w["rrw"], **w["coef"])
+    init = B.make_tables(w, dev, U=U, I=I, seed=123)                  # same seed on every rank: identical replicas
+    tr = ReplicatedTrainer(init, w["implicit"], w["roe"], w["ree"], w["lr"], rank, world)
+    t = lambda a: torch.from_numpy(a).to(dev)
+    prepared = []
+    for (u, i, y, e) in batches:
+        lo, hi = tr.chunk(0, Bg)
+        ge = t(e)
+        gw = tr.hot.stat_envs(ge, tr.hot.env_hist(ge))[1]
+        cu, ci = t(u[lo:hi]), t(i[lo:hi])
+        prepared.append((cu, ci, t(y[lo:hi]), ge[lo:hi].contiguous(), gw[lo:hi].contiguous(), tr.hot.new_plan(cu, ci)))
+
+    def step(s):
+        cu, ci, cy, ce, cw, plan = prepared[s % nb]
+        return drv.run(tr.step_gen(cu, ci, cy, ce, cw, Bg, plan=plan, **kw))
+
+    for s in range(warmup):
+        step(s)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for s in range(warmup, warmup + steps):
+        loss = step(s)
+    ev1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    assert torch.isfinite(loss).all()
+    out = float(ms.item()) / steps, (_lib.launch_count() - l0) / steps, float(loss[5]), Bg, tr.flat.numel()
+    del tr, prepared
+    torch.cuda.empty_cache()
+    return out
+
+
 def run(args, w):
     from invpref_kdd_2022_b200.parallel import DistDriver
     import bench as B
@@ -314,6 +360,36 @@ def run(args, w):
                           "final_loss": r4["loss"]}
         except Exception as ex:      # noqa: BLE001
             legs["c4"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+        try:
+            ms_r, l_r, loss_r, bg_r, p_r = timed_replicated(w4, rank, world, dev, drv, 16, max(args.steps, 32),
+                                                            args.warmup)
+            legs["c4_replicated"] = {"workload": w4["name"], "value": bg_r / (ms_r * 1e-3), "unit": "interactions/s",
+                                     "ms_per_step": ms_r, "global_batch": bg_r, "scaling": "strong",
+                                     "launches_per_step": l_r, "final_loss": loss_r,
+                                     "all_reduce_bytes_per_step": 4 * (p_r + 8),
+                                     "parallelism": f"tables replicated on {world} ranks, contiguous batch chunks, one "
+                                     "NCCL all-reduce of the flat dense gradient per step, dense Adam on every rank "
+                                     "(SURVEY.md 8e, replicated-tables row)"}
+        except Exception as ex:      # noqa: BLE001
+            legs["c4_replicated"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+        # The same config as the reference driver scales it: MIND_InvPref.py:51,206 trains one independent model per
+        # entry of RANDOM_SEED_LIST, one after the other.  Here every rank trains its own seed at the same time
+        # through the single-GPU trainer API (no collective on the path): weak scaling, "replicas only" (DESIGN.md 5).
+        try:
+            dist.barrier()
+            leg = B.config_leg("c4", dev, with_eager=False, seed=17373331 + 90 * rank, quick=True)
+            v = torch.tensor([leg["value"]], device=dev, dtype=torch.float64)
+            vs = [torch.zeros_like(v) for _ in range(world)]
+            dist.all_gather(vs, v)
+            vs = [float(x.item()) for x in vs]
+            legs["c4_replicas"] = {"workload": w4["name"], "value": world * min(vs), "unit": "interactions/s",
+                                   "scaling": "weak", "per_rank_value": vs, "ms_per_step_slowest_rank":
+                                   leg["global_batch"] / min(vs) * 1e3, "launches_per_step": leg["launches_per_step"],
+                                   "parallelism": f"{world} independent seeds, one single-GPU trainer per rank "
+                                   "(train_a_epoch as one CUDA-graph launch), no collective; value = ranks x the slowest "
+                                   "rank's interactions/s"}
+        except Exception as ex:      # noqa: BLE001
+            legs["c4_replicas"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     peak, peak_src = B.measured_peaks()
     if rank == 0:
         Bg, P, D, K, ms = r["Bg"], r["P"], r["D"], r["K"], r["ms"]

@@ -225,6 +225,39 @@ def test_build_segments_bit_exact(B, rows):
         assert np.array_equal(perm.cpu().numpy(), torch.sort(ids, stable=True).indices.numpy())
 
 
+@pytest.mark.parametrize("B,rows,kind", [
+    (4095, 256, "random"), (4097, 257, "random"),            # one key short of / past a 4 096-key sort tile; 8 / 9 key bits
+    (8192, 65536, "random"), (12289, 65537, "random"),       # 16 / 17 key bits: two / three 8-bit passes
+    (300001, (1 << 24) + 5, "random"),                       # 25 key bits: four passes
+    (100000, 1 << 20, "equal"),                              # one segment: every lane of every warp has the same digit
+    (100000, 1 << 20, "sorted"), (100000, 1 << 20, "reversed"),
+    (70000, 3, "random"),                                    # 2 key bits, three long segments
+    (2049, 1 << 30, "high"),                                 # ids near 2^30: top digit only
+])
+def test_radix_sort_edges_bit_exact(B, rows, kind):
+    """The hand-written LSD radix sort + scans of the plan build (csrc/sort.cuh) against torch.sort(stable=True):
+    tile boundaries, every pass count, skewed digits (`perm` bit-equal to the stable sort)."""
+    from invpref_kdd_2022_b200.engine import build_segments
+    gen = torch.Generator(device="cpu").manual_seed(B * 31 + rows)
+    if kind == "random":
+        ids = torch.randint(0, rows, (B,), generator=gen, dtype=torch.int64)
+    elif kind == "equal":
+        ids = torch.full((B,), rows - 7, dtype=torch.int64)
+    elif kind == "sorted":
+        ids = torch.sort(torch.randint(0, rows, (B,), generator=gen, dtype=torch.int64)).values
+    elif kind == "reversed":
+        ids = torch.sort(torch.randint(0, rows, (B,), generator=gen, dtype=torch.int64), descending=True).values
+    else:
+        ids = rows - 1 - torch.randint(0, 1000, (B,), generator=gen, dtype=torch.int64)
+    perm, seg_row, seg_off = build_segments(ids.to(dev()), rows)
+    ref = torch.sort(ids, stable=True)
+    assert torch.equal(perm.cpu(), ref.indices)
+    uq, cnt = torch.unique_consecutive(ref.values, return_counts=True)
+    assert torch.equal(seg_row.cpu(), uq)
+    assert torch.equal((seg_off[1:] - seg_off[:-1]).cpu(), cnt)
+    assert int(seg_off[0]) == 0 and int(seg_off[-1]) == B
+
+
 def _synthetic(U, I, N, K, D, implicit, seed):
     rng = np.random.default_rng(seed)
     u = np.floor(U * rng.random(N) ** 1.5).astype(np.int64)
