@@ -368,6 +368,18 @@ int invpref_owner_adam_push(float* theta_inv, float* theta_env, float* m_inv, fl
                             const int32_t* spos, float* const* caches, const int32_t* npos,
                             const invpref_hyper* hyper, void* stream);
 
+/* invpref_peer_allreduce: in-place SUM all-reduce of buf[0..n) over the ranks + a rank-wide barrier, over peer memory
+ * (two small kernels, no NCCL call: the sharded step of parallel.py needs two such points per step, train.py has no
+ * counterpart -- the reference is single-GPU).  peer_slots / peer_flags: HOST arrays of `world` device pointers to
+ * every rank's slot array (2 * world * n_max floats) and flag array (world uint32, zero-initialised before the first
+ * call on any rank), the caller's own included, mapped into this process.  counter: device uint32 (zero-initialised),
+ * private to the rank, advanced by one per call -- every rank must make the same sequence of calls.  The sum runs
+ * in rank order on every rank (replicas stay bit-identical).  On return (stream order) everything EVERY rank had
+ * enqueued before its call is complete and visible, peer-memory stores included.  n = 0: barrier only.
+ * A peer that does not arrive within a few seconds sets bit 0 of *status (device int32) instead of hanging. */
+int invpref_peer_allreduce(float* buf, int32_t n, int32_t n_max, int32_t world, int32_t rank, float* const* peer_slots,
+                           uint32_t* const* peer_flags, uint32_t* counter, int32_t* status, void* stream);
+
 /* Number of kernels the library has launched in this process (bench.py's gpu_launches). */
 int64_t invpref_launch_count(void);
 

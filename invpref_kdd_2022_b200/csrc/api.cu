@@ -590,6 +590,17 @@ int invpref_owner_adam_push(float* theta_inv, float* theta_env, float* m_inv, fl
                                   stage_env, spos, caches, npos, make_adam(hyper), hyper->dyn, (cudaStream_t)stream);
 }
 
+int invpref_peer_allreduce(float* buf, int32_t n, int32_t n_max, int32_t world, int32_t rank, float* const* peer_slots,
+                           uint32_t* const* peer_flags, uint32_t* counter, int32_t* status, void* stream) {
+    if (world < 1 || world > 16 || rank < 0 || rank >= world || n < 0 || n > n_max || !peer_slots || !peer_flags ||
+        !counter || !status || (n > 0 && !buf))
+        return INVPREF_ERR_BAD_ARG;
+    for (int p = 0; p < world; ++p)
+        if (!peer_flags[p] || (n_max > 0 && !peer_slots[p])) return INVPREF_ERR_BAD_ARG;
+    return launch_peer_allreduce(buf, n, n_max, world, rank, peer_slots, peer_flags, counter, status,
+                                 (cudaStream_t)stream);
+}
+
 int invpref_backward(const invpref_desc* desc, const invpref_params* params, const invpref_batch* batch, double alpha,
                      const float* g_s_inv, const float* g_s_env, const float* g_logp, const void* plan,
                      invpref_params* grads, void* ws, size_t ws_bytes, void* stream) {

@@ -223,7 +223,7 @@ struct Workspace {
     float* chunk_part_u; // [max_chunks * 2 * D]
     float* chunk_part_i; // [max_chunks * 2 * D]
     char* plan;          // scratch plan (when the caller passes none)
-    char* sort_tmp;      // keys / values / flags / scan temp + CUB temp storage
+    char* sort_tmp;      // keys / ping-pong arrays / segment ids + tile counts of the radix sort and scans (sort.cuh)
     size_t sort_tmp_bytes;
     size_t plan_bytes;
 };

@@ -242,6 +242,72 @@ __global__ void __launch_bounds__(256) owner_adam_push_kernel(float* __restrict_
     }
 }
 
+// ---- all-reduce of a few KB + barrier over peer memory (invpref_peer_allreduce) -------------------------------
+// The sharded step needs two rank-wide synchronisation points per step, one of which carries the gradients of the
+// replicated tensors (E, W, b: 2KD + K + 6 floats).  Instead of an NCCL all-reduce per point, every rank
+//   post   : stores its vector into slot [parity][rank] of EVERY rank's mapped slot array (posted NVLink writes),
+//            fences at system scope and release-stores the sequence number into flag [rank] of every rank;
+//   reduce : acquire-spins on its OWN flags until all ranks have posted this sequence number, then sums the slots in
+//            rank order -- the same order on every rank, so the replicas stay bit-identical.
+// Ordering: everything the stream ran before `post` (the item pass and its pushes into peer staging, the owner kernel
+// and its row pushes) happens-before the release store, hence before any peer's kernels that follow its `reduce`.
+// The sequence number lives in device memory (`ctr`, advanced by `reduce`), so a captured CUDA graph replays it
+// correctly.  Slots are double-buffered by sequence parity: a rank can be at most one synchronisation point ahead of a
+// peer (to post point k+2 it must have seen the peer's post of k+1, which the peer issues after its reduce of k).
+// The spin is bounded (~seconds); on expiry bit 0 of *status is set and the kernel goes on (the caller raises).
+struct PeerSync {
+    float* slots[P2P_MAX_WORLD];       // rank p's slot array   [2][world][n_max]
+    unsigned* flags[P2P_MAX_WORLD];    // rank p's flag array   [world]
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) peer_post_kernel(const float* __restrict__ src, int n, int n_max, int world,
+                                                        int rank, PeerSync ps, const unsigned* __restrict__ ctr) {
+    const unsigned seq = *ctr + 1u;
+    const int64_t off = ((int64_t)(seq & 1u) * world + rank) * n_max;
+    for (int idx = threadIdx.x; idx < world * n; idx += blockDim.x) {
+        const int p = idx / n, i = idx - p * n;
+        ps.slots[p][off + i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) st_release_sys(ps.flags[threadIdx.x] + rank, seq);
+}
+
+__global__ void __launch_bounds__(256) peer_reduce_kernel(float* __restrict__ dst, int n, int n_max, int world,
+                                                          const float* my_slots, const unsigned* my_flags,
+                                                          unsigned* ctr, int32_t* status, unsigned spin_limit) {
+    const unsigned seq = *ctr + 1u;
+    if ((int)threadIdx.x < world) {
+        unsigned it = 0;
+        while ((int)(ld_acquire_sys(my_flags + threadIdx.x) - seq) < 0) {
+            if (++it > spin_limit) { atomicOr(status, 1); break; }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    const float* base = my_slots + (int64_t)(seq & 1u) * world * n_max;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        float s = 0.f;
+        for (int p = 0; p < world; ++p) {
+            float v;
+            ldv_sys<1>(base + (int64_t)p * n_max + i, &v);      // written by a peer: never from this SM's L1
+            s += v;
+        }
+        dst[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *ctr = seq;
+}
+
 inline int grid_1d(int64_t work, int max_blocks = 148 * 16) {
     int64_t need = (work + 255) / 256;
     if (need < 1) need = 1;
@@ -328,6 +394,22 @@ int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* 
 #undef PUSH_W
 #undef PUSH_CALL
     count_launch();
+    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
+}
+
+int launch_peer_allreduce(float* buf, int n, int n_max, int world, int rank, float* const* slots_host,
+                          uint32_t* const* flags_host, uint32_t* ctr, int32_t* status, cudaStream_t stream) {
+    if (world < 1 || world > P2P_MAX_WORLD || rank < 0 || rank >= world || n < 0 || n > n_max) return INVPREF_ERR_BAD_ARG;
+    PeerSync ps = {};
+    for (int p = 0; p < world; ++p) {
+        ps.slots[p] = slots_host[p];
+        ps.flags[p] = flags_host[p];
+    }
+    peer_post_kernel<<<1, 256, 0, stream>>>(buf, n, n_max, world, rank, ps, ctr);
+    // 200 ns sleeps: ~25 M iterations = 5 s before a missing peer is reported instead of waited for
+    peer_reduce_kernel<<<1, 256, 0, stream>>>(buf, n, n_max, world, ps.slots[rank], ps.flags[rank], ctr, status,
+                                              25u * 1000u * 1000u);
+    count_launch(2);
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 

@@ -156,6 +156,9 @@ int launch_owner_adam_push(float* th0, float* th1, float* m0, float* m1, float* 
                            float* const* caches_host, const int32_t* npos, const AdamScalars& s,
                            const invpref_dyn* dyn, cudaStream_t stream);
 
+int launch_peer_allreduce(float* buf, int n, int n_max, int world, int rank, float* const* slots_host,
+                          uint32_t* const* flags_host, uint32_t* ctr, int32_t* status, cudaStream_t stream);
+
 // ---- eval.cu ---------------------------------------------------------------------------------
 int launch_mask_scores(float* rating, int64_t b, int64_t n_items, const int64_t* users, const int64_t* off,
                        const int64_t* items, float value, int add, cudaStream_t stream);

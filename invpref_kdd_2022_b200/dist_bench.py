@@ -30,7 +30,7 @@ def _exchange_mode():
     return "nccl" if os.environ.get("INVPREF_P2P", "1") == "0" else "push"
 
 
-def make_sharded(w, U, I, Bg, rank, world, dev, mode, init=None, lazy=True):
+def make_sharded(w, U, I, Bg, rank, world, dev, mode, init=None, lazy=True, sync=None):
     """A ShardedTrainer wired for `mode`; falls back (all ranks together) to the NCCL exchange if symmetric memory
     is unavailable.  Returns (trainer, note)."""
     from invpref_kdd_2022_b200.parallel import ShardedTrainer, SymmetricItemStorage
@@ -38,16 +38,28 @@ def make_sharded(w, U, I, Bg, rank, world, dev, mode, init=None, lazy=True):
     cache_rows = min(I, Bg // world * 2 + 1024)
     stage_rows = min(2 * cache_rows, (I + world - 1) // world * world) if mode == "push" else 0
     store, why = None, "disabled (INVPREF_EXCHANGE=nccl)"
+    peer_sync = os.environ.get("INVPREF_SYNC", "peer").lower() != "nccl" if sync is None else bool(sync)
+    n_small = 2 * K * D + K + 6
     if mode != "nccl":
         try:
-            store = SymmetricItemStorage(I, D, world, cache_rows, dev, dist.group.WORLD, stage_rows=stage_rows)
+            store = SymmetricItemStorage(I, D, world, cache_rows, dev, dist.group.WORLD, stage_rows=stage_rows,
+                                         sync_floats=n_small if peer_sync else 0)
             why = ""
         except Exception as ex:      # noqa: BLE001 -- any failure means "use NCCL"
             store, why = None, f"{type(ex).__name__}: {ex}"[:200]
-    ok = torch.tensor([1 if (store is not None or mode == "nccl") else 0], device=dev)
+    sync_store = None
+    if mode == "nccl" and sync:      # NCCL row / gradient exchange, but the step's all-reduce + barriers over peer memory
+        try:                         # (parity_check: isolates the exchange path, same summation order of E / W / b)
+            sync_store = SymmetricItemStorage(world, D, world, 1, dev, dist.group.WORLD, sync_floats=n_small)
+        except Exception:            # noqa: BLE001
+            sync_store = None
+    ok = torch.tensor([1 if (store is not None or mode == "nccl") else 0,
+                       1 if (sync_store is not None or not (mode == "nccl" and sync)) else 0], device=dev)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    if int(ok.item()) == 0:
+    if int(ok[0].item()) == 0:
         store, mode = None, "nccl"
+    if int(ok[1].item()) == 0:
+        sync_store = None
     tr = ShardedTrainer(U, I, K, D, w["implicit"], w["roe"], w["ree"], w["lr"], rank, world, dev,
                         cache_rows=cache_rows, alloc=store.alloc if store is not None else None, init=init, lazy=lazy,
                         stage_rows=stage_rows if store is not None else 0)
@@ -59,9 +71,16 @@ def make_sharded(w, U, I, Bg, rank, world, dev, mode, init=None, lazy=True):
                            [store.ptrs(f"cache{t}") for t in range(2)])
             note = "peer memory (torch symmetric memory): item pass pushes partial gradients into the owners' " \
                    "staging, owners push updated rows into the requesters' next-batch caches (posted NVLink writes)"
+        if peer_sync:
+            tr.enable_peer_sync(store.ptrs("sync_slots"), store.ptrs("sync_flags"), store.sync_floats)
+            note += "; E/W/b gradient all-reduce and both step barriers over peer memory too (invpref_peer_allreduce: " \
+                    "no NCCL call in the step)"
         tr._store = store
     else:
         note = "NCCL all-to-all (" + (why or "a peer could not map symmetric memory") + ")"
+        if sync_store is not None:
+            tr.enable_peer_sync(sync_store.ptrs("sync_slots"), sync_store.ptrs("sync_flags"), sync_store.sync_floats)
+            tr._store = sync_store
     torch.cuda.synchronize()
     dist.barrier()                       # every shard initialised before anyone touches a peer's memory
     return tr, note, mode
@@ -95,8 +114,13 @@ def parity_check(rank, world, dev, mode, drv):
     for k, sc in (("Uinv", 10.0), ("Iinv", 10.0), ("Uenv", 30.0), ("Ienv", 30.0), ("E", 50.0), ("W", 3.0)):
         init[k] *= sc
     res = {}
+    used_sync = None
     for m in dict.fromkeys((mode, "nccl")):
-        tr, _, got = make_sharded(w, U, I, Bg, rank, world, dev, m, init=init)
+        # the NCCL-exchange twin uses the same synchronisation primitive as the main leg: what is compared bit for
+        # bit is the item exchange (rows + partial gradients), not the summation order of an NCCL all-reduce
+        tr, _, got = make_sharded(w, U, I, Bg, rank, world, dev, m, init=init, sync=used_sync)
+        if used_sync is None:
+            used_sync = tr.sync is not None
         prep = prepare_all(tr, drv, batches, dev)
         losses = []
         for s in range(steps):
@@ -105,6 +129,7 @@ def parity_check(rank, world, dev, mode, drv):
             losses.append(drv.run(tr.step_gen(sb, le, sw, next_sb=nxt, **kw)).clone())
         tr.flush()
         torch.cuda.synchronize()
+        tr.check_sync()
         dist.barrier()
         res[m] = (torch.stack(losses), {k: v.clone() for k, v in tr.local_tables().items()}, got)
         del tr, prep
@@ -151,7 +176,8 @@ def parity_check(rank, world, dev, mode, drv):
                              "why": "the item partials of a row are summed per rank, then across ranks in rank order: "
                                     "a different (fixed) order than the single-GPU sorted order"},
                "pass": bool(lerr <= 1e-5 and max(terr.values()) <= 2e-4),
-               "peer_memory_bitwise_equals_nccl": bool(int(flag.item()))}
+               "peer_memory_bitwise_equals_nccl": bool(int(flag.item())),
+               "sync": "invpref_peer_allreduce (both legs)" if used_sync else "NCCL all-reduce"}
         del hp
     del res, gathered
     torch.cuda.empty_cache()
@@ -222,16 +248,18 @@ def timed_sharded(args, w, rank, world, dev, mode, drv, nb, steps, warmup, want_
         # e2e at N GPUs: per step every rank copies its share's ids (local user rows, item cache slots), scores, envs
         # and sample weights from pinned host memory and rebuilds the sort-segment plan of its share on a loader
         # stream (as the 1-GPU e2e leg does); the item ROUTE (which rows come from which owner) is static per batch
-        # and stays resident.  The six losses go back to the host every step, host-synchronised.
+        # and stays resident.  The six losses go back to the host every step and are read one step later.
         host = [tuple(x.cpu().pin_memory() for x in (sb.users, sb.route.slots, sb.scores, le, sw))
                 for sb, le, sw in prepared[:min(nb, 4)]]
         nh = len(host)
         loader = torch.cuda.Stream(device=dev)
         plan_bufs = [torch.empty(tr.hot.plan_bytes(max(int(sb.users.numel()) for sb, _, _ in prepared) + 1),
                                  dtype=torch.uint8, device=dev) for _ in range(2)]
-        h_loss = torch.empty(6).pin_memory()
-        e2e_steps = max(3, min(steps, 10))
+        h_loss = torch.empty((2, 6)).pin_memory()
+        read_back = [torch.cuda.Event(), torch.cuda.Event()]
+        e2e_steps = max(3, min(steps, 32))
         ready = [torch.cuda.Event(), torch.cuda.Event()]
+        seen = []
 
         def issue(s):
             j = s % nh
@@ -243,26 +271,33 @@ def timed_sharded(args, w, rank, world, dev, mode, drv, nb, steps, warmup, want_
                     sb.plan = tr.hot.new_plan(sb.users, sb.route.slots, out=plan_bufs[s % 2])
                 ready[s % 2].record(loader)
 
-        def e2e_step(s, last):
+        def e2e_step(s, first, last):
             if not last:
                 issue(s + 1)
             torch.cuda.current_stream().wait_event(ready[s % 2])
             sb, le, sw = prepared[s % nh]
             out = drv.run(tr.step_gen(sb, le, sw, next_sb=prepared[(s + 1) % nh][0], **kw))
             loader.wait_stream(torch.cuda.current_stream())
-            h_loss.copy_(out, non_blocking=True)
-            torch.cuda.synchronize()
+            h_loss[s % 2].copy_(out, non_blocking=True)      # this step's six losses -> pinned host memory
+            read_back[s % 2].record()
+            if not first:                                     # the host reads step s-1's losses while step s runs (as the
+                read_back[(s - 1) % 2].synchronize()          # 1-GPU leg does): every step's result is read
+                seen.append(float(h_loss[(s - 1) % 2][5]))
 
         issue(0)
-        e2e_step(0, False)
+        e2e_step(0, True, False)
+        torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for s in range(1, e2e_steps + 1):
-            e2e_step(s, s == e2e_steps)
+            e2e_step(s, s == 1, s == e2e_steps)
+        read_back[e2e_steps % 2].synchronize()
+        seen.append(float(h_loss[e2e_steps % 2][5]))
         tr.flush()
         torch.cuda.synchronize()
         dist.barrier()
+        assert len(seen) == e2e_steps and all(np.isfinite(seen))
         e2e_ms = torch.tensor([(time.perf_counter() - t0) / e2e_steps * 1e3], device=dev)
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         h2d = torch.tensor([sum(t_.numel() * t_.element_size() for t_ in host[0])], device=dev, dtype=torch.float64)
@@ -271,7 +306,8 @@ def timed_sharded(args, w, rank, world, dev, mode, drv, nb, steps, warmup, want_
                "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 24 * world, "steps": e2e_steps,
                "note": "per step every rank copies its share (local user rows, item cache slots, scores, envs, sample "
                        "weights) from pinned host memory and rebuilds its sort-segment plan on a loader stream under "
-                       "the previous step, runs the step, reads the six losses back, host-synchronised.  Unlike the "
+                       "the previous step, runs the step, copies the six losses D2H; the host reads them one step later (while the "
+                       "next step runs), as in the 1-GPU leg.  Unlike the "
                        "1-GPU leg the interactions arrive already routed to their user's owner and the item route "
                        "(which rows from which owner) is resident: building it needs a collective per batch"}
     del tr, prepared
@@ -326,6 +362,63 @@ def timed_replicated(w, rank, world, dev, drv, nb, steps, warmup):
     return out
 
 
+def config_leg_sharded(name, rank, world, dev, mode):
+    """A dataset-scale config through the PUBLIC distributed trainer API (dist_train.Sharded*TrainManager), like
+    bench.config_leg does on one GPU: one synthetic epoch of the config's shape, wall clock over whole
+    train_a_epoch() calls (per-epoch loss read-back included), max over ranks.  With the push exchange every epoch
+    after the first is one CUDA-graph launch per rank (no NCCL call inside)."""
+    import bench as B
+    from invpref_kdd_2022_b200 import _lib
+    from invpref_kdd_2022_b200.dataloader import synthetic_interactions
+    from invpref_kdd_2022_b200.dist_train import ShardedExplicitTrainManager, ShardedImplicitTrainManager
+    w = B.WORKLOADS[name]
+    U, I, N, Bg, K, D = w["U"], w["I"], w["N"], w["B"], w["K"], w["D"]
+    data = synthetic_interactions(U, I, N, w["implicit"])
+    torch.manual_seed(17373331)
+    np.random.seed(17373331)
+    T = ShardedImplicitTrainManager if w["implicit"] else ShardedExplicitTrainManager
+    c = w["coef"]
+    tm = T(U, I, K, D, torch.LongTensor(data), dev, batch_size=Bg, epochs=1, cluster_interval=1, evaluate_interval=1,
+           lr=w["lr"], invariant_coe=c["c_inv"], env_aware_coe=c["c_ea"], env_coe=c["c_env"], L2_coe=c["c_L2"],
+           L1_coe=c["c_L1"], alpha=None, use_class_re_weight=w["crw"], use_recommend_re_weight=w["rrw"],
+           reg_only_embed=w["roe"], reg_env_embed=w["ree"], exchange=mode)
+    tm.stat_envs()
+    for _ in range(3):                       # first epoch builds routes and plans, second captures the graph
+        ld = tm.train_a_epoch()
+    epochs = max(4, 60 // max(1, tm.batch_num))
+    torch.cuda.synchronize()
+    dist.barrier()
+    l0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(epochs):
+        ld = tm.train_a_epoch()
+    torch.cuda.synchronize()
+    wall = torch.tensor([(time.perf_counter() - t0) / epochs * 1e3], device=dev)
+    dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+    wall = float(wall.item())
+    assert np.isfinite(ld["loss"])
+    tc0 = time.perf_counter()
+    for _ in range(2):
+        tm.cluster()
+        tm.stat_envs()
+    torch.cuda.synchronize()
+    cl = torch.tensor([(time.perf_counter() - tc0) / 2 * 1e3], device=dev)
+    dist.all_reduce(cl, op=dist.ReduceOp.MAX)
+    graph = bool(tm._graph is not None and len(tm._graph.handles) > 0)
+    leg = {"workload": w["name"], "interactions_per_epoch": N, "steps_per_epoch": tm.batch_num, "global_batch": Bg,
+           "value": N / (wall * 1e-3), "unit": "interactions/s", "ms_per_step": wall / tm.batch_num,
+           "ms_per_epoch": wall, "scaling": "strong", "final_loss": float(ld["loss"]),
+           "launches_per_step": (_lib.launch_count() - l0) / (epochs * tm.batch_num),
+           "cuda_graph_epochs": graph, "peer_sync": tm.trainer.sync is not None, "exchange": tm.exchange,
+           "timing": "wall clock over %d train_a_epoch() calls of the distributed trainer incl. the per-epoch loss "
+                     "read-back, max over ranks" % epochs,
+           "cluster": {"value": N / (float(cl.item()) * 1e-3), "unit": "samples/s", "ms": float(cl.item())},
+           "parallelism": f"row-sharded over {world} ranks through dist_train.Sharded*TrainManager"}
+    del tm
+    torch.cuda.empty_cache()
+    return leg
+
+
 def run(args, w):
     from invpref_kdd_2022_b200.parallel import DistDriver
     import bench as B
@@ -360,6 +453,10 @@ def run(args, w):
                           "final_loss": r4["loss"]}
         except Exception as ex:      # noqa: BLE001
             legs["c4"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+        try:
+            legs["c4_trainer"] = config_leg_sharded("c4", rank, world, dev, r["mode"])
+        except Exception as ex:      # noqa: BLE001
+            legs["c4_trainer"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
         try:
             ms_r, l_r, loss_r, bg_r, p_r = timed_replicated(w4, rank, world, dev, drv, 16, max(args.steps, 32),
                                                             args.warmup)

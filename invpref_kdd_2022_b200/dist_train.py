@@ -43,12 +43,15 @@ class _ShardedInvPrefTrainManager:
                  use_recommend_re_weight: bool = True, reg_only_embed: bool = False, reg_env_embed: bool = True,
                  evaluator=None, group=None, local_rows: torch.Tensor = None, total_rows: int = None,
                  init: dict = None, seed: int = 17373331, exchange: str = "push", lazy_adam: bool = True,
-                 driver=None, rank: int = None, world: int = None):
+                 driver=None, rank: int = None, world: int = None, peer_sync: bool = True, use_graph: bool = True):
         """Model arguments (``user_num .. factor_num``, ``reg_*``) are those of ``InvPrefExplicit/Implicit``
         (models.py:415-418): the sharded tables live in this object, not in an ``nn.Module``.  ``training_data``:
         int64 ``[n, 3]`` (user, item, score) -- the whole training set, or, with ``local_rows`` (their global row
         numbers, ascending) and ``total_rows``, only the rows whose user this rank owns.  ``init``: optional full
         tables (tests).  ``exchange``: "push" | "pull" (peer memory, needs torch symmetric memory) | "nccl".
+        ``peer_sync``: with a peer-memory exchange, also run the step's small all-reduce and barriers over peer
+        memory (``invpref_peer_allreduce``) instead of NCCL.  ``use_graph``: with push + peer_sync (a step is then
+        nothing but library kernels) every epoch after the first is replayed as ONE CUDA-graph launch per rank.
         ``driver`` / ``rank`` / ``world``: for simulated ranks (tests); default: torch.distributed."""
         if driver is None and world == 1:
             from .parallel import LocalDriver
@@ -112,7 +115,8 @@ class _ShardedInvPrefTrainManager:
             import torch.distributed as dist
             self._store = SymmetricItemStorage(item_num, factor_num, self.world, cache_rows, device,
                                                group if group is not None else dist.group.WORLD,
-                                               stage_rows=stage_rows)
+                                               stage_rows=stage_rows,
+                                               sync_floats=(2 * env_num * factor_num + env_num + 6) if peer_sync else 0)
             alloc = self._store.alloc
         self.trainer = ShardedTrainer(user_num, item_num, env_num, factor_num, self.implicit, reg_only_embed,
                                       reg_env_embed, lr, self.rank, self.world, device, cache_rows=cache_rows, init=init,
@@ -123,6 +127,8 @@ class _ShardedInvPrefTrainManager:
             if exchange == "push":
                 self.trainer.enable_push([[st.ptrs(f"stage{par}{t}") for t in range(2)] for par in range(2)],
                                          [st.ptrs(f"cache{t}") for t in range(2)])
+            if peer_sync:
+                self.trainer.enable_peer_sync(st.ptrs("sync_slots"), st.ptrs("sync_flags"), st.sync_floats)
             import torch.distributed as dist
             torch.cuda.synchronize()
             dist.barrier(group)
@@ -134,6 +140,9 @@ class _ShardedInvPrefTrainManager:
         if int(bad.item()):
             raise IndexError("index out of range in self: item id outside its embedding table")
         self._batches = None
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._loss_rows = None
 
     # ---- setup: this rank's share of every global batch, routed and planned once (the slicing is fixed) ----
     def _prepare(self):
@@ -163,25 +172,89 @@ class _ShardedInvPrefTrainManager:
         return t
 
     # ---- train ------------------------------------------------------------------------------------------
+    def _alpha_at(self, b: int) -> float:
+        if self.update_alpha:                                                     # train.py:891-894
+            p = float(b + (self.epoch_cnt + 1) * self.batch_num) / float((self.epoch_cnt + 1) * self.batch_num)
+            self.alpha = 2. / (1. + np.exp(-10. * p)) - 1.
+        return self.alpha
+
+    def _loss_kw(self):
+        return dict(c_inv=self.invariant_coe, c_ea=self.env_aware_coe, c_env=self.env_coe, c_L2=self.L2_coe,
+                    c_L1=self.L1_coe, use_class_rw=self.use_class_re_weight, use_rec_rw=self.use_recommend_re_weight)
+
+    def _graph_epoch(self) -> bool:
+        """One epoch as ONE CUDA-graph launch per rank (the sharded twin of train.py's ``_graph_epoch``).  Applies to
+        the push exchange with peer-memory synchronisation, where a step is a fixed sequence of library kernels on
+        fixed buffers -- item pass with NVLink pushes, ``invpref_peer_allreduce``, owner reduce + Adam + row push,
+        Adam on E / W / b, ``invpref_peer_allreduce`` -- and what changes between epochs (Adam's bias corrections,
+        alpha, the step number, the synchronisation sequence number) is read from device memory."""
+        tr, n = self.trainer, self.batch_num
+        if not (self.use_graph and self.epoch_cnt >= 1 and tr.sync is not None and tr.push is not None and tr.lazy
+                and tr.hot.m is not None and n <= 256 and all(sb.users.numel() > 0 for sb in self._batches)):
+            return False
+        from .engine import StepGraph
+        if self._graph is None:
+            self._graph = StepGraph(tr.hot, n)
+            self._g_envs = torch.empty_like(self.envs)
+            self._g_sw = torch.empty_like(self.sample_weights)
+        g = self._graph
+        tr.hot.reserve_steps(n)
+        g.valid()
+        main = torch.cuda.current_stream()
+        g.stream.wait_stream(main)
+        with torch.cuda.stream(g.stream):
+            self._g_envs.copy_(self.envs)              # cluster() / stat_envs() re-bind these: stable copies
+            self._g_sw.copy_(self.sample_weights)
+            for b in range(n):
+                g.fill(b, tr.hot.step + 1 + b, self._alpha_at(b))
+            g.upload()
+            key = tr.push["step"] & 1                  # which staging buffer the first step of the epoch uses
+            if key not in g.handles:
+                saved = (tr.hot.host_state(), tr.push["step"], tr._fetched)
+                kw = self._loss_kw()
+
+                def issue():
+                    for b, sb in enumerate(self._batches):
+                        lo, hi = self._lo[b], self._lo[b + 1]
+                        nxt = self._batches[b + 1] if b + 1 < n else None
+                        loss = self.drv.run(tr.step_gen(sb, self._g_envs[lo:hi], self._g_sw[lo:hi], next_sb=nxt,
+                                                        alpha=0.0, dyn=g.record_ptr(b), **kw))
+                        self._loss_rows[b].copy_(loss)
+                    tr.hot.flush(dyn=g.record_ptr(n - 1))
+
+                try:
+                    g.capture(key, issue)
+                finally:                               # capture records, it does not run: undo the host bookkeeping
+                    tr.hot.restore_host_state(saved[0])
+                    tr.push["step"], tr._fetched = saved[1], saved[2]
+            g.launch(key)
+            tr.hot.step += n                           # (no buffer swaps here: user tables in place, item rows exported)
+            tr.hot._dirty = False                      # the captured epoch ends with the flush
+            tr.push["step"] += n
+            tr._fetched = None
+        main.wait_stream(g.stream)
+        return True
+
     def train_a_epoch(self) -> dict:
         """train.py:881-910 on the global batches; returns the same mean loss dictionary on every rank."""
         self._prepare()
         tr = self.trainer
-        rows = torch.zeros((self.batch_num, 6), dtype=torch.float32, device=self.device)
-        kw = dict(c_inv=self.invariant_coe, c_ea=self.env_aware_coe, c_env=self.env_coe, c_L2=self.L2_coe,
-                  c_L1=self.L1_coe, use_class_rw=self.use_class_re_weight, use_rec_rw=self.use_recommend_re_weight)
-        for b, sb in enumerate(self._batches):
-            if self.update_alpha:                                                 # train.py:891-894
-                p = float(b + (self.epoch_cnt + 1) * self.batch_num) / float((self.epoch_cnt + 1) * self.batch_num)
-                self.alpha = 2. / (1. + np.exp(-10. * p)) - 1.
-            lo, hi = self._lo[b], self._lo[b + 1]
-            nxt = self._batches[b + 1] if b + 1 < self.batch_num else None
-            loss = self.drv.run(tr.step_gen(sb, self.envs[lo:hi], self.sample_weights[lo:hi], next_sb=nxt,
-                                            alpha=self.alpha, **kw))
-            rows[b].copy_(loss)
+        if self._loss_rows is None:
+            self._loss_rows = torch.zeros((self.batch_num, 6), dtype=torch.float32, device=self.device)
+        rows = self._loss_rows
+        if not self._graph_epoch():
+            kw = self._loss_kw()
+            for b, sb in enumerate(self._batches):
+                alpha = self._alpha_at(b)
+                lo, hi = self._lo[b], self._lo[b + 1]
+                nxt = self._batches[b + 1] if b + 1 < self.batch_num else None
+                loss = self.drv.run(tr.step_gen(sb, self.envs[lo:hi], self.sample_weights[lo:hi], next_sb=nxt,
+                                                alpha=alpha, **kw))
+                rows[b].copy_(loss)
+            tr.flush()
         self.epoch_cnt += 1
-        tr.flush()
         vals = rows.cpu().tolist()
+        tr.check_sync()
         return merge_dict([dict(zip(LOSS_KEYS, r)) for r in vals], _mean_merge_dict_func)
 
     # ---- EM re-assignment ---------------------------------------------------------------------------------

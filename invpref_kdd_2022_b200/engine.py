@@ -172,10 +172,11 @@ class HotPath:
                 self.shadow[k] = self.params[k].clone()
                 self.generation += 1
 
-    def adam_dense(self, theta, m, v, grad, step=None):
-        """``invpref_adam_dense``: in-place Adam on flat fp32 tensors with a materialised gradient."""
+    def adam_dense(self, theta, m, v, grad, step=None, dyn: Optional[int] = None):
+        """``invpref_adam_dense``: in-place Adam on flat fp32 tensors with a materialised gradient (``dyn``: device
+        address of the step's ``invpref_dyn`` record, CUDA-graph capture)."""
         hyper = _lib.Hyper(0, 0, 0, 0, 0, 0, self.lr, self.betas[0], self.betas[1], self.eps,
-                           int(step if step is not None else self.step), 0, 0, 0, 0, 0)
+                           int(step if step is not None else self.step), 0, 0, 0, 0, 0, dyn)
         _lib.check(self.lib.invpref_adam_dense(_lib.ptr(theta, torch.float32), _lib.ptr(m, torch.float32),
                                                _lib.ptr(v, torch.float32), _lib.ptr(grad, torch.float32),
                                                theta.numel(), C.byref(hyper), _lib.stream_ptr()), "adam_dense")

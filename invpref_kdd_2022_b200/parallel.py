@@ -297,12 +297,17 @@ class SymmetricItemStorage:
     buffer [Iinv | Ienv | gcache0 | gcache1] with the same layout on every rank, so that a peer's table is
     `buffer_ptrs[rank] + offset`.  Raises if symmetric memory is unavailable (callers fall back to NCCL)."""
 
-    def __init__(self, n_items, dim, world, cache_rows, device, group, stage_rows=0):
+    def __init__(self, n_items, dim, world, cache_rows, device, group, stage_rows=0, sync_floats=0):
+        """``sync_floats`` > 0: also the slot / flag arrays of ``invpref_peer_allreduce`` (``ShardedTrainer.
+        enable_peer_sync``) for vectors of up to that many floats."""
         import torch.distributed._symmetric_memory as symm
         rows_max = (n_items + world - 1) // world
         pad = lambda n: (n + 63) // 64 * 64                      # 256-byte aligned sections
         sizes = [("Iinv", pad(rows_max * dim)), ("Ienv", pad(rows_max * dim)),
                  ("gcache0", pad(cache_rows * dim)), ("gcache1", pad(cache_rows * dim))]
+        self.sync_floats = pad(int(sync_floats)) if sync_floats else 0
+        if self.sync_floats:
+            sizes += [("sync_slots", 2 * world * self.sync_floats), ("sync_flags", pad(world))]
         if stage_rows:      # push exchange: peer-written row caches and double-buffered gradient staging
             sizes += [("cache0", pad(cache_rows * dim)), ("cache1", pad(cache_rows * dim))]
             sizes += [(f"stage{par}{t}", pad(stage_rows * dim)) for par in range(2) for t in range(2)]
@@ -424,6 +429,7 @@ class ShardedTrainer:
         self.p2p = None                           # (tables ptr array, grads ptr array) once enable_p2p() ran
         self.push = None                          # push exchange state once enable_push() ran
         self.bar = torch.zeros(1, **f32)          # payload of the barrier all-reduce (peer-memory mode)
+        self.sync = None                          # peer-memory all-reduce / barrier state once enable_peer_sync() ran
 
     def enable_p2p(self, item_inv_ptrs, item_env_ptrs, gcache0_ptrs, gcache1_ptrs):
         """Peer-memory item exchange (NVLink loads instead of NCCL all-to-alls): the arguments are, per rank
@@ -450,6 +456,32 @@ class ShardedTrainer:
             base.append(torch.tensor(flat, dtype=torch.int64, device=self.dev))
         caches = (C.c_void_p * (2 * G))(*[int(x) for t in range(2) for x in cache_ptrs[t]])
         self.push = {"base": base, "caches": caches, "step": 0}
+
+    def enable_peer_sync(self, slot_ptrs, flag_ptrs, n_max):
+        """The two rank-wide synchronisation points of a step (the all-reduce of the E / W / b gradients + loss sums,
+        and the barrier after the owners' row pushes) as ``invpref_peer_allreduce`` over peer memory instead of NCCL
+        all-reduces: ``slot_ptrs[rank]`` / ``flag_ptrs[rank]`` = device address IN THIS PROCESS of rank `rank`'s slot
+        array (2 * world * n_max floats) and flag array (world uint32, zeroed, and a barrier passed since), own rank
+        included.  The sum runs in rank order on every rank.  With it the step issues no NCCL call at all."""
+        G = self.world
+        assert len(slot_ptrs) == len(flag_ptrs) == G and n_max >= self.gsmall.numel()
+        self.sync = {"slots": (C.c_void_p * G)(*[int(x) for x in slot_ptrs]),
+                     "flags": (C.c_void_p * G)(*[int(x) for x in flag_ptrs]), "n_max": int(n_max),
+                     "ctr": torch.zeros(1, dtype=torch.int32, device=self.dev),
+                     "status": torch.zeros(1, dtype=torch.int32, device=self.dev)}
+
+    def _peer_allreduce(self, t):
+        """In-place sum of `t` (or, with None, just the barrier) over the ranks through peer memory."""
+        sy = self.sync
+        _lib.check(self.hot.lib.invpref_peer_allreduce(
+            _lib.ptr(t) if t is not None else None, t.numel() if t is not None else 0, sy["n_max"], self.world,
+            self.rank, sy["slots"], sy["flags"], _lib.ptr(sy["ctr"], torch.int32), _lib.ptr(sy["status"], torch.int32),
+            _lib.stream_ptr()), "peer_allreduce")
+
+    def check_sync(self):
+        """Raises if a peer failed to arrive at a peer-memory synchronisation point (synchronises the device)."""
+        if self.sync is not None and int(self.sync["status"].item()) != 0:
+            raise RuntimeError("invpref_peer_allreduce: a rank did not arrive within the spin limit")
 
     def _mark(self, name):
         if self.phase_events is not None:
@@ -508,9 +540,11 @@ class ShardedTrainer:
             yield ("all_to_all", self.cache[t][:r.n_cache], buf[:ns], r.recv_splits, r.send_splits)
 
     # ---- train step -----------------------------------------------------------------------------------
-    def step_gen(self, sb: ShardedBatch, envs, weights, next_sb: ShardedBatch = None, **kw):
+    def step_gen(self, sb: ShardedBatch, envs, weights, next_sb: ShardedBatch = None, dyn=None, **kw):
         """envs / weights: this rank's slices (aligned with sb.sel).  Returns the loss tensor (global values
-        after the all-reduce).
+        after the all-reduce).  ``dyn``: device address of this step's ``invpref_dyn`` record: every kernel of the step
+        reads Adam's bias corrections, alpha and the step number from it (CUDA-graph capture of an epoch; push
+        exchange with ``enable_peer_sync`` only, where the step issues nothing but library kernels).
 
         Overlap: the dense Adam sweep over the local user rows without a gradient (the largest local kernel,
         pure HBM streaming) runs on a side stream while the main stream exchanges the item gradients over
@@ -534,8 +568,9 @@ class ShardedTrainer:
             if sb.users.numel() > 0:
                 self.hot.train_step(sb.users, r.slots, sb.scores, envs, weights, plan=sb.plan, loss_out=self.loss,
                                     grads_out=self.grads, global_batch=sb.global_batch, flags=self.flags, push=push,
-                                    **kw)
+                                    dyn=dyn, **kw)
             else:   # no interaction routed here: the local rows just fall one more step behind
+                assert dyn is None, "graph capture needs a non-empty share of every batch"
                 self.hot._ensure_state(())
                 self.hot._ensure_lazy()
                 self.hot.step += 1
@@ -562,7 +597,10 @@ class ShardedTrainer:
             # it returns every rank's item pass -- and with it every posted NVLink write -- has completed.  Then ONE
             # kernel per rank reduces its rows from LOCAL memory in rank order, applies Adam and stores the updated
             # rows into the requesters' caches for the next batch.
-            yield ("all_reduce", self.gsmall)
+            if self.sync is not None:
+                self._peer_allreduce(self.gsmall)
+            else:
+                yield ("all_reduce", self.gsmall)
             self._mark("grad_a2a")
             if r.spos is None:
                 r.spos = build_spos_table(r, self.world, self.I_loc)
@@ -572,7 +610,7 @@ class ShardedTrainer:
                     next_sb.route.pos = build_pos_table(next_sb.route, self.world, self.I_loc)
                 npos = next_sb.route.pos
             hyper = _lib.Hyper(0, 0, 0, 0, 0, 0, self.hot.lr, self.hot.betas[0], self.hot.betas[1], self.hot.eps,
-                               int(self.hot.step), 0, 0, 0, 0, 0)
+                               int(self.hot.step), 0, 0, 0, 0, 0, dyn)
             _lib.check(self.hot.lib.invpref_owner_adam_push(
                 _lib.ptr(self.Iinv), _lib.ptr(self.Ienv), _lib.ptr(self.mI[0]), _lib.ptr(self.mI[1]),
                 _lib.ptr(self.vI[0]), _lib.ptr(self.vI[1]), self.I_loc, self.D, self.world,
@@ -582,16 +620,20 @@ class ShardedTrainer:
                 "owner_adam_push")
             self._mark("item_adam")
             n_small = self.small.numel()
-            self.hot.adam_dense(self.small, self.msmall, self.vsmall, self.gsmall[:n_small])
+            self.hot.adam_dense(self.small, self.msmall, self.vsmall, self.gsmall[:n_small], dyn=dyn)
             # Barrier 2: every owner's pushes have landed before anyone's next local step reads its cache.  (The
             # staging buffers need no barrier of their own: they alternate, and barrier 1 of the NEXT step already
             # orders this step's owner kernels before the item pass of the step after it.)
-            yield ("all_reduce", self.bar)
+            if self.sync is not None:
+                self._peer_allreduce(None)
+            else:
+                yield ("all_reduce", self.bar)
             self._mark("small")
             if next_sb is not None:
                 self._fetched = next_sb
             self._mark("prefetch_next")
-            main.wait_stream(self.side)
+            if not self.lazy:                # the side stream carries the dense user sweep only
+                main.wait_stream(self.side)
             self._mark("sweep_wait")
             self.push["step"] += 1
             return self.loss
@@ -599,7 +641,10 @@ class ShardedTrainer:
             # Peer-memory exchange.  Barrier 1 = the all-reduce of the replicated tensors' gradients: when it
             # returns, every rank's item pass has written its partial-gradient cache.  Then ONE kernel per rank
             # pulls the partials of its own rows over NVLink, sums them in rank order and applies Adam.
-            yield ("all_reduce", self.gsmall)
+            if self.sync is not None:
+                self._peer_allreduce(self.gsmall)
+            else:
+                yield ("all_reduce", self.gsmall)
             self._mark("grad_a2a")
             if r.pos is None:
                 r.pos = build_pos_table(r, self.world, self.I_loc)
@@ -614,7 +659,10 @@ class ShardedTrainer:
             self.hot.adam_dense(self.small, self.msmall, self.vsmall, self.gsmall[:n_small])
             # Barrier 2: every owner has updated its rows (and finished reading the gradient caches) before
             # anyone fetches rows for the next batch or overwrites its cache in the next step.
-            yield ("all_reduce", self.bar)
+            if self.sync is not None:
+                self._peer_allreduce(None)
+            else:
+                yield ("all_reduce", self.bar)
             self._mark("small")
             if next_sb is not None:
                 yield from self.fetch_gen(next_sb)
@@ -641,7 +689,10 @@ class ShardedTrainer:
             self.hot.adam_dense(table.view(-1), m.view(-1), v.view(-1), self.gI[t].view(-1))
         self._mark("item_adam")
         # replicated E / W / b: all-reduce of a few KB (gradients + loss partial sums), same Adam on every rank
-        yield ("all_reduce", self.gsmall)
+        if self.sync is not None:
+            self._peer_allreduce(self.gsmall)
+        else:
+            yield ("all_reduce", self.gsmall)
         n_small = self.small.numel()
         self.hot.adam_dense(self.small, self.msmall, self.vsmall, self.gsmall[:n_small])
         self._mark("small")

@@ -62,7 +62,9 @@ def main():
     cnts = tm.stat_envs()
     envs = [None] * world if rank == 0 else None
     dist.gather_object((tm.rows.cpu().numpy(), tm.envs.cpu().numpy()), envs, dst=0)
-    out = {"rank": rank, "exchange": tm.exchange, "ok": True}
+    out = {"rank": rank, "exchange": tm.exchange, "ok": True,
+           "graph_epochs": bool(tm._graph is not None and len(tm._graph.handles) > 0),
+           "peer_sync": tm.trainer.sync is not None}
     if rank == 0:
         class Null:
             def evaluate(self):

@@ -44,6 +44,8 @@ def test_distributed_trainer_matches_single_gpu_on_real_ranks(case, exchange):
     r0 = [o for o in outs if o["rank"] == 0][0]
     assert r0["ok"], r0
     assert r0["exchange"] == exchange
+    if exchange == "push":      # epochs 2 and 3 ran as CUDA-graph replays with the peer-memory all-reduce / barriers
+        assert r0["peer_sync"] and r0["graph_epochs"], r0
     # environments after one re-assignment on the trained tables: only fp32 near-ties may differ (the tables of the
     # two runs differ by ~1e-5: a different, fixed summation order of the item partials)
     assert r0["env_mismatch"] <= 0.01 * r0["N"], r0
