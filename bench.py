@@ -273,6 +273,15 @@ def config_leg(name, dev, with_eager=True, seed=17373331, quick=False):
         tm.stat_envs()
     torch.cuda.synchronize()
     cl_ms = (time.perf_counter() - tc0) / reps * 1e3
+    tm.tie_break_rng = "device"                  # opt-in: tie-break rows from the device generator (not numpy's stream)
+    tm.cluster()
+    torch.cuda.synchronize()
+    tc0 = time.perf_counter()
+    for _ in range(reps):
+        tm.cluster()
+        tm.stat_envs()
+    torch.cuda.synchronize()
+    cl_dev_ms = (time.perf_counter() - tc0) / reps * 1e3
     del tm
     if quick:
         p_ms, p_launch = g_ms, g_launch
@@ -288,7 +297,10 @@ def config_leg(name, dev, with_eager=True, seed=17373331, quick=False):
            "no_graph": {"value": N / (p_ms * 1e-3), "ms_per_step": p_ms / steps, "launches_per_step": p_launch},
            "cluster": {"value": N / (cl_ms * 1e-3), "unit": "samples/s", "ms": cl_ms,
                        "note": "trainer.cluster() + stat_envs(): host-drawn tie-break indices (numpy stream, as the "
-                               "reference) + H2D + one kernel + diff read-back"},
+                               "reference) + H2D + one kernel + diff read-back",
+                       "device_tie_break_rng": {"value": N / (cl_dev_ms * 1e-3), "ms": cl_dev_ms,
+                                                "note": "tie_break_rng='device' (opt-in, not the reference's numpy "
+                                                        "stream): no host draw, no H2D"}},
            "roofline_frac_8d": step_bytes(B, D, K, P) * steps / (g_ms * 1e-3) / 1e9 / measured_peaks()[0]}
     if quick:
         del leg["no_graph"]

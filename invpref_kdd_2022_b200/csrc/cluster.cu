@@ -419,21 +419,29 @@ __global__ void __launch_bounds__(BLOCK, (VEC * NV <= 4 && KT <= 4) ? 4 : 1) clu
     if (tid == INVPREF_MAX_ENVS && a.diff != nullptr && sHist[tid] != 0ull) atomicAdd(a.diff, sHist[tid]);
 }
 
+// Counts in registers (one counter per environment per thread), warp sums with redux, one shared-memory atomic per
+// warp and environment, one global atomic per CTA and environment.  Grid-stride over <= 148 * 8 CTAs: the dataset
+// configs (3 * 10^5 samples) get a full grid instead of the five CTAs of a 2^16-samples-per-CTA split.
 __global__ void __launch_bounds__(256) env_hist_kernel(const int64_t* __restrict__ envs, int64_t N, int K,
                                                        unsigned long long* __restrict__ hist) {
-    __shared__ unsigned int sH[INVPREF_MAX_ENVS];
-    if (threadIdx.x < INVPREF_MAX_ENVS) sH[threadIdx.x] = 0u;
+    __shared__ unsigned long long sH[INVPREF_MAX_ENVS];
+    if (threadIdx.x < INVPREF_MAX_ENVS) sH[threadIdx.x] = 0ull;
     __syncthreads();
-    // a CTA handles 2^16 samples so the 32-bit shared counters cannot overflow
-    const int64_t per = 1 << 16;
-    const int64_t lo = (int64_t)blockIdx.x * per;
-    const int64_t hi = lo + per < N ? lo + per : N;
-    for (int64_t n = lo + threadIdx.x; n < hi; n += blockDim.x) {
-        const int64_t e = envs[n];
-        if (e >= 0 && e < K) atomicAdd(&sH[(int)e], 1u);
+    unsigned cnt[INVPREF_MAX_ENVS];
+#pragma unroll
+    for (int k = 0; k < INVPREF_MAX_ENVS; ++k) cnt[k] = 0u;
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)envs[n];
+#pragma unroll
+        for (int k = 0; k < INVPREF_MAX_ENVS; ++k) cnt[k] += (e == k) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < INVPREF_MAX_ENVS; ++k) {
+        const unsigned w = __reduce_add_sync(0xffffffffu, cnt[k]);
+        if ((threadIdx.x & 31) == 0 && w != 0u && k < K) atomicAdd(&sH[k], (unsigned long long)w);
     }
     __syncthreads();
-    if ((int)threadIdx.x < K && sH[threadIdx.x] != 0u) atomicAdd(&hist[threadIdx.x], (unsigned long long)sH[threadIdx.x]);
+    if ((int)threadIdx.x < K && sH[threadIdx.x] != 0ull) atomicAdd(&hist[threadIdx.x], sH[threadIdx.x]);
 }
 
 // class_weights[k] = min(cnt_k + 1, N - 1) / N in double, rounded to fp32 (train.py:950-955);
@@ -535,9 +543,9 @@ int launch_cluster_sorted(const Geometry& g, const ClusterArgs& a, cudaStream_t 
 }
 
 int launch_env_hist(const int64_t* envs, int64_t N, int K, unsigned long long* hist, cudaStream_t stream) {
-    int64_t per = 1 << 16;
-    int grid = (int)((N + per - 1) / per);
-    if (grid < 1) grid = 1;
+    // a thread's 32-bit counters see N / (grid * 256) samples: below 2^32 for any N < 2^50
+    const int64_t need = (N + 1023) / 1024;
+    const int grid = (int)(need < 1 ? 1 : (need < 148 * 8 ? need : 148 * 8));
     env_hist_kernel<<<grid, 256, 0, stream>>>(envs, N, K, hist);
     count_launch();
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;

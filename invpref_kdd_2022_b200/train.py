@@ -33,8 +33,12 @@ class _InvPrefTrainManager:
             alpha: float = None, use_class_re_weight: bool = False, test_begin_epoch: int = 0,
             begin_cluster_epoch: int = None, stop_cluster_epoch: int = None, cluster_use_random_sort: bool = True,
             use_recommend_re_weight: bool = True, cache_plans: bool = True, lazy_adam: bool = True,
-            use_graph: bool = True, plan_cache_bytes: int = 16 << 30, sorted_cluster: bool = False
+            use_graph: bool = True, plan_cache_bytes: int = 16 << 30, sorted_cluster: bool = False,
+            tie_break_rng: str = "numpy"
     ):
+        if tie_break_rng not in ("numpy", "device"):
+            raise ValueError("tie_break_rng must be 'numpy' (the reference's host stream, train.py:870-871) or 'device'")
+        self.tie_break_rng = tie_break_rng
         self.model = model
         self.evaluator = evaluator
         self.envs_num: int = model.env_num
@@ -306,10 +310,15 @@ class _InvPrefTrainManager:
         self.model.eval()
         n = self.users_tensor.shape[0]
         perm = None
-        if self.cluster_use_random_sort:
+        if self.cluster_use_random_sort and self.tie_break_rng == "device":
+            # NOT the reference's stream: the tie-break rows are drawn by torch's device generator.  The draws only
+            # decide between environments whose distances agree to ~1e-10 (train.py:763-769), but numpy's sequential
+            # Mersenne-Twister stream costs ~10 ns per sample on the host -- 40 of the 53 ms of a MIND-sized cluster()
+            perm = torch.randint(0, self.eps_random_tensor.shape[0], (n,), device=self.device)
+        elif self.cluster_use_random_sort:
             draws = [np.random.randint(0, self.eps_random_tensor.shape[0], min(self.batch_size, n - lo))
                      for lo in range(0, n, self.batch_size)]
-            perm = torch.from_numpy(np.concatenate(draws).astype(np.int64)).to(self.device)
+            perm = torch.from_numpy(np.concatenate(draws)).to(self.device)       # randint draws int64 already
         eps = self.eps_random_tensor if perm is not None else None
         if self.sorted_cluster:
             if self._cl_view is None:

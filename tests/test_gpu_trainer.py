@@ -88,6 +88,28 @@ def test_epoch_cluster_stat_like_the_driver(case, cache_plans):
     assert np.array_equal(tm.sample_weights.cpu().numpy(), on.stat_envs(new, g.K, g.N)[2])
 
 
+def test_device_tie_break_rng_leaves_the_numpy_stream_alone():
+    """tie_break_rng="device" (an opt-in, NOT the reference's stream): cluster() draws the tie-break rows on the device;
+    the assignments can differ from the numpy-stream run only where two distances agree to ~1e-10."""
+    g = Golden("coat_explicit")
+    _, tm_ref = build(g)
+    tm_ref.stat_envs(); tm_ref.train_a_epoch()
+    np.random.seed(5)
+    tm_ref.cluster()
+    _, tm = build(g, tie_break_rng="device")
+    tm.stat_envs(); tm.train_a_epoch()
+    np.random.seed(5)
+    before = np.random.get_state()[1].copy()
+    np.random.seed(5)
+    diff = tm.cluster()
+    assert np.array_equal(np.random.get_state()[1], before)            # no host draw at all
+    a, b = tm.envs.cpu().numpy(), tm_ref.envs.cpu().numpy()
+    assert diff == int((a != g["envs0"]).sum())
+    assert (a != b).mean() <= 0.02                                     # fp32 near-ties only
+    with pytest.raises(ValueError):
+        build(g, tie_break_rng="philox")
+
+
 def test_train_loop_returns_reference_triple():
     g = Golden("coat_explicit")
     model, tm = build(g, epochs=3, cluster_interval=2)
