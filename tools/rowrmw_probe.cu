@@ -1,0 +1,152 @@
+// Access-pattern probe for the fused user pass: what DRAM bandwidth does a B200 deliver for the
+// pass's memory pattern when there is NO arithmetic and NO dependency between rows?
+//
+//   stream : read-modify-write of six [U, 64] fp32 tables front to back (what sweep_kernel does; the copy peak's twin)
+//   rows   : the user pass's pattern -- for S sorted row ids (about a third of the U rows, as a 4 M-interaction batch
+//            over 10 M users touches), read the row of six tables, write it back, write two rows of a sequential
+//            "stash", and gather two random rows of two [I, 64] item tables per 1.27 segments; 16 lanes per row,
+//            float4 per lane, ROWS_IN_FLIGHT independent rows per group
+//   gather : read-only random gather of four rows per sample (the re-assignment kernel's pattern)
+//
+// Prints one JSON line with GB/s of each.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/rowrmw_probe
+// tools/rowrmw_probe.cu ; run on the GPU box (needs ~22 GB).
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <algorithm>
+#include <random>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("{\"error\": \"%s at %d\"}\n", cudaGetErrorString(e_), __LINE__); return 1; } } while (0)
+
+constexpr int D4 = 16;   // float4 per 256-byte row
+
+__global__ void __launch_bounds__(256) stream_kernel(float4* t0, float4* t1, float4* t2, float4* t3, float4* t4,
+                                                      float4* t5, int64_t n4) {
+    float4* tabs[6] = {t0, t1, t2, t3, t4, t5};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) v[t] = __ldcs(tabs[t] + i);
+#pragma unroll
+        for (int t = 0; t < 6; ++t) { v[t].x += 1.f; __stcs(tabs[t] + i, v[t]); }
+    }
+}
+
+template <int INFLIGHT>
+__global__ void __launch_bounds__(256) rows_kernel(float4* t0, float4* t1, float4* t2, float4* t3, float4* t4,
+                                                    float4* t5, const float4* __restrict__ i0,
+                                                    const float4* __restrict__ i1, float4* __restrict__ stash,
+                                                    const int32_t* __restrict__ rows, const int32_t* __restrict__ items,
+                                                    int64_t S, float* sink) {
+    float4* tabs[6] = {t0, t1, t2, t3, t4, t5};
+    const int lane = threadIdx.x & 15;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
+    const int64_t ng = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    float acc = 0.f;
+    for (int64_t s0 = g * INFLIGHT; s0 < S; s0 += ng * INFLIGHT) {
+        float4 v[INFLIGHT][6], it[INFLIGHT][2];
+        int64_t r[INFLIGHT];
+#pragma unroll
+        for (int q = 0; q < INFLIGHT; ++q) {
+            const int64_t s = s0 + q < S ? s0 + q : S - 1;
+            r[q] = rows[s];
+            const int64_t ir = items[s];
+#pragma unroll
+            for (int t = 0; t < 6; ++t) v[q][t] = tabs[t][r[q] * D4 + lane];
+            it[q][0] = i0[ir * D4 + lane];
+            it[q][1] = i1[ir * D4 + lane];
+        }
+#pragma unroll
+        for (int q = 0; q < INFLIGHT; ++q) {
+            if (s0 + q < S) {
+                acc += it[q][0].x + it[q][1].y;
+#pragma unroll
+                for (int t = 0; t < 6; ++t) { v[q][t].x += 1.f; tabs[t][r[q] * D4 + lane] = v[q][t]; }
+                stash[((s0 + q) * 2 + 0) * D4 + lane] = v[q][0];
+                stash[((s0 + q) * 2 + 1) * D4 + lane] = v[q][1];
+            }
+        }
+    }
+    if (acc == 12345.678f) *sink = acc;
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ t0, const float4* __restrict__ t1,
+                                                      const float4* __restrict__ i0, const float4* __restrict__ i1,
+                                                      const int32_t* __restrict__ rows, const int32_t* __restrict__ items,
+                                                      int64_t N, float* sink) {
+    const int lane = threadIdx.x & 15;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
+    const int64_t ng = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    float acc = 0.f;
+    for (int64_t s0 = g * 4; s0 < N; s0 += ng * 4) {
+        float4 v[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t s = s0 + q < N ? s0 + q : N - 1;
+            const int64_t r = rows[s], ir = items[s];
+            v[q][0] = t0[r * D4 + lane]; v[q][1] = t1[r * D4 + lane];
+            v[q][2] = i0[ir * D4 + lane]; v[q][3] = i1[ir * D4 + lane];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc += v[q][0].x + v[q][1].y + v[q][2].z + v[q][3].w;
+    }
+    if (acc == 12345.678f) *sink = acc;
+}
+
+int main() {
+    const int64_t U = 10000000, I = 1000000, B = 1 << 22;
+    std::mt19937_64 gen(20220814);
+    std::uniform_real_distribution<double> uni(0.0, 1.0);
+    std::vector<int32_t> u(B), it(B);
+    for (int64_t k = 0; k < B; ++k) {
+        u[k] = (int32_t)std::min<double>(U - 1, std::floor(U * std::pow(uni(gen), 1.5)));    // SURVEY.md 8d generators
+        it[k] = (int32_t)std::min<double>(I - 1, std::floor(I * std::pow(uni(gen), 3.0)));
+    }
+    std::vector<int32_t> rows(u);
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    const int64_t S = (int64_t)rows.size();
+    std::vector<int32_t> seg_items(it.begin(), it.begin() + S);       // one random item row pair per segment ...
+    float4* tabs[6];
+    for (int t = 0; t < 6; ++t) { CK(cudaMalloc(&tabs[t], U * 256)); CK(cudaMemset(tabs[t], 0, U * 256)); }
+    float4 *i0, *i1, *stash;
+    CK(cudaMalloc(&i0, I * 256)); CK(cudaMalloc(&i1, I * 256)); CK(cudaMalloc(&stash, S * 512));
+    CK(cudaMemset(i0, 0, I * 256)); CK(cudaMemset(i1, 0, I * 256));
+    int32_t *d_rows, *d_items, *d_u, *d_it;
+    CK(cudaMalloc(&d_rows, S * 4)); CK(cudaMalloc(&d_items, S * 4)); CK(cudaMalloc(&d_u, B * 4)); CK(cudaMalloc(&d_it, B * 4));
+    CK(cudaMemcpy(d_rows, rows.data(), S * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_items, seg_items.data(), S * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_u, u.data(), B * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_it, it.data(), B * 4, cudaMemcpyHostToDevice));
+    float* sink; CK(cudaMalloc(&sink, 4));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    auto timeit = [&](auto&& launch, int reps) -> float {
+        launch(); launch();
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0);
+        for (int r = 0; r < reps; ++r) launch();
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        return ms / reps;
+    };
+    const int grid = 148 * 8;
+    const float ms_stream = timeit([&] { stream_kernel<<<grid, 256>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], U * D4); }, 5);
+    const double stream_gb = 6.0 * U * 256 * 2 / 1e9;
+    // rows pattern: 6 rows read + 6 written + 2 stash rows written + 2 item rows read per segment, ids 8 B
+    const double rows_gb = (double)S * (6 * 256 + 6 * 256 + 2 * 256 + 2 * 256 + 8) / 1e9;
+    const float ms_r2 = timeit([&] { rows_kernel<2><<<grid, 256>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 10);
+    const float ms_r4 = timeit([&] { rows_kernel<4><<<grid, 256>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 10);
+    const float ms_r4b = timeit([&] { rows_kernel<4><<<148 * 16, 256>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 10);
+    const float ms_g = timeit([&] { gather_kernel<<<148 * 16, 256>>>(tabs[0], tabs[1], i0, i1, d_u, d_it, B, sink); }, 10);
+    const double gather_gb = (double)B * (4 * 256 + 8) / 1e9;
+    CK(cudaGetLastError());
+    printf("{\"probe\": \"row access patterns, no arithmetic\", \"segments\": %lld, \"stream_rmw_6_tables\": {\"GB\": %.3f, \"ms\": %.4f, \"GBs\": %.1f}, "
+           "\"user_pass_pattern\": {\"GB\": %.3f, \"inflight2\": {\"ms\": %.4f, \"GBs\": %.1f}, \"inflight4\": {\"ms\": %.4f, \"GBs\": %.1f}, "
+           "\"inflight4_grid16\": {\"ms\": %.4f, \"GBs\": %.1f}}, \"random_gather_4_rows\": {\"GB\": %.3f, \"ms\": %.4f, \"GBs\": %.1f}}\n",
+           (long long)S, stream_gb, ms_stream, stream_gb / ms_stream * 1e3, rows_gb, ms_r2, rows_gb / ms_r2 * 1e3, ms_r4,
+           rows_gb / ms_r4 * 1e3, ms_r4b, rows_gb / ms_r4b * 1e3, gather_gb, ms_g, gather_gb / ms_g * 1e3);
+    return 0;
+}
