@@ -16,6 +16,14 @@
 // An extra step of look-ahead with prefetch.global.L2 (no third shared-memory stage needed) was measured and LOSES:
 // user pass 2.91 -> 2.99 ms, re-assignment 3.69 -> 4.66 ms on 25 M samples (round 2, B200): the kernels are bound by
 // DRAM throughput, not by exposed latency, and the prefetches only add request traffic.  Kept as A/B switches.
+// A/B switch (measured, off): user pass, segments with two or more interactions -- request the next segment's stage
+// AFTER the second interaction's item rows instead of at the top of the segment.  cp.async groups complete in order,
+// so the in-loop wait for the item rows (the newest group) also waits for the eight rows of the next stage; ncu's
+// source page shows that wait carrying as many long-scoreboard samples as the top-of-segment wait on half as many
+// executions.  Deferring costs 8 registers (120 -> 128) and measured 2.96-3.01 ms against 2.92 ms (same box).
+#ifndef INVPREF_UPASS_DEFER
+#define INVPREF_UPASS_DEFER 0
+#endif
 #ifndef INVPREF_UPASS_L2_PREFETCH
 #define INVPREF_UPASS_L2_PREFETCH 0
 #endif

@@ -135,9 +135,21 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
         const int stg = ord & 1;
         cp_async_wait<0>();      // A_ord: this segment's rows and scalars, the next segment's descriptor
         __syncwarp(gmask);
-        if (seg_at(ord + 1) < n_seg) request_segment(stg ^ 1, meta + UM_DESC + ((ord + 1) & 3) * 8);
-        request_desc(ord + 3, seg_at(ord + 3));     // its slot held this group's previous segment
-        cp_async_commit();       // A_{ord+1}
+        // the next segment's stage (group A_{ord+1}): now -- or, for a segment with more interactions to come, right
+        // after the second interaction's item rows have been requested (INVPREF_UPASS_DEFER, common.cuh)
+        auto request_next = [&]() {
+            if (seg_at(ord + 1) < n_seg) request_segment(stg ^ 1, meta + UM_DESC + ((ord + 1) & 3) * 8);
+            request_desc(ord + 3, seg_at(ord + 3));     // its slot held this group's previous segment
+            cp_async_commit();       // A_{ord+1}
+        };
+        bool deferred = false;
+#if INVPREF_UPASS_DEFER
+        {
+            const int len0 = meta[UM_DESC + (ord & 3) * 8 + 2] - meta[UM_DESC + (ord & 3) * 8 + 1];
+            deferred = len0 > 1 && len0 <= long_len;
+        }
+#endif
+        if (!deferred) request_next();
 #if INVPREF_UPASS_L2_PREFETCH
         // One more segment of look-ahead without a third shared-memory stage: the eight rows of segment ord+2 (its
         // descriptor is already here) are pulled into L2 now, one 128-byte line per lane, so that the cp.async of
@@ -212,7 +224,10 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
             for (int k = beg; k < end; ++k) {
                 const int par = (k - beg) & 1;
                 if (k > beg) {
-                    cp_async_wait<0>();      // G_{i-1}: this interaction's rows and scalars, the next one's indices
+                    // G_{i-1}: this interaction's rows and scalars, the next one's indices.  Deferred stage: it is the
+                    // only group younger than G_0, so the second interaction need not wait for it
+                    if (deferred && k == beg + 1) cp_async_wait<1>();
+                    else cp_async_wait<0>();
                     __syncwarp(gmask);
                     const int4 sI = *reinterpret_cast<const int4*>(meta + UM_ITS + par * 4);
                     e = sI.x; y = __int_as_float(sI.y); w = __int_as_float(sI.z);
@@ -238,6 +253,7 @@ __global__ void __launch_bounds__(BLOCK, 2) upass_rows_staged_kernel(UserPassArg
                         if (lane == 13) cp_async<4>(smem_addr(meta + UM_ITI + par * 2 + 1), partner + k + 2);
                     }
                     cp_async_commit();       // G_i
+                    if (deferred && k == beg) request_next();
                 }
                 inter_grads<VEC, NV, KT>(a, cfg, myDE, s.sB, rc, rie, q, n, e, y, w, lane, gmask, acc0, Q, ge.x, st, D, K);
                 n = n_a;
