@@ -21,7 +21,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'upa
     -o /tmp/r2z_prof_c5 -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-config-legs --nbatch 4 > gpurun_out/r2z_ncu_c5.log 2>&1
 ncu -i /tmp/r2z_prof_c5.ncu-rep --page raw --csv > gpurun_out/r2z_prof_c5_raw.csv 2>/dev/null
 echo "== ncu full: re-assignment kernels (c5)"; date
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'cluster_kernel|cluster_sorted_kernel' -s 2 -c 2 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:cluster_kernel -s 2 -c 1 \
     -o /tmp/r2z_prof_cl -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-config-legs --nbatch 4 > gpurun_out/r2z_ncu_cl.log 2>&1
 ncu -i /tmp/r2z_prof_cl.ncu-rep --page raw --csv > gpurun_out/r2z_prof_cl_raw.csv 2>/dev/null
 ls -la gpurun_out | grep r2z

@@ -1,11 +1,14 @@
 #!/bin/bash
-# Round 2, multi-GPU development call: the push cases of the real-rank tests, then the N-GPU bench line.
+# Round 2, multi-GPU development call: the push cases of the real-rank tests (skipped with a second argument
+# `notest`), then the N-GPU bench line.
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
+if [ "${2:-tests}" != notest ]; then
 echo "== real-rank tests (push)"; date
 timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -x -k "push" 2>&1 | tail -40 > gpurun_out/r2p_pytest_g$N.log; tail -25 gpurun_out/r2p_pytest_g$N.log
+fi
 echo "== bench N=$N"; date
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/r2p_bench_g${N}.json 2> gpurun_out/r2p_bench_g${N}.err
