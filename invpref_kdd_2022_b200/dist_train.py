@@ -104,6 +104,13 @@ class _ShardedInvPrefTrainManager:
         bounds = torch.arange(0, N + batch_size, batch_size, device=device).clamp_(max=N)
         self._lo = torch.searchsorted(rows, bounds).tolist()          # local slice of every global batch
         per_rank = max(self._lo[b + 1] - self._lo[b] for b in range(self.batch_num))
+        if driver is None and self.world > 1:
+            # the symmetric-memory buffer must have the same layout (hence the same size) on every rank: size the
+            # caches for the largest share any rank has of any batch
+            import torch.distributed as dist
+            t = torch.tensor([per_rank], dtype=torch.int64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            per_rank = int(t.item())
         cache_rows = min(item_num, per_rank + 1024)
         stage_rows = min(2 * cache_rows + 1024, ((item_num + self.world - 1) // self.world) * self.world) \
             if exchange == "push" else 0
