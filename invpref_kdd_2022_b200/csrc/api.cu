@@ -78,10 +78,11 @@ int build_plan_impl(const invpref_desc* d, const int64_t* users, const int64_t* 
                     char* tmp, size_t tmp_bytes, cudaStream_t st) {
     PlanSide pu, pi;
     carve_plan(d, B, plan, &pu, &pi);
-    int rc = build_plan_side(users, items, d->n_items, pu, tmp, tmp_bytes, st);
+    // user side first; the item side then also records, per sorted interaction, the USER segment of its partner row
+    // (pseg: where the item pass finds that row in the stash) -- the user side's pseg has no reader and stays unwritten
+    int rc = build_plan_side(users, items, d->n_items, nullptr, pu, tmp, tmp_bytes, st);
     if (rc != INVPREF_OK) return rc;
-    if ((rc = build_plan_side(items, users, d->n_users, pi, tmp, tmp_bytes, st)) != INVPREF_OK) return rc;
-    return fill_partner_segments(pu, pi, st);
+    return build_plan_side(items, users, d->n_users, pu.seg_of, pi, tmp, tmp_bytes, st);
 }
 
 }  // namespace

@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_chunks_ring_kernel(BwdSideArgs a
 //
 // ncu on bwd_rows_kernel (round 1): 47 % of the warp samples wait on the long scoreboard -- perm/partner ->
 // g-pack + two partner rows per interaction, L2 prefetch or not.  Here
-//  * the plan cuts the segments into cost-balanced CONTIGUOUS ranges (plan.cu: write_ranges_kernel); a group
+//  * the plan cuts the segments into cost-balanced CONTIGUOUS ranges (plan.cu: write_chunks_ranges_kernel); a group
 //    takes ranges g, g + G, ...: inside a range the sorted positions it walks are contiguous across segment
 //    boundaries, and the strided assignment averages out what the cost model misses (a first version with ONE
 //    range per group ran 1.5x longer on its slowest SM than on average);

@@ -170,9 +170,8 @@ int launch_eval_topk(const float* Uinv, const float* Iinv, int64_t n_items, int 
                      int64_t* top_items, float* top_scores, uint8_t* hits, int64_t* n_gt, cudaStream_t stream);
 
 // ---- plan.cu ---------------------------------------------------------------------------------
-int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, PlanSide p, char* tmp,
-                    size_t tmp_bytes, cudaStream_t stream);
-int fill_partner_segments(PlanSide a, PlanSide b, cudaStream_t stream);
+int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, const int32_t* other_seg_of,
+                    PlanSide p, char* tmp, size_t tmp_bytes, cudaStream_t stream);
 int launch_check_ids(const int64_t* users, const int64_t* items, const int64_t* envs, int64_t B, int64_t n_users,
                      int64_t n_items, int64_t n_envs, int32_t* flag, cudaStream_t stream);
 int build_segments_i64(const int64_t* ids, int64_t B, int64_t rows, int64_t* perm, int64_t* seg_row, int64_t* seg_off,

@@ -41,9 +41,13 @@ __global__ void __launch_bounds__(256) check_ids_kernel(const int64_t* __restric
     if (bad != 0 && (threadIdx.x & 31) == 0) atomicOr(flag, bad);
 }
 
+// other_seg_of (nullable): seg_of of the OTHER side's finished plan -> pseg[k] = segment, on the other side, of the
+// partner row of sorted position k (read by the item pass to index the stash of user rows; the user side, built
+// first, has no reader for it and passes nullptr).
 __global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const int32_t* __restrict__ segid,
                                       const int32_t* __restrict__ perm, const int64_t* __restrict__ other_ids,
-                                      int64_t other_rows, int64_t B, PlanSide p) {
+                                      int64_t other_rows, const int32_t* __restrict__ other_seg_of, int64_t B,
+                                      PlanSide p) {
     const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool in = k < B;
     const int lane = threadIdx.x & 31;
@@ -65,7 +69,9 @@ __global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const 
         if (in && (lane == 0 || pw != word) && bits != 0u) atomicOr(&p.touched[word], bits);
     }
     if (!in) return;
-    p.seg_of[perm[k]] = s;
+    const int32_t orig = perm[k];
+    p.seg_of[orig] = s;
+    if (other_seg_of != nullptr) p.pseg[k] = other_seg_of[orig];
     if (head) {
         p.seg_row[s] = key;
         p.seg_off[s] = (int32_t)k;
@@ -75,19 +81,13 @@ __global__ void write_segments_kernel(const int32_t* __restrict__ sorted, const 
         p.seg_off[s + 1] = (int32_t)B;
     }
     if (other_ids != nullptr) {
-        int64_t o = other_ids[perm[k]];
+        int64_t o = other_ids[orig];
         if (o < 0 || o >= other_rows) {
             p.counters[2] = 1;   // flagged like an out-of-range key (prep_keys_kernel), clamped
             o = o < 0 ? 0 : other_rows - 1;
         }
         p.partner[k] = (int32_t)o;
     }
-}
-
-// pseg[k] = segment index, on the other side, of the partner row of sorted position k
-__global__ void fill_pseg_kernel(PlanSide p, const int32_t* __restrict__ other_seg_of) {
-    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (k < p.B) p.pseg[k] = other_seg_of[p.perm[k]];
 }
 
 __global__ void chunk_counts_kernel(PlanSide p, int chunk) {
@@ -102,10 +102,35 @@ __global__ void chunk_counts_kernel(PlanSide p, int chunk) {
     p.seg_chunk[s] = c;
 }
 
-__global__ void write_chunks_kernel(PlanSide p, int chunk, int has_partner) {
-    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    int32_t n_seg = p.counters[0];
-    if (s == 0) p.counters[1] = p.seg_chunk[n_seg];
+// Cost prefix of the segments before s: strictly increasing in s (a long segment, pre-reduced by the chunks
+// kernels, counts len - ceil(len / chunk) * chunk / 2 > 0 of its interactions).
+__device__ __forceinline__ int64_t seg_cost(const PlanSide& p, int64_t s, int half_chunk) {
+    return (int64_t)PLAN_CSEG * s + p.seg_off[s] - (int64_t)half_chunk * p.seg_chunk[s];
+}
+
+// One thread per segment s (one launch instead of two):
+//  * descriptors: seg_desc[s], the chunk descriptors of a long segment, the hot list;
+//  * work ranges: range_start[r] = smallest s in [0, n_seg] with seg_cost(s) * R >= r * seg_cost(n_seg), r = 0..R.
+//    Thread s writes the r's in (q(s-1), q(s)], q(s) = seg_cost(s) * R / total: every r is written exactly once.  q(s-1)
+//    comes from the neighbouring lane (one 64-bit division per thread instead of two).
+__global__ void write_chunks_ranges_kernel(PlanSide p, int chunk, int has_partner, int n_ranges) {
+    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int32_t n_seg = p.counters[0];
+    const int half_chunk = chunk / 2;
+    if (s == 0) {
+        p.counters[1] = p.seg_chunk[n_seg];
+        p.counters[3] = n_ranges;
+        p.range_start[0] = 0;
+    }
+    {
+        const int64_t total = seg_cost(p, n_seg, half_chunk);
+        const bool on = s <= n_seg;
+        const int64_t q = on ? seg_cost(p, s, half_chunk) * n_ranges / total : 0;
+        int64_t q_prev = __shfl_up_sync(0xffffffffu, q, 1);
+        if ((threadIdx.x & 31) == 0 && on && s >= 1) q_prev = seg_cost(p, s - 1, half_chunk) * n_ranges / total;
+        if (on && s >= 1)
+            for (int64_t r = q_prev + 1; r <= q; ++r) p.range_start[r] = (int32_t)s;
+    }
     if (s >= n_seg) return;
     int32_t c0 = p.seg_chunk[s], c1 = p.seg_chunk[s + 1];
     int32_t beg = p.seg_off[s], end = p.seg_off[s + 1];
@@ -123,25 +148,6 @@ __global__ void write_chunks_kernel(PlanSide p, int chunk, int has_partner) {
         int32_t e = b + chunk < end ? b + chunk : end;
         reinterpret_cast<int4*>(p.chunk_desc)[c] = make_int4((int32_t)s, b, e, 0);
     }
-}
-
-// Cost prefix of the segments before s: strictly increasing in s (a long segment, pre-reduced by the chunks
-// kernels, counts len - ceil(len / chunk) * chunk / 2 > 0 of its interactions).
-__device__ __forceinline__ int64_t seg_cost(const PlanSide& p, int64_t s, int half_chunk) {
-    return (int64_t)PLAN_CSEG * s + p.seg_off[s] - (int64_t)half_chunk * p.seg_chunk[s];
-}
-
-// range_start[r] = smallest s in [0, n_seg] with seg_cost(s) * R >= r * seg_cost(n_seg), r = 0..R.
-// Thread s writes the r's that map to it: every r is written exactly once.
-__global__ void write_ranges_kernel(PlanSide p, int half_chunk, int n_ranges) {
-    const int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int32_t n_seg = p.counters[0];
-    if (s == 0) { p.counters[3] = n_ranges; p.range_start[0] = 0; }
-    if (s < 1 || s > n_seg) return;
-    const int64_t total = seg_cost(p, n_seg, half_chunk);
-    const int64_t lo = seg_cost(p, s - 1, half_chunk) * n_ranges / total + 1;
-    const int64_t hi = seg_cost(p, s, half_chunk) * n_ranges / total;
-    for (int64_t r = lo; r <= hi; ++r) p.range_start[r] = (int32_t)s;
 }
 
 __global__ void empty_plan_kernel(PlanSide p) {
@@ -198,8 +204,8 @@ size_t sort_tmp_bytes_for(int64_t B, int64_t max_rows) {
 }
 
 // Builds one side of a plan.  All work is enqueued on `stream`; nothing is read back.
-int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, PlanSide p, char* tmp,
-                    size_t tmp_bytes, cudaStream_t stream) {
+int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_rows, const int32_t* other_seg_of,
+                    PlanSide p, char* tmp, size_t tmp_bytes, cudaStream_t stream) {
     int64_t B = p.B;
     cudaMemsetAsync(p.touched, 0, (size_t)((p.rows + 31) / 32) * 4, stream);
     cudaMemsetAsync(p.counters, 0, 16 * 4, stream);
@@ -211,18 +217,18 @@ int build_plan_side(const int64_t* ids, const int64_t* other_ids, int64_t other_
     if (tmp_bytes < sort_tmp_bytes_for(B, p.rows)) return INVPREF_ERR_WORKSPACE;
     SortTmp t = carve_sort_tmp(tmp, B);
     prep_keys_kernel<<<grid_for(B), 256, 0, stream>>>(ids, B, p.rows, t.keys_in, p.counters);
-    int n_launch = 5;
+    int n_launch = 4;
     // perm = stable argsort of the row ids
     n_launch += psort::radix_sort_pairs(t.keys_in, nullptr, t.keys_out, p.perm, t.keys_tmp, t.vals_tmp, B,
                                         bits_for(p.rows), t.sort_scratch, stream);
     // scan[k] = 1 + segment of sorted position k (inclusive sum of the head flags)
     n_launch += psort::prefix_sum<1, true>(t.keys_out, t.scan, B, t.scan_scratch, stream);
-    write_segments_kernel<<<grid_for(B), 256, 0, stream>>>(t.keys_out, t.scan, p.perm, other_ids, other_rows, B, p);
+    write_segments_kernel<<<grid_for(B), 256, 0, stream>>>(t.keys_out, t.scan, p.perm, other_ids, other_rows,
+                                                           other_seg_of, B, p);
     chunk_counts_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B));
     n_launch += psort::prefix_sum<0, false>(p.seg_chunk, p.seg_chunk, p.max_seg + 1, t.scan_scratch, stream);
-    write_chunks_kernel<<<grid_for(p.max_seg > 0 ? p.max_seg : 1), 256, 0, stream>>>(p, chunk_for(B),
-                                                                                       other_ids != nullptr);
-    write_ranges_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B) / 2, (int)plan_ranges(B));
+    write_chunks_ranges_kernel<<<grid_for(p.max_seg + 1), 256, 0, stream>>>(p, chunk_for(B), other_ids != nullptr,
+                                                                           (int)plan_ranges(B));
     count_launch(n_launch);
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
@@ -236,14 +242,6 @@ int launch_check_ids(const int64_t* users, const int64_t* items, const int64_t* 
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
 
-int fill_partner_segments(PlanSide a, PlanSide b, cudaStream_t stream) {
-    if (a.B == 0) return INVPREF_OK;
-    fill_pseg_kernel<<<grid_for(a.B), 256, 0, stream>>>(a, b.seg_of);
-    fill_pseg_kernel<<<grid_for(b.B), 256, 0, stream>>>(b, a.seg_of);
-    count_launch(2);
-    return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
-}
-
 int build_segments_i64(const int64_t* ids, int64_t B, int64_t rows, int64_t* perm, int64_t* seg_row, int64_t* seg_off,
                        int64_t* n_seg, char* ws, size_t ws_bytes, cudaStream_t stream) {
     int64_t Bp = B > 0 ? B : 1;
@@ -252,7 +250,7 @@ int build_segments_i64(const int64_t* ids, int64_t B, int64_t rows, int64_t* per
     if (ws_bytes < need) return INVPREF_ERR_WORKSPACE;
     PlanSide p = carve_plan_side(ws, Bp, rows);
     p.B = B;
-    int rc = build_plan_side(ids, nullptr, 0, p, ws + side, ws_bytes - side, stream);
+    int rc = build_plan_side(ids, nullptr, 0, nullptr, p, ws + side, ws_bytes - side, stream);
     if (rc != INVPREF_OK) return rc;
     if (B > 0) {
         widen_kernel<<<grid_for(B), 256, 0, stream>>>(p.perm, perm, B, nullptr, 0);
