@@ -406,9 +406,9 @@ int launch_peer_allreduce(float* buf, int n, int n_max, int world, int rank, flo
         ps.flags[p] = flags_host[p];
     }
     peer_post_kernel<<<1, 256, 0, stream>>>(buf, n, n_max, world, rank, ps, ctr);
-    // 200 ns sleeps: ~25 M iterations = 5 s before a missing peer is reported instead of waited for
+    // 200 ns sleeps: 50 M iterations = at least 10 s before a missing peer is reported instead of waited for
     peer_reduce_kernel<<<1, 256, 0, stream>>>(buf, n, n_max, world, ps.slots[rank], ps.flags[rank], ctr, status,
-                                              25u * 1000u * 1000u);
+                                              50u * 1000u * 1000u);
     count_launch(2);
     return cudaGetLastError() == cudaSuccess ? INVPREF_OK : INVPREF_ERR_CUDA;
 }
