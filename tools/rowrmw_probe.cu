@@ -7,6 +7,9 @@
 //            "stash", and gather two random rows of two [I, 64] item tables per 1.27 segments; 16 lanes per row,
 //            float4 per lane, ROWS_IN_FLIGHT independent rows per group
 //   gather : read-only random gather of four rows per sample (the re-assignment kernel's pattern)
+//   items  : the item pass's pattern -- for every touched item row (sorted), read-modify-write the row of six [I, 64]
+//            tables, and per interaction gather two rows of the sequential-by-user-segment stash (random order) and
+//            read a 32-byte g-pack record
 //
 // Prints one JSON line with GB/s of each.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/rowrmw_probe
 // tools/rowrmw_probe.cu ; run on the GPU box (needs ~22 GB).
@@ -95,6 +98,44 @@ __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ 
     if (acc == 12345.678f) *sink = acc;
 }
 
+__global__ void __launch_bounds__(256) items_kernel(float4* t0, float4* t1, float4* t2, float4* t3, float4* t4,
+                                                     float4* t5, const float4* __restrict__ stash,
+                                                     const float4* __restrict__ gpack, const int32_t* __restrict__ seg_row,
+                                                     const int32_t* __restrict__ pseg, int64_t S, int64_t B,
+                                                     float* sink) {
+    float4* tabs[6] = {t0, t1, t2, t3, t4, t5};
+    const int lane = threadIdx.x & 15;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
+    const int64_t ng = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    float acc = 0.f;
+    // (a) per interaction, in item-sorted order: two stash rows (by user segment: random) + the g-pack record.  Walked
+    //     four interactions at a time by whichever group comes next, NOT segment by segment: a hot item's 40 000
+    //     interactions would otherwise serialise on one group (the real pass pre-reduces long segments in chunks)
+    for (int64_t k = g * 4; k < B; k += ng * 4) {
+        float4 a[4][2], gp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t kk = k + q < B ? k + q : B - 1;
+            const int64_t ps = pseg[kk];
+            a[q][0] = stash[(ps * 2 + 0) * D4 + lane];
+            a[q][1] = stash[(ps * 2 + 1) * D4 + lane];
+            gp[q] = gpack[kk * 2 + (lane & 1)];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc += a[q][0].x + a[q][1].y + gp[q].z;
+    }
+    // (b) per touched item row: read-modify-write of the row of the six tables
+    for (int64_t s = g; s < S; s += ng) {
+        const int64_t r = seg_row[s];
+        float4 v[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) v[t] = tabs[t][r * D4 + lane];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) { v[t].x += acc; tabs[t][r * D4 + lane] = v[t]; }
+    }
+    if (acc == 12345.678f) *sink = acc;
+}
+
 int main() {
     const int64_t U = 10000000, I = 1000000, B = 1 << 22;
     std::mt19937_64 gen(20220814);
@@ -142,7 +183,32 @@ int main() {
     const float ms_r4b = timeit([&] { rows_kernel<4><<<148 * 16, 256>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 10);
     const float ms_g = timeit([&] { gather_kernel<<<148 * 16, 256>>>(tabs[0], tabs[1], i0, i1, d_u, d_it, B, sink); }, 10);
     const double gather_gb = (double)B * (4 * 256 + 8) / 1e9;
+    // ---- item pass pattern: item segments of the same batch, partner = user segment of each interaction ----
+    std::vector<int32_t> order(B);
+    for (int64_t k = 0; k < B; ++k) order[k] = (int32_t)k;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return it[x] < it[y]; });
+    std::vector<int32_t> i_row, i_off, i_pseg(B);
+    for (int64_t k = 0; k < B; ++k) {
+        const int32_t n = order[k];
+        if (k == 0 || it[n] != it[order[k - 1]]) { i_row.push_back(it[n]); i_off.push_back((int32_t)k); }
+        i_pseg[k] = (int32_t)(std::lower_bound(rows.begin(), rows.end(), u[n]) - rows.begin());
+    }
+    i_off.push_back((int32_t)B);
+    const int64_t SI = (int64_t)i_row.size();
+    float4* it_tabs[6];
+    for (int t = 0; t < 6; ++t) { CK(cudaMalloc(&it_tabs[t], I * 256)); CK(cudaMemset(it_tabs[t], 0, I * 256)); }
+    float4* gpack; CK(cudaMalloc(&gpack, B * 32)); CK(cudaMemset(gpack, 0, B * 32));
+    int32_t *d_irow, *d_ioff, *d_ipseg;
+    CK(cudaMalloc(&d_irow, SI * 4)); CK(cudaMalloc(&d_ioff, (SI + 1) * 4)); CK(cudaMalloc(&d_ipseg, B * 4));
+    CK(cudaMemcpy(d_irow, i_row.data(), SI * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ioff, i_off.data(), (SI + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ipseg, i_pseg.data(), B * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(stash, 0, S * 512));
+    const float ms_it = timeit([&] { items_kernel<<<148 * 16, 256>>>(it_tabs[0], it_tabs[1], it_tabs[2], it_tabs[3], it_tabs[4], it_tabs[5], stash, gpack, d_irow, d_ipseg, SI, B, sink); }, 10);
+    const double items_gb = ((double)SI * 12 * 256 + (double)B * (2 * 256 + 32 + 4)) / 1e9;
     CK(cudaGetLastError());
+    printf("{\"item_pass_pattern\": {\"item_segments\": %lld, \"GB\": %.3f, \"ms\": %.4f, \"GBs\": %.1f}}\n",
+           (long long)SI, items_gb, ms_it, items_gb / ms_it * 1e3);
     printf("{\"probe\": \"row access patterns, no arithmetic\", \"segments\": %lld, \"stream_rmw_6_tables\": {\"GB\": %.3f, \"ms\": %.4f, \"GBs\": %.1f}, "
            "\"user_pass_pattern\": {\"GB\": %.3f, \"inflight2\": {\"ms\": %.4f, \"GBs\": %.1f}, \"inflight4\": {\"ms\": %.4f, \"GBs\": %.1f}, "
            "\"inflight4_grid16\": {\"ms\": %.4f, \"GBs\": %.1f}}, \"random_gather_4_rows\": {\"GB\": %.3f, \"ms\": %.4f, \"GBs\": %.1f}}\n",
