@@ -75,6 +75,42 @@ __global__ void __launch_bounds__(256) rows_kernel(float4* t0, float4* t1, float
     if (acc == 12345.678f) *sink = acc;
 }
 
+// One segment in flight per group (the fused pass's depth) + prefetch.global.L2 of the rows of the group's segment DIST
+// rounds ahead: lane l pulls one 128-byte line (6 table rows + 2 item rows, two lines each).
+template <int DIST>
+__global__ void __launch_bounds__(256) rows_pf_kernel(float4* t0, float4* t1, float4* t2, float4* t3, float4* t4,
+                                                       float4* t5, const float4* __restrict__ i0,
+                                                       const float4* __restrict__ i1, float4* __restrict__ stash,
+                                                       const int32_t* __restrict__ rows,
+                                                       const int32_t* __restrict__ items, int64_t S, float* sink) {
+    float4* tabs[6] = {t0, t1, t2, t3, t4, t5};
+    const int lane = threadIdx.x & 15;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 4;
+    const int64_t ng = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    float acc = 0.f;
+    for (int64_t s = g; s < S; s += ng) {
+        const int64_t sp = s + DIST * ng;
+        if (sp < S) {
+            const int t = lane >> 1, half = lane & 1;
+            const float4* base = t < 6 ? tabs[t] : (t == 6 ? i0 : i1);
+            const int64_t rr = t < 6 ? rows[sp] : items[sp];
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(base + rr * D4 + half * 8));
+        }
+        const int64_t r = rows[s], ir = items[s];
+        float4 v[6], it0, it1;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) v[t] = tabs[t][r * D4 + lane];
+        it0 = i0[ir * D4 + lane];
+        it1 = i1[ir * D4 + lane];
+        acc += it0.x + it1.y;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) { v[t].x += 1.f; tabs[t][r * D4 + lane] = v[t]; }
+        stash[(s * 2 + 0) * D4 + lane] = v[0];
+        stash[(s * 2 + 1) * D4 + lane] = v[1];
+    }
+    if (acc == 12345.678f) *sink = acc;
+}
+
 __global__ void __launch_bounds__(256) gather_kernel(const float4* __restrict__ t0, const float4* __restrict__ t1,
                                                       const float4* __restrict__ i0, const float4* __restrict__ i1,
                                                       const int32_t* __restrict__ rows, const int32_t* __restrict__ items,
@@ -181,6 +217,24 @@ int main() {
     const float ms_r2 = timeit([&] { rows_kernel<2><<<grid, 256>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 10);
     const float ms_r4 = timeit([&] { rows_kernel<4><<<grid, 256>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 10);
     const float ms_r4b = timeit([&] { rows_kernel<4><<<148 * 16, 256>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 10);
+    // the same pattern at the FUSED KERNEL'S occupancy: 2 CTAs of 256 threads per SM (100 KB of dynamic shared memory
+    // each, unused), one wave of 296 CTAs, 1 / 2 / 4 independent segments in flight per 16-lane group
+    cudaFuncSetAttribute(rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    const float ms_o1 = timeit([&] { rows_kernel<1><<<296, 256, 100 * 1024>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 5);
+    const float ms_o2 = timeit([&] { rows_kernel<2><<<296, 256, 100 * 1024>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 5);
+    const float ms_o4 = timeit([&] { rows_kernel<4><<<296, 256, 100 * 1024>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 5);
+    printf("{\"user_pass_pattern_at_16_warps_per_sm\": {\"inflight1\": {\"ms\": %.4f, \"GBs\": %.1f}, \"inflight2\": {\"ms\": %.4f, \"GBs\": %.1f}, \"inflight4\": {\"ms\": %.4f, \"GBs\": %.1f}}}\n",
+           ms_o1, rows_gb / ms_o1 * 1e3, ms_o2, rows_gb / ms_o2 * 1e3, ms_o4, rows_gb / ms_o4 * 1e3);
+    cudaFuncSetAttribute(rows_pf_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(rows_pf_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(rows_pf_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    const float ms_p2 = timeit([&] { rows_pf_kernel<2><<<296, 256, 100 * 1024>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 5);
+    const float ms_p4 = timeit([&] { rows_pf_kernel<4><<<296, 256, 100 * 1024>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 5);
+    const float ms_p8 = timeit([&] { rows_pf_kernel<8><<<296, 256, 100 * 1024>>>(tabs[0], tabs[1], tabs[2], tabs[3], tabs[4], tabs[5], i0, i1, stash, d_rows, d_items, S, sink); }, 5);
+    printf("{\"user_pass_pattern_at_16_warps_per_sm_1_in_flight_plus_L2_prefetch\": {\"dist2\": {\"ms\": %.4f, \"GBs\": %.1f}, \"dist4\": {\"ms\": %.4f, \"GBs\": %.1f}, \"dist8\": {\"ms\": %.4f, \"GBs\": %.1f}}}\n",
+           ms_p2, rows_gb / ms_p2 * 1e3, ms_p4, rows_gb / ms_p4 * 1e3, ms_p8, rows_gb / ms_p8 * 1e3);
     const float ms_g = timeit([&] { gather_kernel<<<148 * 16, 256>>>(tabs[0], tabs[1], i0, i1, d_u, d_it, B, sink); }, 10);
     const double gather_gb = (double)B * (4 * 256 + 8) / 1e9;
     // ---- item pass pattern: item segments of the same batch, partner = user segment of each interaction ----
