@@ -481,6 +481,18 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
     for (int q = 0; q < RING - 1; ++q) produce();
 
     // ---- consumer: the same ranges, segment by segment ----
+#if INVPREF_ITEM_STAGE_OWN
+    auto request_own = [&](int64_t row_) {     // theta / m / v rows of one item row -> the six slots behind the ring
+        stage_row_async<VEC, NV>(ring, RING * 2 + 0, a.own_inv_in, row_, D, lane);
+        stage_row_async<VEC, NV>(ring, RING * 2 + 1, a.own_env_in, row_, D, lane);
+        if (EPI == EPI_ADAM) {
+            stage_row_async<VEC, NV>(ring, RING * 2 + 2, a.m_inv, row_, D, lane);
+            stage_row_async<VEC, NV>(ring, RING * 2 + 3, a.m_env, row_, D, lane);
+            stage_row_async<VEC, NV>(ring, RING * 2 + 4, a.v_inv, row_, D, lane);
+            stage_row_async<VEC, NV>(ring, RING * 2 + 5, a.v_env, row_, D, lane);
+        }
+    };
+#endif
     int rslot = 0, rgs = 0;
     int csa_n = 0, csb_n = 0;      // bounds of the consumer's next range
     if (g < NR) { csa_n = range_start[g]; csb_n = range_start[g + 1]; }
@@ -501,6 +513,11 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
                 if (c1 - c0 > HOT_CHUNKS) continue;           // reduced by a whole CTA above
             }
             Row<VEC, NV> th_i, th_e, m_i, m_e, v_i, v_e;
+#if INVPREF_ITEM_STAGE_OWN
+            // own rows: global -> shared now (slots behind the ring; each lane its own slice), read after the loop.
+            // The copies join the cp.async group of the next commit (the first produce() below).
+            request_own(row);
+#else
             load_row<VEC, NV>(th_i, a.own_inv_in, row, D, lane);
             load_row<VEC, NV>(th_e, a.own_env_in, row, D, lane);
             if (EPI == EPI_ADAM) {
@@ -509,6 +526,7 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
                 load_row<VEC, NV, true>(v_i, a.v_inv, row, D, lane);
                 load_row<VEC, NV, true>(v_e, a.v_env, row, D, lane);
             }
+#endif
             Row<VEC, NV> gi, ge;
 #pragma unroll
             for (int x = 0; x < NV * VEC; ++x) { gi.x[x] = 0.f; ge.x[x] = 0.f; }
@@ -520,6 +538,10 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
 #pragma unroll
                     for (int x = 0; x < NV * VEC; ++x) { gi.x[x] += pi.x[x]; ge.x[x] += pe.x[x]; }
                 }
+#if INVPREF_ITEM_STAGE_OWN
+                cp_async_commit();       // no produce() on this path: the own rows get a group of their own
+                cp_async_wait<0>();
+#endif
             } else {
                 for (int k = beg; k < end; ++k) {
                     produce();
@@ -529,7 +551,29 @@ __global__ void __launch_bounds__(BLOCK, 3) bwd_rows_ring_kernel(BwdSideArgs a, 
                     if (++rslot == RING) rslot = 0;
                     if (++rgs == RING + 1) rgs = 0;
                 }
+#if INVPREF_ITEM_STAGE_OWN
+                // The own rows travel in the group of the segment's FIRST produce(); len - 1 groups were committed after
+                // it.  A loop of RING or more interactions has waited for it already (wait<RING - 1> after its last
+                // produce); a shorter one allows exactly the younger groups to stay pending.
+                {
+                    const int len = end - beg;
+                    if (len == 1) cp_async_wait<0>();
+                    else if (len == 2) cp_async_wait<(RING > 1 ? 1 : 0)>();
+                    else if (len == 3) cp_async_wait<(RING > 2 ? 2 : RING - 1)>();
+                    else if (len < RING) cp_async_wait<0>();      // deeper rings (A/B builds): be conservative
+                }
+#endif
             }
+#if INVPREF_ITEM_STAGE_OWN
+            read_staged_row<VEC, NV>(th_i, ring, RING * 2 + 0, D, lane);
+            read_staged_row<VEC, NV>(th_e, ring, RING * 2 + 1, D, lane);
+            if (EPI == EPI_ADAM) {
+                read_staged_row<VEC, NV>(m_i, ring, RING * 2 + 2, D, lane);
+                read_staged_row<VEC, NV>(m_e, ring, RING * 2 + 3, D, lane);
+                read_staged_row<VEC, NV>(v_i, ring, RING * 2 + 4, D, lane);
+                read_staged_row<VEC, NV>(v_e, ring, RING * 2 + 5, D, lane);
+            }
+#endif
             finish_row<VEC, NV, EPI>(a, row, (float)(end - beg), th_i, th_e, m_i, m_e, v_i, v_e, gi, ge, lane, D);
         }
     }
@@ -776,9 +820,9 @@ static bool ring_enabled() {
     return enabled;
 }
 
-static size_t ring_smem(const Geometry& g) {
+static size_t ring_smem(const Geometry& g) {   // E, W, g-pack slots, the ring of partner rows (+ six own-row slots)
     return ((size_t)ring_align_up(((2 * g.K * g.D + 3) & ~3) + GROUPS_PER_BLOCK * (RING + 1) * 12) +
-            (size_t)RING * 2 * g.NV * g.VEC * BLOCK) * sizeof(float);
+            (size_t)(RING * 2 + (INVPREF_ITEM_STAGE_OWN ? 6 : 0)) * g.NV * g.VEC * BLOCK) * sizeof(float);
 }
 
 int launch_bwd_chunks(const Geometry& g, const BwdSideArgs& a, cudaStream_t stream) {

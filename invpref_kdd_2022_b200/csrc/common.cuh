@@ -24,6 +24,16 @@
 #ifndef INVPREF_UPASS_DEFER
 #define INVPREF_UPASS_DEFER 0
 #endif
+// Item pass (ring rows kernel): the six own rows (theta, m, v of both item tables) of a segment are copied global ->
+// shared with cp.async at the top of the segment and read after its interaction loop, instead of being
+// register-destination loads issued before the loop: ptxas attaches the scoreboard wait of such loads to the loop's
+// first branch, and ncu's source page showed 37 % of ALL warp samples of the kernel sitting on that branch.
+// Measured 1.00-1.02 -> 0.95-0.96 ms on C5 (0: the register loads).  Requesting them one segment AHEAD instead (a group
+// of their own, right after the previous segment's rows had been read out of the slots) measured the same 0.95 ms and
+// was not kept.
+#ifndef INVPREF_ITEM_STAGE_OWN
+#define INVPREF_ITEM_STAGE_OWN 1
+#endif
 #ifndef INVPREF_UPASS_L2_PREFETCH
 #define INVPREF_UPASS_L2_PREFETCH 0
 #endif
