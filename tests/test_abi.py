@@ -69,3 +69,17 @@ def test_no_cpu_fallback():
     m = InvPrefExplicit(5, 6, 2, 8)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64), torch.zeros(3, dtype=torch.int64), 1.0)
+
+
+def test_shipped_library_contains_no_cub_or_thrust_kernels():
+    """The sort-segment plan is built by the library's own radix sort and prefix sums (csrc/sort.cuh): the device
+    code of the shipped .so holds the psort:: kernels and no CUB / Thrust instantiation (round 1 called
+    cub::DeviceRadixSort / DeviceScan there)."""
+    from invpref_kdd_2022_b200 import _lib
+    _lib.load()
+    path = os.environ.get("INVPREF_LIB") or os.path.join(ROOT, "invpref_kdd_2022_b200", "libinvpref_b200.so")
+    blob = open(path, "rb").read()
+    for needle in (b"DeviceRadixSort", b"DeviceScan", b"thrust", b"cub17", b"3cub"):
+        assert needle not in blob, needle
+    for needle in (b"rs_scatter_kernel", b"rs_hist_kernel", b"rs_offsets_kernel", b"sc_scan_kernel", b"sc_mid_kernel"):
+        assert needle in blob, needle
