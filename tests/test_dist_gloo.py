@@ -45,3 +45,17 @@ def test_routing_over_gloo(world):
     for a in range(world):
         for b in range(world):
             assert by[a]["recv"][b] == by[b]["send"][a]
+
+
+def test_replicated_chunks_partition_every_batch():
+    """Host logic of the replicated-tables trainer: the ranks' contiguous chunks of a global batch slice
+    [lo, hi) are disjoint, ordered and cover it, for any world size (empty chunks allowed)."""
+    from types import SimpleNamespace
+    from invpref_kdd_2022_b200.parallel import ReplicatedTrainer
+    for world in (1, 2, 3, 4, 8):
+        for lo, hi in ((0, 0), (0, 1), (5, 12), (0, 262144), (262144, 311704), (7, 7 + world - 1)):
+            cuts = [ReplicatedTrainer.chunk(SimpleNamespace(rank=r, world=world), lo, hi) for r in range(world)]
+            assert cuts[0][0] == lo and cuts[-1][1] == hi
+            for (a0, a1), (b0, b1) in zip(cuts[:-1], cuts[1:]):
+                assert a0 <= a1 == b0 <= b1
+            assert sum(b - a for a, b in cuts) == hi - lo
